@@ -1,0 +1,384 @@
+"""TEST INFRASTRUCTURE ONLY — seeded parity cases shared by the golden generator and the tests.
+
+`make_inputs(case)` builds every input (weights, batches, injected noise / indices) from
+`np.random.RandomState(seed)` (stream stable across numpy versions and machines), so the committed fixtures
+in `tests/golden/` only need to store the REFERENCE'S OUTPUTS. `run_reference` drives the unmodified
+reference modules (container only); `run_port` drives `oracle/port.py`; the GPU tests drive the CUDA path on
+the same inputs (tests/cuda_cases.py).
+"""
+from __future__ import annotations
+
+import contextlib
+import math
+from typing import Dict, List
+
+import numpy as np
+import torch
+
+from . import port
+
+# name -> config. `full` cases are stored completely; the others as sampled entries + moments.
+CASES: Dict[str, dict] = {
+  'actor_small': dict(kind='actor', S=12, A=3, H=32, n=16, seed=11),
+  'actor_hopper': dict(kind='actor', S=12, A=3, H=256, n=256, seed=12),
+  'sac_small': dict(kind='sac', S=12, A=3, H=32, B=16, steps=2, seed=21, discount=0.97, entropy_target=-1.5, polyak=0.99, lr=3e-4, wd=0.0),
+  'sac_small_wd': dict(kind='sac', S=18, A=6, H=48, B=24, steps=3, seed=22, discount=0.99, entropy_target=-6.0, polyak=0.995, lr=1e-3, wd=0.01),
+  'sac_hopper': dict(kind='sac', S=12, A=3, H=256, B=256, steps=2, seed=23, discount=0.97, entropy_target=-1.5, polyak=0.99, lr=3e-4, wd=0.0),
+  'gail_default': dict(kind='gail', S=12, A=3, H=64, B=256, steps=2, seed=31, spectral_norm=True, grad_penalty=1.0, entropy_bonus=0.0, loss='BCE', lr=3e-5, wd=10.0, reward='AIRL'),
+  'gail_entropy_nosn': dict(kind='gail', S=18, A=6, H=32, B=64, steps=2, seed=32, spectral_norm=False, grad_penalty=0.5, entropy_bonus=0.1, loss='BCE', lr=1e-3, wd=0.1, reward='GAIL'),
+  'gail_pugail': dict(kind='gail', S=12, A=3, H=64, B=64, steps=2, seed=33, spectral_norm=True, grad_penalty=1.0, entropy_bonus=0.0, loss='PUGAIL', lr=1e-3, wd=0.0, reward='FAIRL'),
+  'gail_mixup': dict(kind='gail', S=12, A=3, H=64, B=64, steps=2, seed=34, spectral_norm=True, grad_penalty=0.0, entropy_bonus=0.0, loss='Mixup', lr=1e-3, wd=0.0, reward='AIRL'),
+  'gmmil_hopper': dict(kind='gmmil', S=12, A=3, B=64, seed=41),
+  'gmmil_halfcheetah': dict(kind='gmmil', S=18, A=6, B=256, seed=42),
+  'pwil_small': dict(kind='pwil', S=12, A=3, N=150, T=40, steps=100, seed=51),
+  'replay_ring': dict(kind='replay', S=12, A=3, size=37, appends=90, B=32, seed=61),
+}
+
+
+def _rs(seed): return np.random.RandomState(seed)
+
+
+def _mlp_weights(rs, sizes, scale=1.0) -> List[np.ndarray]:
+  out = []
+  for i in range(len(sizes) - 1):
+    out.append((rs.standard_normal((sizes[i + 1], sizes[i])) * scale / math.sqrt(sizes[i])).astype(np.float32))
+    out.append((rs.standard_normal(sizes[i + 1]) * 0.1).astype(np.float32))
+  return out
+
+
+def _batch(rs, B, S, A, absorbing_frac=0.1) -> Dict[str, np.ndarray]:
+  f = lambda *s: rs.standard_normal(s).astype(np.float32)
+  states, next_states = f(B, S), f(B, S)
+  absb = (rs.uniform(size=B) < absorbing_frac).astype(np.float32)
+  states[:, -1] = absb
+  states[absb == 1, :-1] = 0
+  next_states[:, -1] = (rs.uniform(size=B) < absorbing_frac).astype(np.float32)
+  actions = np.tanh(f(B, A))
+  actions[absb == 1] = 0
+  return dict(step=np.arange(1, B + 1, dtype=np.float32), states=states, actions=actions.astype(np.float32), rewards=f(B), next_states=next_states,
+              terminals=(rs.uniform(size=B) < 0.1).astype(np.float32), timeouts=np.zeros(B, np.float32),
+              weights=np.where(rs.uniform(size=B) < 0.2, 0.5, 1.0).astype(np.float32), absorbing=absb)
+
+
+def make_inputs(name: str) -> Dict[str, np.ndarray]:
+  c = CASES[name]
+  rs = _rs(c['seed'])
+  inp: Dict[str, np.ndarray] = {}
+  k = c['kind']
+  if k == 'actor':
+    for i, w in enumerate(_mlp_weights(rs, [c['S'], c['H'], c['H'], 2 * c['A']])): inp[f'actor_{i}'] = w
+    inp['states'] = rs.standard_normal((c['n'], c['S'])).astype(np.float32)
+    inp['eps'] = rs.standard_normal((c['n'], c['A'])).astype(np.float32)
+    inp['actions'] = np.clip(np.tanh(rs.standard_normal((c['n'], c['A'])) * 2), -1, 1).astype(np.float32)
+    inp['actions'][0, 0] = 1.0  # exercises the clamp at models.py:98
+  elif k == 'sac':
+    S, A, H = c['S'], c['A'], c['H']
+    for i, w in enumerate(_mlp_weights(rs, [S, H, H, 2 * A])): inp[f'actor_{i}'] = w
+    for t in (1, 2):
+      for i, w in enumerate(_mlp_weights(rs, [S + A, H, H, 1])): inp[f'critic{t}_{i}'] = w
+      for i, w in enumerate(_mlp_weights(rs, [S + A, H, H, 1])): inp[f'target{t}_{i}'] = w
+    inp['log_alpha'] = np.float32([-0.3])
+    for s in range(c['steps']):
+      for key, v in _batch(rs, c['B'], S, A).items(): inp[f'b{s}_{key}'] = v
+      inp[f'b{s}_eps_next'] = rs.standard_normal((c['B'], A)).astype(np.float32)
+      inp[f'b{s}_eps_new'] = rs.standard_normal((c['B'], A)).astype(np.float32)
+  elif k == 'gail':
+    S, A, H = c['S'], c['A'], c['H']
+    for i, w in enumerate(_mlp_weights(rs, [S + A, H, 1], scale=1.5)): inp[f'g_{i}'] = w
+    for s in range(c['steps']):
+      for key, v in _batch(rs, c['B'], S, A).items(): inp[f'p{s}_{key}'] = v
+      for key, v in _batch(rs, c['B'], S, A).items(): inp[f'e{s}_{key}'] = v
+      inp[f's{s}_eps_gp'] = rs.uniform(size=c['B']).astype(np.float32)
+      inp[f's{s}_eps_mix'] = rs.beta(1.0, 1.0, size=c['B']).astype(np.float32)
+    if c['spectral_norm']:
+      for l, (h, w) in enumerate(((H, S + A), (1, H))):
+        inp[f'u_{l}'] = rs.standard_normal(h).astype(np.float32)
+        inp[f'v_{l}'] = rs.standard_normal(w).astype(np.float32)
+  elif k == 'gmmil':
+    for pre in ('p', 'e'):
+      for key, v in _batch(rs, c['B'], c['S'], c['A']).items(): inp[f'{pre}_{key}'] = v
+    for key, v in _batch(rs, c['B'], c['S'], c['A']).items(): inp[f'p2_{key}'] = v  # second call (frozen bandwidths)
+  elif k == 'pwil':
+    inp['expert_states'] = rs.standard_normal((c['N'], c['S'])).astype(np.float32)
+    inp['expert_states'][:, -1] = 0  # constant feature -> scale 1 (models.py:207)
+    inp['expert_actions'] = np.tanh(rs.standard_normal((c['N'], c['A']))).astype(np.float32)
+    inp['states'] = rs.standard_normal((c['steps'], c['S'])).astype(np.float32)
+    inp['states'][:, -1] = 0
+    inp['actions'] = np.tanh(rs.standard_normal((c['steps'], c['A']))).astype(np.float32)
+  elif k == 'replay':
+    n = c['appends']
+    inp['states'] = rs.standard_normal((n, c['S'])).astype(np.float32)
+    inp['states'][:, -1] = 0
+    inp['next_states'] = rs.standard_normal((n, c['S'])).astype(np.float32)
+    inp['next_states'][:, -1] = 0
+    inp['actions'] = rs.standard_normal((n, c['A'])).astype(np.float32)
+    inp['rewards'] = rs.standard_normal(n).astype(np.float32)
+    inp['event'] = rs.choice(3, size=n, p=[0.85, 0.1, 0.05]).astype(np.int64)  # 0 none, 1 early terminal (+wrap), 2 timeout
+  return inp
+
+
+def _t(x): return torch.from_numpy(np.ascontiguousarray(x))
+
+
+def _np(x): return x.detach().cpu().numpy().copy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Running the oracle PORT
+# ----------------------------------------------------------------------------------------------------------
+def _batch_from(inp, prefix) -> Dict[str, torch.Tensor]:
+  return {key[len(prefix):]: _t(v) for key, v in inp.items() if key.startswith(prefix) and not key[len(prefix):].startswith('eps')}
+
+
+def run_port(name: str, inp: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+  c = CASES[name]
+  k = c['kind']
+  out: Dict[str, np.ndarray] = {}
+  if k == 'actor':
+    actor = [_t(inp[f'actor_{i}']) for i in range(6)]
+    s = _t(inp['states'])
+    mean, log_std = port.actor_mean_logstd(actor, s)
+    a, lp = port.actor_sample(actor, s, _t(inp['eps']))
+    out.update(mean=_np(mean), log_std=_np(log_std), action=_np(a), log_prob_sample=_np(lp), greedy=_np(port.actor_greedy_action(actor, s)),
+               log_prob_action=_np(port.actor_log_prob(actor, s, _t(inp['actions']))))
+  elif k == 'sac':
+    agent = port.SacAgent([_t(inp[f'actor_{i}']) for i in range(6)], [[_t(inp[f'critic{t}_{i}']) for i in range(6)] for t in (1, 2)], lr=c['lr'], weight_decay=c['wd'],
+                          log_alpha=float(inp['log_alpha'][0]), target=[[_t(inp[f'target{t}_{i}']) for i in range(6)] for t in (1, 2)])
+    for s in range(c['steps']):
+      r = port.sac_update(agent, _batch_from(inp, f'b{s}_'), _t(inp[f'b{s}_eps_next']), _t(inp[f'b{s}_eps_new']), c['discount'], c['entropy_target'], c['polyak'])
+      for key in ('log_probs', 'q_values', 'value_loss', 'policy_loss', 'temperature_loss', 'target_values'): out[f's{s}_{key}'] = _np(r[key])
+    for i, p in enumerate(agent.actor): out[f'actor_{i}'] = _np(p)
+    for t in (0, 1):
+      for i, p in enumerate(agent.twin[t]): out[f'critic{t + 1}_{i}'] = _np(p)
+      for i, p in enumerate(agent.target[t]): out[f'target{t + 1}_{i}'] = _np(p)
+    out['log_alpha'] = _np(agent.log_alpha)
+    for which in ('actor', 'critic', 'alpha'):
+      m, v = agent.adam_state(which)
+      for i, (mi, vi) in enumerate(zip(m, v)): out[f'adam_{which}_m_{i}'], out[f'adam_{which}_v_{i}'] = _np(mi), _np(vi)
+  elif k == 'gail':
+    g = [_t(inp[f'g_{i}']) for i in range(4)]
+    sn = [(port._l2_normalise(_t(inp[f'u_{l}'])), port._l2_normalise(_t(inp[f'v_{l}']))) for l in range(2)] if c['spectral_norm'] else None
+    disc = port.GailDiscriminator(g, sn, discount=0.97, reward_function=c['reward'])
+    opt = torch.optim.AdamW(disc.parameters(), lr=c['lr'], weight_decay=c['wd'])
+    for s in range(c['steps']):
+      pol, exp = _batch_from(inp, f'p{s}_'), _batch_from(inp, f'e{s}_')
+      r = port.gail_update(disc, opt, pol, exp, _t(inp[f's{s}_eps_gp']), loss_function=c['loss'], grad_penalty=c['grad_penalty'], entropy_bonus=c['entropy_bonus'],
+                           eps_mixup=_t(inp[f's{s}_eps_mix']))
+      with torch.no_grad():
+        out[f's{s}_reward'] = _np(disc.predict_reward(pol['states'], pol['actions']))
+        out[f's{s}_logits'] = _np(disc.forward(pol['states'], pol['actions']))
+    for i, p in enumerate(disc.g):
+      out[f'g_{i}'] = _np(p)
+      out[f'adam_m_{i}'], out[f'adam_v_{i}'] = _np(opt.state[p]['exp_avg']), _np(opt.state[p]['exp_avg_sq'])
+    if sn is not None:
+      for l, (u, v) in enumerate(disc.g_sn): out[f'u_{l}'], out[f'v_{l}'] = _np(u), _np(v)
+  elif k == 'gmmil':
+    d = port.GmmilDiscriminator()
+    p, e, p2 = _batch_from(inp, 'p_'), _batch_from(inp, 'e_'), _batch_from(inp, 'p2_')
+    out['reward_1'] = _np(d.predict_reward(p['states'], p['actions'], e['states'], e['actions'], p['weights'], e['weights']))
+    out['gammas'] = np.float32([d.gamma_1, d.gamma_2])
+    out['reward_2'] = _np(d.predict_reward(p2['states'], p2['actions'], e['states'], e['actions'], p2['weights'], e['weights']))
+  elif k == 'pwil':
+    d = port.PwilDiscriminator(_t(inp['expert_states']), _t(inp['expert_actions']), c['T'])
+    rewards = []
+    for i in range(c['steps']):
+      rewards.append(d.compute_reward(_t(inp['states'][i:i + 1]), _t(inp['actions'][i:i + 1])))
+      if (i + 1) % c['T'] == 0: d.reset()
+    out['rewards'] = np.float32(rewards)
+  elif k == 'replay':
+    mem = port.Replay(c['size'], c['S'], c['A'], absorbing=True)
+    _drive_replay(mem, inp, c)
+    np.random.seed(c['seed'])
+    t = mem.sample(c['B'])
+    for key, v in t.items(): out[f'sample_{key}'] = _np(v)
+    for key in port.FIELDS: out[f'mem_{key}'] = _np(mem.data[key])
+    out['meta'] = np.int64([mem.idx, int(mem.full), mem.num_trajectories])
+  return out
+
+
+def _drive_replay(mem, inp, c):
+  """train.py:157-163 append / wrap schedule driven by the seeded `event` stream."""
+  for i in range(c['appends']):
+    ev = int(inp['event'][i])
+    mem.append(i + 1, _t(inp['states'][i]), _t(inp['actions'][i]), float(inp['rewards'][i]), _t(inp['next_states'][i]), ev == 1, ev == 2)
+    if ev == 1: mem.wrap_for_absorbing_states()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Running the unmodified REFERENCE (container only)
+# ----------------------------------------------------------------------------------------------------------
+@contextlib.contextmanager
+def injected_noise(normal_eps: List[torch.Tensor], uniform_eps: List[torch.Tensor], beta_eps: List[torch.Tensor]):
+  """Patches torch's samplers so the reference consumes the case's injected draws instead of its RNG:
+  Normal.sample/rsample -> loc + scale * eps (models.py:93 users), torch.rand_like (training.py:118),
+  Beta.sample (training.py:106). The reference source is untouched."""
+  from torch.distributions import Normal, Beta
+  saved = (Normal.sample, Normal.rsample, torch.rand_like, Beta.sample)
+  def _sample(self, sample_shape=torch.Size()):
+    with torch.no_grad(): return self.loc + self.scale * normal_eps.pop(0)
+  def _rsample(self, sample_shape=torch.Size()): return self.loc + normal_eps.pop(0) * self.scale
+  Normal.sample, Normal.rsample = _sample, _rsample
+  torch.rand_like = lambda x, **kw: uniform_eps.pop(0)
+  Beta.sample = lambda self, sample_shape=torch.Size(): beta_eps.pop(0)
+  try:
+    yield
+  finally:
+    Normal.sample, Normal.rsample, torch.rand_like, Beta.sample = saved
+
+
+def _load_mlp(seq, weights):
+  linears = [m for m in seq if isinstance(m, torch.nn.Linear)]
+  with torch.no_grad():
+    for l, lin in enumerate(linears):
+      lin.weight.copy_(_t(weights[2 * l]))
+      lin.bias.copy_(_t(weights[2 * l + 1]))
+
+
+def run_reference(name: str, inp: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+  from . import refstub
+  ref = refstub.load()
+  DC = ref.DictConfig
+  c = CASES[name]
+  k = c['kind']
+  out: Dict[str, np.ndarray] = {}
+  model_cfg = lambda H: DC(hidden_size=H, depth=2, activation='relu')
+  if k == 'actor':
+    actor = ref.models.SoftActor(c['S'], c['A'], model_cfg(c['H']))
+    _load_mlp(actor.actor, [inp[f'actor_{i}'] for i in range(6)])
+    s = _t(inp['states'])
+    with torch.no_grad(), injected_noise([_t(inp['eps'])], [], []):
+      pol = actor(s)
+      a = pol.sample()
+      out.update(mean=_np(pol.base_dist.mean), log_std=_np(pol.base_dist.stddev.log()), action=_np(a), log_prob_sample=_np(pol.log_prob(a)),
+                 greedy=_np(actor.get_greedy_action(s)), log_prob_action=_np(actor.log_prob(s, _t(inp['actions']))))
+  elif k == 'sac':
+    S, A, H = c['S'], c['A'], c['H']
+    actor, critic = ref.models.SoftActor(S, A, model_cfg(H)), ref.models.TwinCritic(S, A, model_cfg(H))
+    _load_mlp(actor.actor, [inp[f'actor_{i}'] for i in range(6)])
+    _load_mlp(critic.critic_1.critic, [inp[f'critic1_{i}'] for i in range(6)])
+    _load_mlp(critic.critic_2.critic, [inp[f'critic2_{i}'] for i in range(6)])
+    target = ref.models.create_target_network(critic)
+    _load_mlp(target.critic_1.critic, [inp[f'target1_{i}'] for i in range(6)])
+    _load_mlp(target.critic_2.critic, [inp[f'target2_{i}'] for i in range(6)])
+    log_alpha = torch.tensor(inp['log_alpha'].copy(), requires_grad=True)
+    oa = torch.optim.AdamW(actor.parameters(), lr=c['lr'], weight_decay=c['wd'])
+    oc = torch.optim.AdamW(critic.parameters(), lr=c['lr'], weight_decay=c['wd'])
+    ot = torch.optim.Adam([log_alpha], lr=c['lr'])
+    for s in range(c['steps']):
+      batch = _batch_from(inp, f'b{s}_')
+      with injected_noise([_t(inp[f'b{s}_eps_next']), _t(inp[f'b{s}_eps_new'])], [], []):
+        lp, q = ref.training.sac_update(actor, critic, log_alpha, target, batch, oa, oc, ot, c['discount'], c['entropy_target'], c['polyak'])
+      out[f's{s}_log_probs'], out[f's{s}_q_values'] = _np(lp), _np(q)
+    for i, p in enumerate(actor.parameters()): out[f'actor_{i}'] = _np(p)
+    for t, net in ((1, critic.critic_1), (2, critic.critic_2)):
+      for i, p in enumerate(net.parameters()): out[f'critic{t}_{i}'] = _np(p)
+    for t, net in ((1, target.critic_1), (2, target.critic_2)):
+      for i, p in enumerate(net.parameters()): out[f'target{t}_{i}'] = _np(p)
+    out['log_alpha'] = _np(log_alpha)
+    for which, opt, params in (('actor', oa, list(actor.parameters())), ('critic', oc, list(critic.parameters())), ('alpha', ot, [log_alpha])):
+      for i, p in enumerate(params): out[f'adam_{which}_m_{i}'], out[f'adam_{which}_v_{i}'] = _np(opt.state[p]['exp_avg']), _np(opt.state[p]['exp_avg_sq'])
+  elif k == 'gail':
+    S, A, H = c['S'], c['A'], c['H']
+    icfg = DC(state_only=False, spectral_norm=c['spectral_norm'], loss_function=c['loss'], grad_penalty=c['grad_penalty'], mixup_alpha=1, entropy_bonus=c['entropy_bonus'],
+              pos_class_prior=0.7, nonnegative_margin=float('inf'),
+              discriminator=DC(hidden_size=H, depth=1, activation='relu', input_dropout=0.5, dropout=0.75, reward_shaping=False, subtract_log_policy=False, reward_function=c['reward']))
+    disc = ref.models.GAILDiscriminator(S, A, icfg, 0.97)
+    lins = [m for m in disc.g if isinstance(m, torch.nn.Linear)]
+    with torch.no_grad():
+      for l, lin in enumerate(lins):
+        if c['spectral_norm']:
+          lin.parametrizations.weight.original.copy_(_t(inp[f'g_{2 * l}']))
+          lin.parametrizations.weight[0]._u.copy_(port._l2_normalise(_t(inp[f'u_{l}'])))
+          lin.parametrizations.weight[0]._v.copy_(port._l2_normalise(_t(inp[f'v_{l}'])))
+        else:
+          lin.weight.copy_(_t(inp[f'g_{2 * l}']))
+        lin.bias.copy_(_t(inp[f'g_{2 * l + 1}']))
+    # parameters() order for parametrized Linear is (bias, original); collect as (weight, bias) per layer
+    plist = []
+    for lin in lins: plist += [lin.parametrizations.weight.original if c['spectral_norm'] else lin.weight, lin.bias]
+    opt = torch.optim.AdamW(disc.parameters(), lr=c['lr'], weight_decay=c['wd'])
+    disc.eval()
+    for s in range(c['steps']):
+      pol, exp = _batch_from(inp, f'p{s}_'), _batch_from(inp, f'e{s}_')
+      disc.train()
+      with injected_noise([], [_t(inp[f's{s}_eps_gp'])], [_t(inp[f's{s}_eps_mix'])]):
+        ref.training.adversarial_imitation_update(None, disc, pol, exp, opt, icfg)
+      disc.eval()
+      with torch.inference_mode():
+        out[f's{s}_reward'] = _np(disc.predict_reward(**ref.models.make_gail_input(pol['states'], pol['actions'], pol['next_states'], pol['terminals'], None, False, False)))
+        out[f's{s}_logits'] = _np(disc(pol['states'], pol['actions']))
+    for i, p in enumerate(plist):
+      out[f'g_{i}'] = _np(p)
+      out[f'adam_m_{i}'], out[f'adam_v_{i}'] = _np(opt.state[p]['exp_avg']), _np(opt.state[p]['exp_avg_sq'])
+    if c['spectral_norm']:
+      for l, lin in enumerate(lins): out[f'u_{l}'], out[f'v_{l}'] = _np(lin.parametrizations.weight[0]._u), _np(lin.parametrizations.weight[0]._v)
+  elif k == 'gmmil':
+    d = ref.models.GMMILDiscriminator(c['S'], c['A'], DC(state_only=False))
+    p, e, p2 = _batch_from(inp, 'p_'), _batch_from(inp, 'e_'), _batch_from(inp, 'p2_')
+    out['reward_1'] = _np(d.predict_reward(p['states'], p['actions'], e['states'], e['actions'], p['weights'], e['weights']))
+    out['gammas'] = np.float32([d.gamma_1, d.gamma_2])
+    out['reward_2'] = _np(d.predict_reward(p2['states'], p2['actions'], e['states'], e['actions'], p2['weights'], e['weights']))
+  elif k == 'pwil':
+    n = c['N']
+    z = torch.zeros
+    mem = ref.memory.ReplayMemory(n, c['S'], c['A'], True, transitions=dict(states=_t(inp['expert_states']), actions=_t(inp['expert_actions']), rewards=z(n), next_states=z(n, c['S']),
+                                                                            terminals=z(n), timeouts=z(n), weights=torch.ones(n), num_trajectories=1))
+    d = ref.models.PWILDiscriminator(c['S'], c['A'], DC(state_only=False, reward_scale=5, reward_bandwidth_scale=5), mem, c['T'])
+    rewards = []
+    for i in range(c['steps']):
+      rewards.append(d.compute_reward(_t(inp['states'][i:i + 1]), _t(inp['actions'][i:i + 1])))
+      if (i + 1) % c['T'] == 0: d.reset()
+    out['rewards'] = np.float32(rewards)
+  elif k == 'replay':
+    mem = ref.memory.ReplayMemory(c['size'], c['S'], c['A'], True)
+    for key in ('step', 'states', 'actions', 'rewards', 'next_states', 'terminals', 'timeouts', 'weights'): getattr(mem, key).zero_()  # torch.empty -> defined
+    _drive_replay(mem, inp, c)
+    np.random.seed(c['seed'])
+    t = mem.sample(c['B'])
+    for key, v in t.items(): out[f'sample_{key}'] = _np(v)
+    for key in port.FIELDS: out[f'mem_{key}'] = _np(getattr(mem, key))
+    out['meta'] = np.int64([mem.idx, int(mem.full), mem.num_trajectories])
+  return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Compact storage: full arrays for small outputs, sampled entries + moments for large ones
+# ----------------------------------------------------------------------------------------------------------
+SAMPLE_THRESHOLD, SAMPLES = 4096, 192
+
+
+def compress(outputs: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+  z = {}
+  for key, v in outputs.items():
+    v = np.asarray(v)
+    if v.size <= SAMPLE_THRESHOLD:
+      z[key] = v
+    else:
+      idx = _rs(v.size).choice(v.size, SAMPLES, replace=False)
+      z[key + '@idx'], z[key + '@val'] = idx.astype(np.int64), v.reshape(-1)[idx]
+      z[key + '@mom'] = np.float64([v.astype(np.float64).sum(), (v.astype(np.float64) ** 2).sum()])
+  return z
+
+
+def compare(golden: Dict[str, np.ndarray], outputs: Dict[str, np.ndarray], rtol: float, atol: float, keys=None) -> List[str]:
+  """Returns a list of mismatch descriptions (empty = parity) of `outputs` against a compressed golden."""
+  bad = []
+  names = sorted({k.split('@')[0] for k in golden.keys()})
+  for key in names:
+    if keys is not None and key not in keys: continue
+    if key not in outputs:
+      bad.append(f'{key}: missing')
+      continue
+    v = np.asarray(outputs[key])
+    if key in golden:
+      ref, got = golden[key], v
+    else:
+      ref, got = golden[key + '@val'], v.reshape(-1)[golden[key + '@idx']]
+      mom = np.float64([v.astype(np.float64).sum(), (v.astype(np.float64) ** 2).sum()])
+      if not np.allclose(mom, golden[key + '@mom'], rtol=max(rtol, 1e-4) * 10, atol=atol * v.size): bad.append(f'{key}: moments {mom} vs {golden[key + "@mom"]}')
+    if ref.shape != got.shape:
+      bad.append(f'{key}: shape {got.shape} vs {ref.shape}')
+    elif not np.allclose(got, ref, rtol=rtol, atol=atol):
+      err = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+      bad.append(f'{key}: max abs err {err.max():.3e} (ref scale {np.abs(ref).max():.3e})')
+  return bad
