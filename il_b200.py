@@ -1,0 +1,11 @@
+"""Import shim: the package directory is named `imitation-learning_b200/` (not an importable identifier), so
+`import il_b200` loads it under this name."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'imitation-learning_b200')
+_spec = importlib.util.spec_from_file_location('il_b200', os.path.join(_dir, '__init__.py'), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules['il_b200'] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,170 @@
+// Shared device/host helpers for the sm_100a hot path. Compiled only for sm_100a (see build.py).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/il_b200.h"
+
+struct il_handle {
+  int device;
+  int sm_count;
+  int gemm_mode;
+  long long launches;
+};
+
+extern thread_local char g_il_error[512];
+
+#define IL_FAIL(...)                                     \
+  do {                                                   \
+    snprintf(g_il_error, sizeof(g_il_error), __VA_ARGS__); \
+    return 1;                                            \
+  } while (0)
+
+#define IL_CHECK(cond, ...)        \
+  do {                             \
+    if (!(cond)) IL_FAIL(__VA_ARGS__); \
+  } while (0)
+
+#define IL_CUDA(expr)                                                                             \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) IL_FAIL("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// Launch + count + check (cudaPeekAtLastError is legal during stream capture).
+#define IL_LAUNCH(h, kernel, grid, block, smem, stream, ...)                                      \
+  do {                                                                                            \
+    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);                     \
+    (h)->launches++;                                                                              \
+    cudaError_t _e = cudaPeekAtLastError();                                                       \
+    if (_e != cudaSuccess) IL_FAIL("launch of %s failed: %s (%s:%d)", #kernel, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define IL_TRY(expr)          \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != 0) return _r;   \
+  } while (0)
+
+static inline int64_t il_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// ---- row layout (il_batch / il_replay) -------------------------------------------------------------------
+struct RowLayout {
+  int state, action, reward, next_state, terminal, timeout, weight, step, len;
+};
+__host__ __device__ inline RowLayout row_layout(int S, int A) {
+  RowLayout L;
+  L.state = 0;
+  L.action = S;
+  L.reward = S + A;
+  L.next_state = S + A + 1;
+  L.terminal = 2 * S + A + 1;
+  L.timeout = L.terminal + 1;
+  L.weight = L.terminal + 2;
+  L.step = L.terminal + 3;
+  L.len = (2 * S + A + 5 + 3) / 4 * 4;
+  return L;
+}
+
+// ---- MLP flat-parameter layout ---------------------------------------------------------------------------
+struct MlpOffsets {
+  int64_t w[IL_MAX_LAYERS], b[IL_MAX_LAYERS], total;
+};
+static inline MlpOffsets mlp_offsets(const int32_t* dims, int n_layers) {
+  MlpOffsets o;
+  int64_t off = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    o.w[l] = off;
+    off = il_align_up(off + (int64_t)dims[l + 1] * dims[l], 4);
+    o.b[l] = off;
+    off = il_align_up(off + dims[l + 1], 4);
+  }
+  o.total = il_align_up(off, 32);
+  return o;
+}
+
+// ---- device math -------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == IL_ACT_RELU) return fmaxf(x, 0.f);
+  if (act == IL_ACT_TANH) return tanhf(x);
+  return 1.f / (1.f + expf(-x));
+}
+// derivative of the activation expressed through its OUTPUT y
+__device__ __forceinline__ float act_grad_from_output(float y, int act) {
+  if (act == IL_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == IL_ACT_TANH) return 1.f - y * y;
+  return y * (1.f - y);
+}
+__device__ __forceinline__ float softplusf(float x) {  // torch softplus (beta 1, threshold 20)
+  return x > 20.f ? x : log1pf(expf(x));
+}
+__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Block-wide sum for blockDim.x <= 1024 (deterministic order); `red` is >= 32 floats of shared memory.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (warp == 0) {
+    r = lane < nw ? red[lane] : 0.f;
+    r = warp_sum(r);
+    if (lane == 0) red[0] = r;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+// ---- Philox4x32-10 ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u32_to_unit(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }  // [0, 1)
+
+// ---- grouped GEMM (gemm.cu) ---------------------------------------------------------------------------------
+// C[g] (M x N) = A[g] (M x K) * B[g] (K x N) with fused epilogue; all fp32.
+struct GemmArgs {
+  const float* A;        // a_kmajor: stored [M, K] (K contiguous, row stride lda); else stored [K, M] (M contiguous, row stride lda)
+  int64_t a_gs;
+  int a_gdiv, lda, a_kmajor;
+  const float* B;        // b_kmajor: stored [N, K] (K contiguous, row stride ldb)  (a Linear weight); else stored [K, N] (N contiguous)
+  int64_t b_gs;
+  int b_gdiv, ldb, b_kmajor;
+  float* C;              // [M, N], row stride ldc
+  int64_t c_gs;
+  int ldc;
+  const float* bias;     // [N] per group or nullptr
+  int64_t bias_gs;
+  int act;               // -1 none, else IL_ACT_* applied to the output
+  const float* mask;     // optional [M, N] (row stride ldmask): output *= act'(mask) with mask = activation OUTPUT
+  int64_t mask_gs;
+  int ldmask, mask_act;
+  float* colsum;         // optional (only with !a_kmajor): colsum[m] = sum_k A[k, m]  (bias gradient)
+  int64_t colsum_gs;
+  int accumulate;        // C += result (before activation; only with act == -1)
+  int M, N, K, G;
+};
+int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream);

@@ -1,0 +1,546 @@
+// GAILDiscriminator (models.py:152-180, depth-1 `g` network, optional spectral norm) — one CTA per replica.
+//   il_gail_update : adversarial_imitation_update (training.py:85-134): BCE / PUGAIL / Mixup loss, gradient
+//                    penalty (closed-form double backward for a one-hidden-layer net),
+//                    entropy bonus, spectral-norm power iterations per train-mode forward (a12) and their
+//                    backward projection, AdamW — everything in shared memory, parameters touched once.
+//   il_gail_reward : eval-mode forward + reward (models.py:177-180).
+#include "common.cuh"
+
+namespace {
+
+constexpr int THREADS = 256;
+enum PassKind { PASS_POLICY = 0, PASS_EXPERT = 1, PASS_MIX = 2 };
+
+struct GailDims {
+  int S, A, d, H, B, row, ldx, ldz, RB, HD;
+};
+
+struct GailSmem {
+  float *W1, *W1e, *G1, *b1, *w2, *w2e, *G2, *gb1, *G2k, *gb1k, *u1, *v1, *v2, *tvec, *slots, *X, *Z, *GX, *DF, *CO, *red, *scal;
+};
+
+__host__ __device__ inline int gail_slot_floats(int H, int d) { return 2 * H + d + 4; }  // u1[H] v1[d] v2[H] + sigma1 sigma2 u2 pad
+
+__host__ __device__ inline int64_t gail_carve(const GailDims& g, float* base, GailSmem* s) {
+  int64_t o = 0;
+  auto take = [&](int n) { float* p = base ? base + o : nullptr; o += (n + 3) / 4 * 4; return p; };
+  GailSmem t;
+  t.W1 = take(g.HD); t.W1e = take(g.HD); t.G1 = take(g.HD);
+  t.b1 = take(g.H); t.w2 = take(g.H); t.w2e = take(g.H); t.G2 = take(g.H); t.gb1 = take(g.H); t.G2k = take(g.H); t.gb1k = take(g.H);
+  t.u1 = take(g.H); t.v1 = take(g.d); t.v2 = take(g.H); t.tvec = take(g.H > g.d ? g.H : g.d);
+  t.slots = take(3 * gail_slot_floats(g.H, g.d));
+  t.X = take(g.RB * g.ldx); t.Z = take(g.RB * g.ldz); t.GX = take(g.RB * g.ldx); t.DF = take(g.RB); t.CO = take(g.RB);
+  t.red = take(32); t.scal = take(32);
+  if (s) *s = t;
+  return o * 4;
+}
+
+__host__ inline GailDims gail_dims(int S, int A, int H, int B, int state_only, int RB) {
+  GailDims g;
+  g.S = S; g.A = A; g.d = state_only ? S : S + A; g.H = H; g.B = B; g.row = row_layout(S, A).len;
+  g.ldx = g.d | 1; g.ldz = H | 1; g.RB = RB; g.HD = (H * g.d + 3) / 4 * 4;
+  return g;
+}
+
+struct GailUpdParams {
+  il_gail_update_args a;
+  GailDims g;
+  int64_t off_w1, off_b1, off_w2, off_b2;
+};
+struct GailRewParams {
+  il_gail disc;
+  il_batch batch;
+  GailDims g;
+  int64_t off_w1, off_b1, off_w2, off_b2;
+  float* reward; int64_t reward_rs; int reward_ld;
+  float* logits;
+};
+
+__device__ __forceinline__ float bsum(float v, float* red) { return block_sum(v, red); }
+
+// W v for a [H, d] matrix in shared memory -> out[H]
+__device__ void matvec(const float* W, const float* v, float* out, int H, int d) {
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < d; ++j) s = fmaf(W[h * d + j], v[j], s);
+    out[h] = s;
+  }
+}
+__device__ void matvec_t(const float* W, const float* u, float* out, int H, int d) {
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    float s = 0.f;
+    for (int h = 0; h < H; ++h) s = fmaf(W[h * d + j], u[h], s);
+    out[j] = s;
+  }
+}
+__device__ float sq_norm(const float* x, int n, float* red) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(x[i], x[i], s);
+  return bsum(s, red);
+}
+
+// torch _SpectralNorm: (training) u <- normalize(W v), v <- normalize(W^T u); sigma = u . (W v).
+__device__ float spectral_sigma(const float* W, float* u, float* v, float* tvec, float* red, int H, int d, bool training) {
+  if (training) {
+    matvec(W, v, tvec, H, d);
+    __syncthreads();
+    float dn = fmaxf(sqrtf(sq_norm(tvec, H, red)), 1e-12f);
+    for (int h = threadIdx.x; h < H; h += blockDim.x) u[h] = tvec[h] / dn;
+    __syncthreads();
+    matvec_t(W, u, tvec, H, d);
+    __syncthreads();
+    dn = fmaxf(sqrtf(sq_norm(tvec, d, red)), 1e-12f);
+    for (int j = threadIdx.x; j < d; j += blockDim.x) v[j] = tvec[j] / dn;
+    __syncthreads();
+  }
+  matvec(W, v, tvec, H, d);
+  __syncthreads();
+  float s = 0.f;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) s = fmaf(u[h], tvec[h], s);
+  s = bsum(s, red);
+  return s;
+}
+
+// Loads rows [b0, b0 + nb) of a pass into X (features) and CO (sample weight w); DF receives the mixing epsilon.
+__device__ void load_rows(const GailDims& g, const float* pol, const float* exp_, const float* eps, int kind, int b0, int nb, float* X, float* CO, float* DF) {
+  const RowLayout L = row_layout(g.S, g.A);
+  for (int idx = threadIdx.x; idx < nb * g.d; idx += blockDim.x) {
+    const int b = idx / g.d, j = idx % g.d;
+    const int64_t ro = (int64_t)(b0 + b) * g.row + j;  // state | action are adjacent at the row start
+    float v;
+    if (kind == PASS_POLICY) v = pol[ro];
+    else if (kind == PASS_EXPERT) v = exp_[ro];
+    else {
+      const float e = eps[b0 + b];
+      v = __fadd_rn(__fmul_rn(e, exp_[ro]), __fmul_rn(__fsub_rn(1.f, e), pol[ro]));  // training.py:81
+    }
+    X[b * g.ldx + j] = v;
+  }
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+    const int64_t wo = (int64_t)(b0 + b) * g.row + L.weight;
+    float w, e = 0.f;
+    if (kind == PASS_POLICY) w = pol[wo];
+    else if (kind == PASS_EXPERT) w = exp_[wo];
+    else {
+      e = eps[b0 + b];
+      w = __fadd_rn(__fmul_rn(e, exp_[wo]), __fmul_rn(__fsub_rn(1.f, e), pol[wo]));
+    }
+    CO[b] = w;
+    DF[b] = e;
+  }
+}
+
+// hidden = relu(W1e x + b1) into Z; logits f into FO (one warp per row).
+__device__ void forward_chunk(const GailDims& g, const GailSmem& s, int nb, float b2, float* FO) {
+  const int H = g.H, d = g.d;
+  for (int p = threadIdx.x; p < nb * H; p += blockDim.x) {
+    const int b = p % nb, h = p / nb;
+    float z = s.b1[h];
+    const float* wr = s.W1e + h * d;
+    const float* xr = s.X + b * g.ldx;
+    for (int j = 0; j < d; ++j) z = fmaf(wr[j], xr[j], z);
+    s.Z[b * g.ldz + h] = fmaxf(z, 0.f);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int b = warp; b < nb; b += nw) {
+    float f = 0.f;
+    for (int h = lane; h < H; h += 32) f = fmaf(s.w2e[h], s.Z[b * g.ldz + h], f);
+    f = warp_sum(f);
+    if (lane == 0) FO[b] = f + b2;
+  }
+  __syncthreads();
+}
+
+template <int NE>
+__global__ void __launch_bounds__(THREADS) gail_update_kernel(const GailUpdParams p) {
+  extern __shared__ __align__(16) float sm[];
+  const GailDims g = p.g;
+  GailSmem s;
+  gail_carve(g, sm, &s);
+  const il_gail_update_args& a = p.a;
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const int H = g.H, d = g.d, B = g.B;
+  float* prm = a.disc.g.params + (int64_t)r * a.disc.g.stride;
+  const bool sn = a.disc.u != nullptr;
+  const float* pol = a.policy.rows + (int64_t)r * a.policy.replica_stride;
+  const float* exp_ = a.expert.rows + (int64_t)r * a.expert.replica_stride;
+  const float* eps_gp = a.eps_gp ? a.eps_gp + (int64_t)r * B : nullptr;
+  const float* eps_mix = a.eps_mix ? a.eps_mix + (int64_t)r * B : nullptr;
+  const float invB = 1.f / (float)B;
+
+  // ---- load parameters / buffers -------------------------------------------------------------------------
+  for (int i = tid; i < H * d; i += THREADS) { s.W1[i] = prm[p.off_w1 + i]; s.G1[i] = 0.f; }
+  for (int h = tid; h < H; h += THREADS) {
+    s.b1[h] = prm[p.off_b1 + h]; s.w2[h] = prm[p.off_w2 + h]; s.G2[h] = 0.f; s.gb1[h] = 0.f;
+    if (sn) { s.u1[h] = a.disc.u[(int64_t)r * a.disc.u_stride + h]; s.v2[h] = a.disc.v[(int64_t)r * a.disc.v_stride + d + h]; }
+  }
+  if (sn) for (int j = tid; j < d; j += THREADS) s.v1[j] = a.disc.v[(int64_t)r * a.disc.v_stride + j];
+  const float b2 = prm[p.off_b2];
+  float u2 = sn ? a.disc.u[(int64_t)r * a.disc.u_stride + H] : 1.f;
+  __syncthreads();
+
+  // ---- pass schedule (training.py:94-127): [policy, expert] or [mixup], then the gradient-penalty mix -----
+  int kinds[3], n_pass = 0;
+  const float* pass_eps[3] = {nullptr, nullptr, nullptr};
+  int gp_pass = -1;
+  if (a.loss_function == IL_LOSS_MIXUP) { kinds[n_pass] = PASS_MIX; pass_eps[n_pass++] = eps_mix; }
+  else { kinds[n_pass++] = PASS_POLICY; kinds[n_pass++] = PASS_EXPERT; }
+  if (a.grad_penalty > 0.f) { gp_pass = n_pass; kinds[n_pass] = PASS_MIX; pass_eps[n_pass++] = eps_gp; }
+
+  // ---- phase 1: one power iteration per layer per train-mode forward; remember (u, v, sigma) of each ------
+  const int SF = gail_slot_floats(H, d);
+  for (int k = 0; k < n_pass; ++k) {
+    float* slot = s.slots + k * SF;
+    float sig1 = 1.f, sig2 = 1.f;
+    if (sn) {
+      sig1 = spectral_sigma(s.W1, s.u1, s.v1, s.tvec, s.red, H, d, a.training != 0);
+      // layer 2 is a [1, H] matrix: u2 scalar, v2 [H]
+      float t = 0.f;
+      if (a.training) {
+        for (int h = tid; h < H; h += THREADS) t = fmaf(s.w2[h], s.v2[h], t);
+        t = bsum(t, s.red);
+        u2 = t / fmaxf(fabsf(t), 1e-12f);
+        for (int h = tid; h < H; h += THREADS) s.tvec[h] = s.w2[h] * u2;
+        __syncthreads();
+        const float dn = fmaxf(sqrtf(sq_norm(s.tvec, H, s.red)), 1e-12f);
+        for (int h = tid; h < H; h += THREADS) s.v2[h] = s.tvec[h] / dn;
+        __syncthreads();
+      }
+      t = 0.f;
+      for (int h = tid; h < H; h += THREADS) t = fmaf(s.w2[h], s.v2[h], t);
+      sig2 = u2 * bsum(t, s.red);
+    }
+    for (int h = tid; h < H; h += THREADS) { slot[h] = s.u1[h]; slot[H + d + h] = s.v2[h]; }
+    for (int j = tid; j < d; j += THREADS) slot[H + j] = s.v1[j];
+    if (tid == 0) { slot[2 * H + d] = sig1; slot[2 * H + d + 1] = sig2; slot[2 * H + d + 2] = u2; }
+    __syncthreads();
+  }
+
+  // ---- phase 2 (PUGAIL only): the clamp of training.py:102 needs the batch scalar before any gradient ------
+  float pu_gate = 1.f;
+  float loss_bce = 0.f, loss_gp = 0.f;
+  if (a.loss_function == IL_LOSS_PUGAIL) {
+    float sums[2] = {0.f, 0.f};  // sum w_p softplus(f_p), sum w_e softplus(f_e)
+    for (int k = 0; k < 2; ++k) {
+      const float* slot = s.slots + k * SF;
+      const float sig1 = slot[2 * H + d], sig2 = slot[2 * H + d + 1];
+      for (int i = tid; i < H * d; i += THREADS) s.W1e[i] = s.W1[i] / sig1;
+      for (int h = tid; h < H; h += THREADS) s.w2e[h] = s.w2[h] / sig2;
+      __syncthreads();
+      float part = 0.f;
+      for (int b0 = 0; b0 < B; b0 += g.RB) {
+        const int nb = min(g.RB, B - b0);
+        load_rows(g, pol, exp_, nullptr, kinds[k], b0, nb, s.X, s.CO, s.DF);
+        __syncthreads();
+        forward_chunk(g, s, nb, b2, s.DF);
+        for (int b = tid; b < nb; b += THREADS) part += s.CO[b] * softplusf(s.DF[b]);
+        __syncthreads();
+      }
+      sums[k] = bsum(part, s.red);
+    }
+    const float inner = a.pos_class_prior * (sums[1] * invB) - sums[0] * invB;
+    pu_gate = inner >= -a.nonnegative_margin ? 1.f : 0.f;  // torch.clamp(min=) passes gradient where x >= min
+  }
+
+  // ---- phase 3: forward + backward per pass, projected through that pass's spectral norm --------------------
+  float g1k[NE];
+  float gb2 = 0.f;
+  for (int k = 0; k < n_pass; ++k) {
+    const float* slot = s.slots + k * SF;
+    const float sig1 = slot[2 * H + d], sig2 = slot[2 * H + d + 1], u2k = slot[2 * H + d + 2];
+    const int kind = kinds[k];
+    const bool is_gp = (k == gp_pass);
+    for (int i = tid; i < H * d; i += THREADS) s.W1e[i] = s.W1[i] / sig1;
+    for (int h = tid; h < H; h += THREADS) { s.w2e[h] = s.w2[h] / sig2; s.G2k[h] = 0.f; s.gb1k[h] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < NE; ++i) g1k[i] = 0.f;
+    float gb2k = 0.f, loss_part = 0.f;
+    __syncthreads();
+    for (int b0 = 0; b0 < B; b0 += g.RB) {
+      const int nb = min(g.RB, B - b0);
+      load_rows(g, pol, exp_, pass_eps[k], kind, b0, nb, s.X, s.CO, s.DF);
+      __syncthreads();
+      if (!is_gp) {
+        // DF holds eps (mixup) on entry; forward writes logits into GX[0..nb) scratch first
+        forward_chunk(g, s, nb, b2, s.GX);
+        for (int b = tid; b < nb; b += THREADS) {
+          const float f = s.GX[b], w = s.CO[b], sg = sigmoidf(f);
+          float df;
+          if (a.loss_function == IL_LOSS_MIXUP) {  // training.py:112
+            const float e = s.DF[b];
+            df = w * (sg - e) * invB;
+            loss_part += e * w * softplusf(-f) + (1.f - e) * w * softplusf(f);
+          } else if (a.loss_function == IL_LOSS_BCE) {  // training.py:98-99
+            df = kind == PASS_EXPERT ? w * (sg - 1.f) * invB : w * sg * invB;
+            loss_part += kind == PASS_EXPERT ? w * softplusf(-f) : w * softplusf(f);
+          } else {  // PUGAIL, training.py:101-102
+            const float pr = a.pos_class_prior;
+            df = kind == PASS_EXPERT ? pr * w * (sg - 1.f) * invB + pu_gate * pr * w * sg * invB : -pu_gate * w * sg * invB;
+            loss_part += kind == PASS_EXPERT ? pr * w * softplusf(-f) + pu_gate * pr * w * softplusf(f) : -pu_gate * w * softplusf(f);
+          }
+          if (a.entropy_bonus > 0.f) df += a.entropy_bonus * w * f * sg * (1.f - sg) * invB;  // training.py:130-132
+          s.DF[b] = df;
+          gb2k += df;
+        }
+        __syncthreads();
+        // dL/dw2e[h] += sum_b df_b hidden[b,h];  dz[b,h] = df_b w2e[h] 1[hidden>0] (in place);  dL/db1[h] += sum_b dz[b,h]
+        for (int h = tid; h < H; h += THREADS) {
+          float acc2 = 0.f, accb = 0.f;
+          const float w2h = s.w2e[h];
+          for (int b = 0; b < nb; ++b) {
+            const float hv = s.Z[b * g.ldz + h], df = s.DF[b];
+            acc2 = fmaf(df, hv, acc2);
+            const float dz = hv > 0.f ? df * w2h : 0.f;
+            s.Z[b * g.ldz + h] = dz;
+            accb += dz;
+          }
+          s.G2k[h] += acc2;
+          s.gb1k[h] += accb;
+        }
+        __syncthreads();
+        // dL/dW1e[h, j] += sum_b dz[b,h] x[b,j]
+#pragma unroll
+        for (int i = 0; i < NE; ++i) {
+          const int e = tid + i * THREADS;
+          if (e < H * d) {
+            const int h = e / d, j = e % d;
+            float acc = g1k[i];
+            for (int b = 0; b < nb; ++b) acc = fmaf(s.Z[b * g.ldz + h], s.X[b * g.ldx + j], acc);
+            g1k[i] = acc;
+          }
+        }
+        __syncthreads();
+      } else {
+        // gradient penalty (training.py:117-127): g_x = W1e^T (m . w2e); loss = mean(lambda w_m |g_x|^2)
+        forward_chunk(g, s, nb, b2, s.DF);  // Z = hidden (mask source); logits unused
+        for (int q = tid; q < nb * d; q += THREADS) {
+          const int b = q / d, j = q % d;
+          float acc = 0.f;
+          for (int h = 0; h < H; ++h) acc = fmaf(s.Z[b * g.ldz + h] > 0.f ? s.w2e[h] : 0.f, s.W1e[h * d + j], acc);
+          s.GX[b * g.ldx + j] = acc;
+        }
+        __syncthreads();
+        for (int b = tid; b < nb; b += THREADS) {
+          float pen = 0.f;
+          for (int j = 0; j < d; ++j) pen = fmaf(s.GX[b * g.ldx + j], s.GX[b * g.ldx + j], pen);
+          const float wm = s.CO[b];
+          loss_part += a.grad_penalty * wm * pen;
+          s.DF[b] = 2.f * a.grad_penalty * wm * invB;  // coef_b
+        }
+        __syncthreads();
+        // dL/dw2e[h] += sum_b coef_b m[b,h] (W1e g_b)[h]
+        for (int h = tid; h < H; h += THREADS) {
+          float acc2 = 0.f;
+          const float* wr = s.W1e + h * d;
+          for (int b = 0; b < nb; ++b) {
+            if (s.Z[b * g.ldz + h] > 0.f) {
+              float t = 0.f;
+              for (int j = 0; j < d; ++j) t = fmaf(wr[j], s.GX[b * g.ldx + j], t);
+              acc2 = fmaf(s.DF[b], t, acc2);
+            }
+          }
+          s.G2k[h] += acc2;
+        }
+        // dL/dW1e[h, j] += sum_b coef_b (m[b,h] w2e[h]) g_b[j]
+#pragma unroll
+        for (int i = 0; i < NE; ++i) {
+          const int e = tid + i * THREADS;
+          if (e < H * d) {
+            const int h = e / d, j = e % d;
+            const float w2h = s.w2e[h];
+            float acc = g1k[i];
+            for (int b = 0; b < nb; ++b) acc = fmaf(s.Z[b * g.ldz + h] > 0.f ? s.DF[b] * w2h : 0.f, s.GX[b * g.ldx + j], acc);
+            g1k[i] = acc;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // ---- spectral-norm backward: dL/dW = (G - <G, W_eff> u v^T) / sigma, accumulate over passes
+    float inner1 = 0.f, inner2 = 0.f;
+    if (sn) {
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
+        const int e = tid + i * THREADS;
+        if (e < H * d) inner1 = fmaf(g1k[i], s.W1e[e], inner1);
+      }
+      inner1 = bsum(inner1, s.red);
+      for (int h = tid; h < H; h += THREADS) inner2 = fmaf(s.G2k[h], s.w2e[h], inner2);
+      inner2 = bsum(inner2, s.red);
+    }
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      const int e = tid + i * THREADS;
+      if (e < H * d) {
+        const int h = e / d, j = e % d;
+        s.G1[e] += sn ? (g1k[i] - inner1 * slot[h] * slot[H + j]) / sig1 : g1k[i];
+      }
+    }
+    for (int h = tid; h < H; h += THREADS) {
+      s.G2[h] += sn ? (s.G2k[h] - inner2 * u2k * slot[H + d + h]) / sig2 : s.G2k[h];
+      s.gb1[h] += s.gb1k[h];
+    }
+    gb2k = bsum(gb2k, s.red);
+    gb2 += gb2k;
+    loss_part = bsum(loss_part, s.red);
+    if (is_gp) loss_gp = loss_part * invB; else loss_bce += loss_part * invB;
+    __syncthreads();
+  }
+  if (tid == 0 && a.out_losses) { a.out_losses[r * 2 + 0] = loss_bce; a.out_losses[r * 2 + 1] = loss_gp; }
+
+  // ---- AdamW (train.py:84; torch _single_tensor_adam) -----------------------------------------------------------
+  if (tid == 0) {
+    const double t = (double)*a.opt.step;
+    s.scal[0] = (float)(a.opt.lr / (1.0 - pow(a.opt.beta1, t)));
+    s.scal[1] = (float)sqrt(1.0 - pow(a.opt.beta2, t));
+  }
+  __syncthreads();
+  const float step_size = s.scal[0], bc2_sqrt = s.scal[1];
+  const float decay = (float)(1.0 - a.opt.lr * a.opt.weight_decay), w1 = (float)(1.0 - a.opt.beta1), w2c = (float)(1.0 - a.opt.beta2), beta2 = (float)a.opt.beta2,
+              eps = (float)a.opt.eps;
+  const bool has_wd = a.opt.weight_decay != 0.0;
+  float* am = a.opt.m + (int64_t)r * a.disc.g.stride;
+  float* avv = a.opt.v + (int64_t)r * a.disc.g.stride;
+  auto adam = [&](int64_t off, float grad) {
+    float pi = prm[off], mi = am[off], vi = avv[off];
+    if (has_wd) pi = __fmul_rn(pi, decay);
+    mi = __fadd_rn(mi, __fmul_rn(w1, __fsub_rn(grad, mi)));
+    vi = __fadd_rn(__fmul_rn(vi, beta2), __fmul_rn(__fmul_rn(w2c, grad), grad));
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);
+    pi = __fadd_rn(pi, __fmul_rn(-step_size, __fdiv_rn(mi, denom)));
+    prm[off] = pi; am[off] = mi; avv[off] = vi;
+  };
+  for (int i = tid; i < H * d; i += THREADS) adam(p.off_w1 + i, s.G1[i]);
+  for (int h = tid; h < H; h += THREADS) { adam(p.off_b1 + h, s.gb1[h]); adam(p.off_w2 + h, s.G2[h]); }
+  if (tid == 0) adam(p.off_b2, gb2);
+  if (sn) {  // persist the power-iteration state (in-place buffers of the parametrization)
+    for (int h = tid; h < H; h += THREADS) { a.disc.u[(int64_t)r * a.disc.u_stride + h] = s.u1[h]; a.disc.v[(int64_t)r * a.disc.v_stride + d + h] = s.v2[h]; }
+    for (int j = tid; j < d; j += THREADS) a.disc.v[(int64_t)r * a.disc.v_stride + j] = s.v1[j];
+    if (tid == 0) a.disc.u[(int64_t)r * a.disc.u_stride + H] = u2;
+  }
+}
+
+__global__ void __launch_bounds__(THREADS) gail_reward_kernel(const GailRewParams p) {
+  extern __shared__ __align__(16) float sm[];
+  const GailDims g = p.g;
+  GailSmem s;
+  gail_carve(g, sm, &s);
+  const int r = blockIdx.x, tid = threadIdx.x, H = g.H, d = g.d, B = g.B;
+  const float* prm = p.disc.g.params + (int64_t)r * p.disc.g.stride;
+  const bool sn = p.disc.u != nullptr;
+  for (int i = tid; i < H * d; i += THREADS) s.W1[i] = prm[p.off_w1 + i];
+  for (int h = tid; h < H; h += THREADS) {
+    s.b1[h] = prm[p.off_b1 + h]; s.w2[h] = prm[p.off_w2 + h];
+    if (sn) { s.u1[h] = p.disc.u[(int64_t)r * p.disc.u_stride + h]; s.v2[h] = p.disc.v[(int64_t)r * p.disc.v_stride + d + h]; }
+  }
+  if (sn) for (int j = tid; j < d; j += THREADS) s.v1[j] = p.disc.v[(int64_t)r * p.disc.v_stride + j];
+  const float b2 = prm[p.off_b2];
+  __syncthreads();
+  float sig1 = 1.f, sig2 = 1.f;
+  if (sn) {  // eval mode: no power iteration, sigma from the stored (u, v) (train.py:180,194)
+    sig1 = spectral_sigma(s.W1, s.u1, s.v1, s.tvec, s.red, H, d, false);
+    float t = 0.f;
+    for (int h = tid; h < H; h += THREADS) t = fmaf(s.w2[h], s.v2[h], t);
+    sig2 = p.disc.u[(int64_t)r * p.disc.u_stride + H] * bsum(t, s.red);
+  }
+  for (int i = tid; i < H * d; i += THREADS) s.W1e[i] = s.W1[i] / sig1;
+  for (int h = tid; h < H; h += THREADS) s.w2e[h] = s.w2[h] / sig2;
+  __syncthreads();
+  const float* rows = p.batch.rows + (int64_t)r * p.batch.replica_stride;
+  for (int b0 = 0; b0 < B; b0 += g.RB) {
+    const int nb = min(g.RB, B - b0);
+    load_rows(g, rows, rows, nullptr, PASS_POLICY, b0, nb, s.X, s.CO, s.DF);
+    __syncthreads();
+    forward_chunk(g, s, nb, b2, s.DF);
+    for (int b = tid; b < nb; b += THREADS) {
+      const float f = s.DF[b];
+      if (p.logits) p.logits[(int64_t)r * B + b0 + b] = f;
+      if (p.reward) {  // models.py:177-180
+        const float D = sigmoidf(f);
+        float hh = p.disc.reward_function == IL_REWARD_GAIL ? -log1pf(-D + 1e-6f) : logf(D + 1e-6f) - log1pf(-D + 1e-6f);
+        if (p.disc.reward_function == IL_REWARD_FAIRL) hh = expf(hh) * -hh;
+        p.reward[(int64_t)r * p.reward_rs + (int64_t)(b0 + b) * p.reward_ld] = hh;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void gail_tick_kernel(int64_t* s) { *s += 1; }
+
+int gail_setup(const il_gail* disc, const il_batch* batch, GailDims* g, int64_t* smem, int64_t off[4], const char* what) {
+  IL_CHECK(disc && disc->g.params, "%s: null discriminator", what);
+  IL_CHECK(disc->g.n_layers == 2 && disc->g.dims[2] == 1, "%s: only the depth-1 discriminator (GAIL.yaml:10-13) is supported by this kernel (n_layers=%d)", what, disc->g.n_layers);
+  IL_CHECK(disc->g.activation == IL_ACT_RELU, "%s: only relu discriminators are supported", what);
+  const int d = disc->state_only ? batch->S : batch->S + batch->A;
+  IL_CHECK(disc->g.dims[0] == d, "%s: discriminator input %d != %d", what, disc->g.dims[0], d);
+  const int H = disc->g.dims[1];
+  IL_CHECK(H * d <= 64 * THREADS, "%s: hidden*input = %d exceeds the kernel limit %d", what, H * d, 64 * THREADS);
+  IL_CHECK((disc->u == nullptr) == (disc->v == nullptr), "%s: spectral-norm buffers must both be set or both be null", what);
+  if (disc->u) IL_CHECK(disc->u_stride >= H + 1 && disc->v_stride >= d + H, "%s: spectral-norm buffer strides too small", what);
+  int RB = 64;
+  for (;;) {
+    *g = gail_dims(batch->S, batch->A, H, batch->B, disc->state_only, RB);
+    *smem = gail_carve(*g, nullptr, nullptr);
+    if (*smem <= 220 * 1024 || RB == 8) break;
+    RB /= 2;
+  }
+  IL_CHECK(*smem <= 220 * 1024, "%s: discriminator %dx%d does not fit in shared memory", what, H, d);
+  const MlpOffsets o = mlp_offsets(disc->g.dims, 2);
+  off[0] = o.w[0]; off[1] = o.b[0]; off[2] = o.w[1]; off[3] = o.b[1];
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int64_t il_gail_workspace_bytes(const il_gail_update_args*) { return 0; }
+
+extern "C" int il_gail_update(il_handle* h, const il_gail_update_args* a, void* stream) {
+  IL_CHECK(h && a, "il_gail_update: null argument");
+  IL_CHECK(a->R > 0 && a->policy.rows && a->expert.rows, "il_gail_update: bad batches");
+  IL_CHECK(a->policy.B == a->expert.B && a->policy.S == a->expert.S && a->policy.A == a->expert.A, "il_gail_update: policy/expert batch shape mismatch");
+  IL_CHECK(a->policy.row == row_layout(a->policy.S, a->policy.A).len && a->expert.row == a->policy.row, "il_gail_update: bad row length");
+  IL_CHECK(a->opt.m && a->opt.v && a->opt.step, "il_gail_update: null optimiser state");
+  IL_CHECK(a->loss_function >= 0 && a->loss_function <= 2, "il_gail_update: bad loss function %d", a->loss_function);
+  IL_CHECK(!(a->grad_penalty > 0.f && !a->eps_gp), "il_gail_update: grad_penalty > 0 needs eps_gp");
+  IL_CHECK(!(a->loss_function == IL_LOSS_MIXUP && !a->eps_mix), "il_gail_update: Mixup needs eps_mix");
+  GailUpdParams p;
+  p.a = *a;
+  int64_t smem, off[4];
+  IL_TRY(gail_setup(&a->disc, &a->policy, &p.g, &smem, off, "il_gail_update"));
+  p.off_w1 = off[0]; p.off_b1 = off[1]; p.off_w2 = off[2]; p.off_b2 = off[3];
+  cudaStream_t st = (cudaStream_t)stream;
+  IL_LAUNCH(h, gail_tick_kernel, 1, 1, 0, st, a->opt.step);
+  const int ne = (p.g.H * p.g.d + THREADS - 1) / THREADS;
+#define GAIL_LAUNCH(NE) IL_LAUNCH(h, gail_update_kernel<NE>, a->R, THREADS, (size_t)smem, st, p)
+  if (ne <= 4) GAIL_LAUNCH(4);
+  else if (ne <= 16) GAIL_LAUNCH(16);
+  else if (ne <= 32) GAIL_LAUNCH(32);
+  else GAIL_LAUNCH(64);
+#undef GAIL_LAUNCH
+  return 0;
+}
+
+extern "C" int il_gail_reward(il_handle* h, const il_gail* disc, int R, const il_batch* batch, float* reward, int64_t reward_rs, int reward_ld, float* logits, void* stream) {
+  IL_CHECK(h && disc && batch && batch->rows && R > 0, "il_gail_reward: bad argument");
+  IL_CHECK(batch->row == row_layout(batch->S, batch->A).len, "il_gail_reward: bad row length");
+  GailRewParams p;
+  p.disc = *disc; p.batch = *batch;
+  int64_t smem, off[4];
+  IL_TRY(gail_setup(disc, batch, &p.g, &smem, off, "il_gail_reward"));
+  p.off_w1 = off[0]; p.off_b1 = off[1]; p.off_w2 = off[2]; p.off_b2 = off[3];
+  p.reward = reward; p.reward_rs = reward_rs; p.reward_ld = reward_ld; p.logits = logits;
+  IL_LAUNCH(h, gail_reward_kernel, R, THREADS, (size_t)smem, (cudaStream_t)stream, p);
+  return 0;
+}
+
+// Opt in to > 48 KB dynamic shared memory once (not inside a stream capture).
+int gail_init() {
+  IL_CUDA(cudaFuncSetAttribute(gail_update_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  IL_CUDA(cudaFuncSetAttribute(gail_update_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  IL_CUDA(cudaFuncSetAttribute(gail_update_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  IL_CUDA(cudaFuncSetAttribute(gail_update_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  IL_CUDA(cudaFuncSetAttribute(gail_reward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  return 0;
+}

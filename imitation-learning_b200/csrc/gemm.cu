@@ -1,0 +1,272 @@
+// Grouped fp32 GEMM with fused MLP epilogues (bias, activation, activation-derivative mask, bias-gradient
+// column sums). One launch covers all replicas (groups): the reference's per-network nn.Linear forward /
+// autograd backward (models.py:48-69 as used by training.py:14-54) batched over the replica axis.
+//
+// This is the exact-fp32 (FFMA) engine. The dense H x H layers can instead be routed to the tcgen05 engine
+// (tc_gemm.cu) by il_set_gemm_mode; everything thin (K = state size, N = 1 or 2A) stays here.
+#include "common.cuh"
+
+namespace {
+
+template <int V>
+__device__ __forceinline__ void lds_vec(float* dst, const float* src) {
+  if constexpr (V == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(src);
+    dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+  } else if constexpr (V == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(src);
+    dst[0] = t.x; dst[1] = t.y;
+  } else {
+    dst[0] = src[0];
+  }
+}
+
+template <int BM, int BN, int BK, int TM, int TN, bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(256, 2) gemm_grouped_kernel(const GemmArgs p) {
+  constexpr int THREADS = 256;
+  static_assert((BM / TM) * (BN / TN) == THREADS, "tile/thread mismatch");
+  constexpr int VM = TM >= 4 ? 4 : TM, VN = TN >= 4 ? 4 : TN;
+  constexpr int RC = TM / VM, CC = TN / VN;
+  constexpr int LDAS = BM + 4, LDBS = BN + 4;
+  constexpr int A_F4 = BM * BK / 4, B_F4 = BN * BK / 4;
+  constexpr int LA = (A_F4 + THREADS - 1) / THREADS, LB = (B_F4 + THREADS - 1) / THREADS;
+
+  __shared__ __align__(16) float As[2][BK][LDAS];
+  __shared__ __align__(16) float Bs[2][BK][LDBS];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  const int g = blockIdx.z;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int M = p.M, N = p.N, K = p.K;
+
+  const float* __restrict__ A = p.A + (int64_t)(g / p.a_gdiv) * p.a_gs;
+  const float* __restrict__ B = p.B + (int64_t)(g / p.b_gdiv) * p.b_gs;
+  const bool vecA = ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) && (p.a_gs % 4 == 0) && (p.lda % 4 == 0);
+  const bool vecB = ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0) && (p.b_gs % 4 == 0) && (p.ldb % 4 == 0);
+
+  float4 ra[LA], rb[LB];
+  float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool do_colsum = (!A_KMAJOR) && (p.colsum != nullptr) && (blockIdx.x == 0);
+
+  auto load_a = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < LA; ++j) {
+      const int i = tid + j * THREADS;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < A_F4) {
+        if constexpr (A_KMAJOR) {
+          const int row = m0 + i / (BK / 4), kq = k0 + (i % (BK / 4)) * 4;
+          if (row < M) {
+            const float* src = A + (int64_t)row * p.lda + kq;
+            if (vecA && kq + 3 < K) {
+              v = __ldg(reinterpret_cast<const float4*>(src));
+            } else {
+              if (kq + 0 < K) v.x = __ldg(src + 0);
+              if (kq + 1 < K) v.y = __ldg(src + 1);
+              if (kq + 2 < K) v.z = __ldg(src + 2);
+              if (kq + 3 < K) v.w = __ldg(src + 3);
+            }
+          }
+        } else {
+          const int kr = k0 + i / (BM / 4), mq = m0 + (i % (BM / 4)) * 4;
+          if (kr < K) {
+            const float* src = A + (int64_t)kr * p.lda + mq;
+            if (vecA && mq + 3 < M) {
+              v = __ldg(reinterpret_cast<const float4*>(src));
+            } else {
+              if (mq + 0 < M) v.x = __ldg(src + 0);
+              if (mq + 1 < M) v.y = __ldg(src + 1);
+              if (mq + 2 < M) v.z = __ldg(src + 2);
+              if (mq + 3 < M) v.w = __ldg(src + 3);
+            }
+          }
+        }
+      }
+      ra[j] = v;
+    }
+  };
+  auto load_b = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < LB; ++j) {
+      const int i = tid + j * THREADS;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < B_F4) {
+        if constexpr (B_KMAJOR) {
+          const int row = n0 + i / (BK / 4), kq = k0 + (i % (BK / 4)) * 4;
+          if (row < N) {
+            const float* src = B + (int64_t)row * p.ldb + kq;
+            if (vecB && kq + 3 < K) {
+              v = __ldg(reinterpret_cast<const float4*>(src));
+            } else {
+              if (kq + 0 < K) v.x = __ldg(src + 0);
+              if (kq + 1 < K) v.y = __ldg(src + 1);
+              if (kq + 2 < K) v.z = __ldg(src + 2);
+              if (kq + 3 < K) v.w = __ldg(src + 3);
+            }
+          }
+        } else {
+          const int kr = k0 + i / (BN / 4), nq = n0 + (i % (BN / 4)) * 4;
+          if (kr < K) {
+            const float* src = B + (int64_t)kr * p.ldb + nq;
+            if (vecB && nq + 3 < N) {
+              v = __ldg(reinterpret_cast<const float4*>(src));
+            } else {
+              if (nq + 0 < N) v.x = __ldg(src + 0);
+              if (nq + 1 < N) v.y = __ldg(src + 1);
+              if (nq + 2 < N) v.z = __ldg(src + 2);
+              if (nq + 3 < N) v.w = __ldg(src + 3);
+            }
+          }
+        }
+      }
+      rb[j] = v;
+    }
+  };
+  auto store_a = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < LA; ++j) {
+      const int i = tid + j * THREADS;
+      if (i < A_F4) {
+        if constexpr (A_KMAJOR) {
+          const int row = i / (BK / 4), kq = (i % (BK / 4)) * 4;
+          As[buf][kq + 0][row] = ra[j].x;
+          As[buf][kq + 1][row] = ra[j].y;
+          As[buf][kq + 2][row] = ra[j].z;
+          As[buf][kq + 3][row] = ra[j].w;
+        } else {
+          const int kr = i / (BM / 4), mq = (i % (BM / 4)) * 4;
+          *reinterpret_cast<float4*>(&As[buf][kr][mq]) = ra[j];
+          if (do_colsum) { csum.x += ra[j].x; csum.y += ra[j].y; csum.z += ra[j].z; csum.w += ra[j].w; }
+        }
+      }
+    }
+  };
+  auto store_b = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < LB; ++j) {
+      const int i = tid + j * THREADS;
+      if (i < B_F4) {
+        if constexpr (B_KMAJOR) {
+          const int row = i / (BK / 4), kq = (i % (BK / 4)) * 4;
+          Bs[buf][kq + 0][row] = rb[j].x;
+          Bs[buf][kq + 1][row] = rb[j].y;
+          Bs[buf][kq + 2][row] = rb[j].z;
+          Bs[buf][kq + 3][row] = rb[j].w;
+        } else {
+          const int kr = i / (BN / 4), nq = (i % (BN / 4)) * 4;
+          *reinterpret_cast<float4*>(&Bs[buf][kr][nq]) = rb[j];
+        }
+      }
+    }
+  };
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int nk = (K + BK - 1) / BK;
+  load_a(0);
+  load_b(0);
+  store_a(0);
+  store_b(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) {
+      load_a((kt + 1) * BK);
+      load_b((kt + 1) * BK);
+    }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int rc = 0; rc < RC; ++rc) lds_vec<VM>(&a[rc * VM], &As[buf][k][rc * (BM / RC) + ty * VM]);
+#pragma unroll
+      for (int cc = 0; cc < CC; ++cc) lds_vec<VN>(&b[cc * VN], &Bs[buf][k][cc * (BN / CC) + tx * VN]);
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      store_a(buf ^ 1);
+      store_b(buf ^ 1);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue ----
+  float* __restrict__ C = p.C + (int64_t)g * p.c_gs;
+  const float* __restrict__ bias = p.bias ? p.bias + (int64_t)g * p.bias_gs : nullptr;
+  const float* __restrict__ mask = p.mask ? p.mask + (int64_t)g * p.mask_gs : nullptr;
+#pragma unroll
+  for (int rc = 0; rc < RC; ++rc) {
+#pragma unroll
+    for (int i = 0; i < VM; ++i) {
+      const int m = m0 + rc * (BM / RC) + ty * VM + i;
+      if (m >= M) continue;
+#pragma unroll
+      for (int cc = 0; cc < CC; ++cc) {
+#pragma unroll
+        for (int j = 0; j < VN; ++j) {
+          const int n = n0 + cc * (BN / CC) + tx * VN + j;
+          if (n >= N) continue;
+          float v = acc[rc * VM + i][cc * VN + j];
+          if (bias) v += __ldg(bias + n);
+          if (p.accumulate) v += C[(int64_t)m * p.ldc + n];
+          if (p.act >= 0) v = act_apply(v, p.act);
+          if (mask) v *= act_grad_from_output(__ldg(mask + (int64_t)m * p.ldmask + n), p.mask_act);
+          C[(int64_t)m * p.ldc + n] = v;
+        }
+      }
+    }
+  }
+
+  if constexpr (!A_KMAJOR) {
+    if (do_colsum) {  // bias gradient: colsum[m] = sum_k A[k, m], deterministic order
+      float4* red = reinterpret_cast<float4*>(&As[0][0][0]);
+      red[tid] = csum;
+      __syncthreads();
+      if (tid < BM && m0 + tid < M) {
+        constexpr int CH = BM / 4;                               // float4 chunks per k row
+        constexpr int ACTIVE = A_F4 < THREADS ? A_F4 : THREADS;  // threads that loaded A
+        const int chunk = tid / 4, comp = tid % 4;
+        float s = 0.f;
+        for (int t = chunk; t < ACTIVE; t += CH) s += reinterpret_cast<const float*>(&red[t])[comp];
+        p.colsum[(int64_t)g * p.colsum_gs + m0 + tid] = s;
+      }
+    }
+  }
+}
+
+template <int BM, int BN, int TM, int TN>
+int launch_cfg(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
+  constexpr int BK = 16;
+  dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, a.G), block(256);
+  if (a.a_kmajor && a.b_kmajor) {
+    IL_LAUNCH(h, (gemm_grouped_kernel<BM, BN, BK, TM, TN, true, true>), grid, block, 0, stream, a);
+  } else if (a.a_kmajor && !a.b_kmajor) {
+    IL_LAUNCH(h, (gemm_grouped_kernel<BM, BN, BK, TM, TN, true, false>), grid, block, 0, stream, a);
+  } else if (!a.a_kmajor && !a.b_kmajor) {
+    IL_LAUNCH(h, (gemm_grouped_kernel<BM, BN, BK, TM, TN, false, false>), grid, block, 0, stream, a);
+  } else {
+    IL_FAIL("gemm: unsupported operand layout (A m-major with B k-major)");
+  }
+  return 0;
+}
+
+}  // namespace
+
+int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
+  IL_CHECK(a.M > 0 && a.N > 0 && a.K > 0 && a.G > 0, "gemm: empty problem M=%d N=%d K=%d G=%d", a.M, a.N, a.K, a.G);
+  IL_CHECK(a.G <= 65535, "gemm: too many groups (%d)", a.G);
+  IL_CHECK(!(a.colsum && a.a_kmajor), "gemm: colsum needs the [K, M] operand layout");
+  IL_CHECK(!(a.accumulate && a.act >= 0), "gemm: accumulate with activation is not supported");
+  if (a.M <= 16) return launch_cfg<16, 128, 1, 8>(h, a, stream);
+  if (a.N <= 16) return launch_cfg<128, 16, 8, 1>(h, a, stream);
+  if (a.M <= 32) return launch_cfg<32, 128, 2, 8>(h, a, stream);
+  return launch_cfg<128, 128, 8, 8>(h, a, stream);
+}

@@ -1,0 +1,299 @@
+// Replica-batched MLP programs + SoftActor / TwinCritic entry points + Adam / polyak kernels.
+#include "mlp.cuh"
+
+#include <math.h>
+
+int mlp_validate(const il_mlp* m, const char* what) {
+  IL_CHECK(m != nullptr && m->params != nullptr, "%s: null mlp", what);
+  IL_CHECK(m->n_layers >= 1 && m->n_layers <= IL_MAX_LAYERS, "%s: n_layers %d out of range", what, m->n_layers);
+  IL_CHECK(m->activation >= 0 && m->activation <= 2, "%s: bad activation %d", what, m->activation);
+  for (int l = 0; l <= m->n_layers; ++l) IL_CHECK(m->dims[l] > 0, "%s: dims[%d] = %d", what, l, m->dims[l]);
+  const MlpOffsets o = mlp_offsets(m->dims, m->n_layers);
+  IL_CHECK(m->stride >= o.total - 31 && m->stride % 4 == 0, "%s: stride %lld too small / unaligned for %lld parameters", what, (long long)m->stride, (long long)o.total);
+  IL_CHECK((reinterpret_cast<uintptr_t>(m->params) & 15) == 0, "%s: params not 16-byte aligned", what);
+  return 0;
+}
+
+int mlp_max_hidden(const il_mlp* m) {
+  int mx = 1;
+  for (int l = 1; l <= m->n_layers; ++l) mx = m->dims[l] > mx ? m->dims[l] : mx;
+  return mx;
+}
+
+int64_t mlp_acts_bytes(const il_mlp* m, int G, int n) {
+  int64_t b = 0;
+  for (int l = 0; l + 1 < m->n_layers; ++l) b += il_align_up((int64_t)G * n * m->dims[l + 1] * 4, 256);
+  return b;
+}
+
+char* mlp_acts_carve(const il_mlp* m, int G, int n, char* ws, MlpActs* acts) {
+  for (int l = 0; l < IL_MAX_LAYERS; ++l) acts->hid[l] = nullptr;
+  for (int l = 0; l + 1 < m->n_layers; ++l) {
+    acts->hid[l] = reinterpret_cast<float*>(ws);
+    ws += il_align_up((int64_t)G * n * m->dims[l + 1] * 4, 256);
+  }
+  return ws;
+}
+
+int mlp_forward(il_handle* h, const il_mlp* m, int G, int n, MatView X, const MlpActs& acts, float* out, int64_t out_gs, int ld_out, cudaStream_t stream) {
+  const MlpOffsets o = mlp_offsets(m->dims, m->n_layers);
+  const int L = m->n_layers;
+  for (int l = 0; l < L; ++l) {
+    GemmArgs a{};
+    if (l == 0) {
+      a.A = X.ptr; a.a_gs = X.gs; a.a_gdiv = X.gdiv; a.lda = X.ld;
+    } else {
+      a.A = acts.hid[l - 1]; a.a_gs = (int64_t)n * m->dims[l]; a.a_gdiv = 1; a.lda = m->dims[l];
+    }
+    a.a_kmajor = 1;
+    a.B = m->params + o.w[l]; a.b_gs = m->stride; a.b_gdiv = 1; a.ldb = m->dims[l]; a.b_kmajor = 1;
+    a.bias = m->params + o.b[l]; a.bias_gs = m->stride;
+    if (l == L - 1) {
+      a.C = out; a.c_gs = out_gs; a.ldc = ld_out; a.act = -1;
+    } else {
+      a.C = acts.hid[l]; a.c_gs = (int64_t)n * m->dims[l + 1]; a.ldc = m->dims[l + 1]; a.act = m->activation;
+    }
+    a.M = n; a.N = m->dims[l + 1]; a.K = m->dims[l]; a.G = G;
+    IL_TRY(launch_gemm(h, a, stream));
+  }
+  return 0;
+}
+
+int mlp_backward(il_handle* h, const il_mlp* m, int G, int n, MatView X, const MlpActs& acts, MatView dOut, float* grads, int64_t grad_stride,
+                 float* dX, int64_t dx_gs, int ld_dx, int dx_col0, int dx_cols, float* tmpA, float* tmpB, cudaStream_t stream) {
+  const MlpOffsets o = mlp_offsets(m->dims, m->n_layers);
+  const int L = m->n_layers;
+  MatView dZ = dOut;  // gradient w.r.t. the pre-activation output of layer l
+  float* next_tmp = tmpA;
+  for (int l = L - 1; l >= 0; --l) {
+    MatView Xin = l == 0 ? X : MatView{acts.hid[l - 1], (int64_t)n * m->dims[l], 1, m->dims[l]};
+    if (grads) {  // dW_l[o, i] = sum_b dZ[b, o] * Xin[b, i];  db_l[o] = sum_b dZ[b, o]
+      GemmArgs a{};
+      a.A = dZ.ptr; a.a_gs = dZ.gs; a.a_gdiv = dZ.gdiv; a.lda = dZ.ld; a.a_kmajor = 0;
+      a.B = Xin.ptr; a.b_gs = Xin.gs; a.b_gdiv = Xin.gdiv; a.ldb = Xin.ld; a.b_kmajor = 0;
+      a.C = grads + o.w[l]; a.c_gs = grad_stride; a.ldc = m->dims[l]; a.act = -1;
+      a.colsum = grads + o.b[l]; a.colsum_gs = grad_stride;
+      a.M = m->dims[l + 1]; a.N = m->dims[l]; a.K = n; a.G = G;
+      IL_TRY(launch_gemm(h, a, stream));
+    }
+    if (l > 0) {  // dZ_{l-1}[b, i] = (sum_o dZ[b, o] * W_l[o, i]) * act'(hid_{l-1}[b, i])
+      GemmArgs a{};
+      a.A = dZ.ptr; a.a_gs = dZ.gs; a.a_gdiv = dZ.gdiv; a.lda = dZ.ld; a.a_kmajor = 1;
+      a.B = m->params + o.w[l]; a.b_gs = m->stride; a.b_gdiv = 1; a.ldb = m->dims[l]; a.b_kmajor = 0;
+      a.C = next_tmp; a.c_gs = (int64_t)n * m->dims[l]; a.ldc = m->dims[l]; a.act = -1;
+      a.mask = acts.hid[l - 1]; a.mask_gs = (int64_t)n * m->dims[l]; a.ldmask = m->dims[l]; a.mask_act = m->activation;
+      a.M = n; a.N = m->dims[l]; a.K = m->dims[l + 1]; a.G = G;
+      IL_TRY(launch_gemm(h, a, stream));
+      dZ = MatView{next_tmp, (int64_t)n * m->dims[l], 1, m->dims[l]};
+      next_tmp = next_tmp == tmpA ? tmpB : tmpA;
+    } else if (dX) {  // gradient w.r.t. a column slice of the input
+      GemmArgs a{};
+      a.A = dZ.ptr; a.a_gs = dZ.gs; a.a_gdiv = dZ.gdiv; a.lda = dZ.ld; a.a_kmajor = 1;
+      a.B = m->params + o.w[0] + dx_col0; a.b_gs = m->stride; a.b_gdiv = 1; a.ldb = m->dims[0]; a.b_kmajor = 0;
+      a.C = dX; a.c_gs = dx_gs; a.ldc = ld_dx; a.act = -1;
+      a.M = n; a.N = dx_cols; a.K = m->dims[1]; a.G = G;
+      IL_TRY(launch_gemm(h, a, stream));
+    }
+  }
+  return 0;
+}
+
+// ---- tanh-Gaussian head (models.py:90-102; torch TransformedDistribution / TanhTransform arithmetic) -------
+namespace {
+
+__global__ void actor_head_kernel(const HeadFwdArgs p) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= (int64_t)p.R * p.n) return;
+  const int r = (int)(row / p.n), i = (int)(row % p.n);
+  const int A = p.A;
+  const float* hd = p.head + row * 2 * A;
+  float* act_row = p.action ? p.action + (int64_t)r * p.action_rs + (int64_t)i * p.ld_action : nullptr;
+  if (p.copy_src && act_row) {
+    const float* src = p.copy_src + (int64_t)r * p.copy_rs + (int64_t)i * p.copy_ld;
+    for (int j = 0; j < p.copy_cols; ++j) act_row[j - p.copy_cols] = __ldg(src + j);
+  }
+  const float keep = p.zero_mask ? 1.f - __ldg(p.zero_mask + (int64_t)r * p.zero_mask_rs + (int64_t)i * p.zero_mask_ld) : 1.f;
+  const float LOG_SQRT_2PI = 0.91893853320467274178f, LOG2 = 0.69314718055994530942f;
+  const float A_LO = (float)(-1.0 + 1e-6), A_HI = (float)(1.0 - 1e-6);
+  float sum_ladj = 0.f, sum_nlp = 0.f;
+  const bool want_lp = p.log_prob != nullptr && (p.eps != nullptr || p.given != nullptr);
+  for (int j = 0; j < A; ++j) {
+    const float mu = hd[j];
+    const float ls = fminf(fmaxf(hd[A + j], -20.f), 2.f);  // models.py:92
+    if (p.mean) p.mean[row * A + j] = mu;
+    if (p.log_std) p.log_std[row * A + j] = ls;
+    float x, a;
+    const float sd = expf(ls);
+    if (p.given) {  // models.py:97-99: clamp, atanh
+      a = fminf(fmaxf(p.given[row * A + j], A_LO), A_HI);
+      x = atanhf(a);
+    } else if (p.eps) {  // Normal.sample / rsample: loc + eps * scale
+      x = __fadd_rn(mu, __fmul_rn(sd, p.eps[row * A + j]));
+      a = tanhf(x);
+    } else {  // models.py:101-102
+      x = mu;
+      a = tanhf(mu);
+    }
+    if (act_row && !p.given) act_row[j] = keep * a;
+    if (want_lp) {
+      const float var = __fmul_rn(sd, sd);
+      const float diff = __fsub_rn(x, mu);
+      float nlp = __fdiv_rn(-__fmul_rn(diff, diff), __fmul_rn(2.f, var));
+      nlp = __fsub_rn(__fsub_rn(nlp, logf(sd)), LOG_SQRT_2PI);
+      const float ladj = __fmul_rn(2.f, __fsub_rn(__fsub_rn(LOG2, x), softplusf(__fmul_rn(-2.f, x))));
+      sum_nlp += nlp;
+      sum_ladj += ladj;
+    }
+  }
+  if (want_lp) p.log_prob[row] = __fadd_rn(__fsub_rn(0.f, sum_ladj), sum_nlp);
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, const int64_t* __restrict__ step,
+                            double lr, double beta1_d, double beta2_d, double eps_d, double wd, int64_t n) {
+  __shared__ float s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {  // torch _single_tensor_adam: Python-double scalars, then cast to the tensor dtype
+    const double t = (double)*step;
+    const double bc1 = 1.0 - pow(beta1_d, t), bc2 = 1.0 - pow(beta2_d, t);
+    s_step_size = (float)(lr / bc1);
+    s_bc2_sqrt = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const float decay = (float)(1.0 - lr * wd), w1 = (float)(1.0 - beta1_d), w2 = (float)(1.0 - beta2_d);
+  const float beta2 = (float)beta2_d, eps = (float)eps_d;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float pi = p[i];
+    const float gi = g[i];
+    float mi = m[i], vi = v[i];
+    if (wd != 0.0) pi = __fmul_rn(pi, decay);                                  // param.mul_(1 - lr * weight_decay)
+    mi = __fadd_rn(mi, __fmul_rn(w1, __fsub_rn(gi, mi)));                      // exp_avg.lerp_(grad, 1 - beta1)
+    vi = __fadd_rn(__fmul_rn(vi, beta2), __fmul_rn(__fmul_rn(w2, gi), gi));    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);        // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
+    pi = __fadd_rn(pi, __fmul_rn(-step_size, __fdiv_rn(mi, denom)));           // param.addcdiv_(exp_avg, denom, value=-step_size)
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+}
+
+__global__ void tick_kernel(int64_t* s0, int64_t* s1, int64_t* s2) {
+  if (s0) *s0 += 1;
+  if (s1) *s1 += 1;
+  if (s2) *s2 += 1;
+}
+
+__global__ void polyak_kernel(float* __restrict__ t, const float* __restrict__ o, int64_t n, float tau, float one_minus_tau) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    t[i] = __fadd_rn(__fmul_rn(t[i], tau), __fmul_rn(one_minus_tau, o[i]));  // models.py:81: mul_(tau).add_((1 - tau) * param)
+}
+
+// q1/q2 split of the twin output [2R, n] -> q1 [R, n], q2 [R, n]
+__global__ void split_twin_kernel(const float* __restrict__ q, float* __restrict__ q1, float* __restrict__ q2, int R, int n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)R * n) return;
+  const int r = (int)(i / n), b = (int)(i % n);
+  if (q1) q1[i] = q[((int64_t)2 * r) * n + b];
+  if (q2) q2[i] = q[((int64_t)2 * r + 1) * n + b];
+}
+
+// X[r, i, :] = cat(state[r, i, :S], action[r, i, :A])   (models.py:20-21)
+__global__ void concat_kernel(const float* __restrict__ s, int64_t s_rs, int ld_s, int S, const float* __restrict__ a, int64_t a_rs, int ld_a, int A,
+                              float* __restrict__ x, int R, int n) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int d = S + A;
+  if (idx >= (int64_t)R * n * d) return;
+  const int j = (int)(idx % d);
+  const int64_t row = idx / d;
+  const int r = (int)(row / n), i = (int)(row % n);
+  x[idx] = j < S ? s[(int64_t)r * s_rs + (int64_t)i * ld_s + j] : a[(int64_t)r * a_rs + (int64_t)i * ld_a + (j - S)];
+}
+
+inline int ew_blocks(int64_t n, int threads, int sm_count) {
+  int64_t b = (n + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+int launch_actor_head(il_handle* h, const HeadFwdArgs& a, cudaStream_t stream) {
+  const int64_t rows = (int64_t)a.R * a.n;
+  IL_LAUNCH(h, actor_head_kernel, (unsigned)((rows + 127) / 128), 128, 0, stream, a);
+  return 0;
+}
+
+int launch_adam(il_handle* h, float* params, const float* grads, const il_adam* opt, int64_t n, cudaStream_t stream) {
+  IL_CHECK(opt->m && opt->v && opt->step, "adam: null state");
+  IL_LAUNCH(h, adam_kernel, ew_blocks(n, 256, h->sm_count), 256, 0, stream, params, grads, opt->m, opt->v, opt->step, opt->lr, opt->beta1, opt->beta2, opt->eps,
+            opt->weight_decay, n);
+  return 0;
+}
+
+int launch_tick(il_handle* h, int64_t* s0, int64_t* s1, int64_t* s2, cudaStream_t stream) {
+  IL_LAUNCH(h, tick_kernel, 1, 1, 0, stream, s0, s1, s2);
+  return 0;
+}
+
+extern "C" int il_adam_step(il_handle* h, float* params, const float* grads, const il_adam* opt, int64_t n, void* stream) {
+  IL_CHECK(h && params && grads && opt, "il_adam_step: null argument");
+  IL_TRY(launch_tick(h, opt->step, nullptr, nullptr, (cudaStream_t)stream));
+  return launch_adam(h, params, grads, opt, n, (cudaStream_t)stream);
+}
+
+extern "C" int il_polyak(il_handle* h, float* target, const float* online, int64_t n, float polyak_factor, void* stream) {
+  IL_CHECK(h && target && online && n >= 0, "il_polyak: bad argument");
+  if (n == 0) return 0;
+  IL_LAUNCH(h, polyak_kernel, ew_blocks(n, 256, h->sm_count), 256, 0, (cudaStream_t)stream, target, online, n, polyak_factor, (float)(1.0 - (double)polyak_factor));
+  return 0;
+}
+
+// ---- SoftActor ------------------------------------------------------------------------------------------------
+extern "C" int64_t il_actor_workspace_bytes(const il_mlp* actor, int R, int n) {
+  return mlp_acts_bytes(actor, R, n) + il_align_up((int64_t)R * n * actor->dims[actor->n_layers] * 4, 256);
+}
+
+extern "C" int il_actor_forward(il_handle* h, const il_mlp* actor, int R, int n, const float* states, int64_t states_rs, int ld_states, const float* eps,
+                                const float* given_action, float* action, float* log_prob, float* mean, float* log_std, void* workspace, int64_t workspace_bytes,
+                                void* stream) {
+  IL_CHECK(h && states && workspace, "il_actor_forward: null argument");
+  IL_TRY(mlp_validate(actor, "il_actor_forward"));
+  IL_CHECK(R > 0 && n > 0, "il_actor_forward: R=%d n=%d", R, n);
+  const int out = actor->dims[actor->n_layers];
+  IL_CHECK(out % 2 == 0, "il_actor_forward: head size %d is not 2*A", out);
+  IL_CHECK(workspace_bytes >= il_actor_workspace_bytes(actor, R, n), "il_actor_forward: workspace too small");
+  MlpActs acts;
+  char* ws = mlp_acts_carve(actor, R, n, static_cast<char*>(workspace), &acts);
+  float* head = reinterpret_cast<float*>(ws);
+  IL_TRY(mlp_forward(h, actor, R, n, MatView{states, states_rs, 1, ld_states}, acts, head, (int64_t)n * out, out, (cudaStream_t)stream));
+  HeadFwdArgs a{};
+  a.head = head; a.eps = eps; a.given = given_action;
+  a.action = action; a.action_rs = (int64_t)n * (out / 2); a.ld_action = out / 2;
+  a.log_prob = log_prob; a.mean = mean; a.log_std = log_std;
+  a.R = R; a.n = n; a.A = out / 2;
+  return launch_actor_head(h, a, (cudaStream_t)stream);
+}
+
+// ---- TwinCritic -----------------------------------------------------------------------------------------------
+extern "C" int64_t il_critic_workspace_bytes(const il_mlp* critic, int R, int n) {
+  return mlp_acts_bytes(critic, 2 * R, n) + il_align_up((int64_t)R * n * critic->dims[0] * 4, 256) + il_align_up((int64_t)2 * R * n * 4, 256);
+}
+
+extern "C" int il_critic_forward(il_handle* h, const il_mlp* twin, int R, int n, int S, const float* states, int64_t states_rs, int ld_states, const float* actions,
+                                 int64_t actions_rs, int ld_actions, float* q1, float* q2, void* workspace, int64_t workspace_bytes, void* stream) {
+  IL_CHECK(h && states && actions && workspace, "il_critic_forward: null argument");
+  IL_TRY(mlp_validate(twin, "il_critic_forward"));
+  IL_CHECK(twin->dims[twin->n_layers] == 1, "il_critic_forward: critic head must have one output");
+  IL_CHECK(workspace_bytes >= il_critic_workspace_bytes(twin, R, n), "il_critic_forward: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int d = twin->dims[0];
+  MlpActs acts;
+  char* ws = mlp_acts_carve(twin, 2 * R, n, static_cast<char*>(workspace), &acts);
+  float* X = reinterpret_cast<float*>(ws);
+  ws += il_align_up((int64_t)R * n * d * 4, 256);
+  float* q = reinterpret_cast<float*>(ws);
+  const int A = d - S;
+  IL_CHECK(S > 0 && A > 0, "il_critic_forward: S=%d with input width %d", S, d);
+  const int64_t total = (int64_t)R * n * d;
+  IL_LAUNCH(h, concat_kernel, (unsigned)((total + 255) / 256), 256, 0, st, states, states_rs, ld_states, S, actions, actions_rs, ld_actions, A, X, R, n);
+  IL_TRY(mlp_forward(h, twin, 2 * R, n, MatView{X, (int64_t)n * d, 2, d}, acts, q, (int64_t)n, 1, st));
+  IL_LAUNCH(h, split_twin_kernel, (unsigned)(((int64_t)R * n + 255) / 256), 256, 0, st, q, q1, q2, R, n);
+  return 0;
+}

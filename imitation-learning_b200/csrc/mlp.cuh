@@ -1,0 +1,58 @@
+// Replica-batched MLP forward / backward programs built from the grouped GEMM (gemm.cu).
+#pragma once
+#include "common.cuh"
+
+// A grouped row-major matrix view: element (g, i, j) at ptr + (g / gdiv) * gs + i * ld + j.
+struct MatView {
+  const float* ptr;
+  int64_t gs;
+  int gdiv;
+  int ld;
+};
+
+struct MlpActs {  // outputs of the hidden layers ([G, n, dims[l+1]] contiguous), kept for the backward pass
+  float* hid[IL_MAX_LAYERS];
+};
+
+// Bytes for the hidden activations of G nets on n rows (il_align_up'ed per buffer).
+int64_t mlp_acts_bytes(const il_mlp* m, int G, int n);
+// Carves hidden-activation buffers out of `ws`; returns the advanced pointer.
+char* mlp_acts_carve(const il_mlp* m, int G, int n, char* ws, MlpActs* acts);
+
+// Forward of G nets: out[g] ([n, dims[L]], row stride ld_out, group stride out_gs) = net_g(X[g]).
+int mlp_forward(il_handle* h, const il_mlp* m, int G, int n, MatView X, const MlpActs& acts, float* out, int64_t out_gs, int ld_out,
+                cudaStream_t stream);
+
+// Backward of G nets from dOut (gradient at the linear head), using the saved hidden outputs.
+//  grads != nullptr : parameter gradients written in the flat parameter layout (net stride grad_stride).
+//  dX    != nullptr : gradient w.r.t. input columns [dx_col0, dx_col0 + dx_cols) written to dX (ld_dx, group stride dx_gs).
+//  tmpA / tmpB      : two scratch buffers of G * n * max_hidden floats (ping-pong for the layer gradients).
+int mlp_backward(il_handle* h, const il_mlp* m, int G, int n, MatView X, const MlpActs& acts, MatView dOut, float* grads, int64_t grad_stride,
+                 float* dX, int64_t dx_gs, int ld_dx, int dx_col0, int dx_cols, float* tmpA, float* tmpB, cudaStream_t stream);
+
+int mlp_max_hidden(const il_mlp* m);
+int mlp_validate(const il_mlp* m, const char* what);
+
+// ---- tanh-Gaussian head (mlp.cu) ---------------------------------------------------------------------------
+struct HeadFwdArgs {
+  const float* head;        // [rows, 2A] raw actor output (mean | log-std)
+  const float* eps;         // [rows, A] or nullptr
+  const float* given;       // [rows, A] or nullptr (log-prob of a given action, atanh path)
+  float* action;            // nullable; element (r, i, j) at action + r * action_rs + i * ld_action + j
+  int64_t action_rs;
+  int ld_action;
+  const float* zero_mask;   // nullable [rows]: action *= (1 - zero_mask[row])   (training.py:23)
+  int64_t zero_mask_rs;     // replica stride of zero_mask (row i of replica r at zero_mask + r*rs + i*zero_mask_ld)
+  int zero_mask_ld;
+  float* log_prob;          // nullable [rows]
+  float* mean;              // nullable [rows, A]
+  float* log_std;           // nullable [rows, A]
+  const float* copy_src;    // nullable: copy `copy_cols` floats of row (r, i) from copy_src + r*copy_rs + i*copy_ld to action row start - copy_cols
+  int64_t copy_rs;
+  int copy_ld, copy_cols;
+  int R, n, A;
+};
+int launch_actor_head(il_handle* h, const HeadFwdArgs& a, cudaStream_t stream);
+
+int launch_adam(il_handle* h, float* params, const float* grads, const il_adam* opt, int64_t n, cudaStream_t stream);
+int launch_tick(il_handle* h, int64_t* s0, int64_t* s1, int64_t* s2, cudaStream_t stream);

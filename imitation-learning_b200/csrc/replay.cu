@@ -1,0 +1,192 @@
+// ReplayMemory (memory.py:12-68) as packed 16-byte-aligned rows per replica: append / absorbing wrap, index
+// sampling, gather, and the mixed-batch overwrite (models.py:287-290).
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void write_row(float* dst, const RowLayout& L, int S, int A, int lane, const float* state, const float* action, float reward, const float* next_state,
+                                          float terminal, float timeout, float step, bool state_absorbing, bool next_absorbing) {
+  for (int j = lane; j < S; j += 32) {
+    dst[L.state + j] = state_absorbing ? (j == S - 1 ? 1.f : 0.f) : state[j];
+    dst[L.next_state + j] = next_absorbing ? (j == S - 1 ? 1.f : 0.f) : next_state[j];
+  }
+  for (int j = lane; j < A; j += 32) dst[L.action + j] = state_absorbing ? 0.f : action[j];
+  if (lane == 0) {
+    dst[L.reward] = reward;
+    dst[L.terminal] = terminal;
+    dst[L.timeout] = timeout;
+    dst[L.weight] = 1.f;  // memory.py:41
+    dst[L.step] = step;
+    for (int j = L.step + 1; j < L.len; ++j) dst[j] = 0.f;
+  }
+}
+
+// One warp per replica.
+__global__ void replay_append_kernel(il_replay mem, int R, const float* __restrict__ step, const float* __restrict__ state, const float* __restrict__ action,
+                                     const float* __restrict__ reward, const float* __restrict__ next_state, const float* __restrict__ terminal,
+                                     const float* __restrict__ timeout, const int32_t* __restrict__ active, int wrap) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x & 31;
+  if (r >= R) return;
+  if (active && !active[r]) return;
+  const int S = mem.S, A = mem.A;
+  const RowLayout L = row_layout(S, A);
+  const int mi = mem.shared ? 0 : r;
+  float* rows = mem.rows + (int64_t)r * mem.replica_stride;
+  int idx = mem.idx[mi];
+  const float term = terminal[r], tout = timeout[r], stp = step[r];
+  const bool do_wrap = wrap && term != 0.f;  // train.py:162
+  // memory.py:40-44 (+ :67: when wrapping, the stored next state becomes the absorbing state and terminal is cleared)
+  write_row(rows + (int64_t)idx * L.len, L, S, A, lane, state + (int64_t)r * S, action + (int64_t)r * A, reward[r], next_state + (int64_t)r * S, do_wrap ? 0.f : term, tout,
+            stp, false, do_wrap);
+  int full = mem.full[mi];
+  idx = (idx + 1) % mem.size;
+  full = full || idx == 0;
+  if (do_wrap) {  // memory.py:68: absorbing -> absorbing transition, zero action, zero reward, same step
+    write_row(rows + (int64_t)idx * L.len, L, S, A, lane, nullptr, nullptr, 0.f, nullptr, 0.f, 0.f, stp, true, true);
+    idx = (idx + 1) % mem.size;
+    full = full || idx == 0;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    mem.idx[mi] = idx;
+    mem.full[mi] = full;
+    if (term != 0.f || tout != 0.f) mem.num_trajectories[mi] += 1;
+  }
+}
+
+// memory.py:65-68 as a separate call (wrap_for_absorbing_states on the row appended last). One warp per replica.
+__global__ void replay_wrap_kernel(il_replay mem, int R, const int32_t* __restrict__ mask) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x & 31;
+  if (r >= R) return;
+  if (mask && !mask[r]) return;
+  const int S = mem.S, A = mem.A;
+  const RowLayout L = row_layout(S, A);
+  const int mi = mem.shared ? 0 : r;
+  float* rows = mem.rows + (int64_t)r * mem.replica_stride;
+  int idx = mem.idx[mi];
+  const int last = (idx - 1 + mem.size) % mem.size;
+  float* lr = rows + (int64_t)last * L.len;
+  for (int j = lane; j < S; j += 32) lr[L.next_state + j] = j == S - 1 ? 1.f : 0.f;
+  const float stp = lr[L.step];
+  __syncwarp();
+  if (lane == 0) lr[L.terminal] = 0.f;
+  write_row(rows + (int64_t)idx * L.len, L, S, A, lane, nullptr, nullptr, 0.f, nullptr, 0.f, 0.f, stp, true, true);
+  __syncwarp();
+  if (lane == 0) {
+    idx = (idx + 1) % mem.size;
+    mem.idx[mi] = idx;
+    mem.full[mi] = mem.full[mi] || idx == 0;
+  }
+}
+
+// memory.py:51-59: uniform over [0, size) (full) or [0, idx-1) (not full), never the newest row (idx-1) % size.
+__global__ void replay_sample_idx_kernel(il_replay mem, int R, int n, int32_t* __restrict__ out, uint64_t seed, uint64_t stream_id, const uint64_t* __restrict__ counter) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)R * n) return;
+  const int r = (int)(i / n);
+  const int mi = mem.shared ? 0 : r;
+  const int idx = mem.idx[mi], full = mem.full[mi];
+  const uint64_t c = (counter ? *counter : 0ull) + (uint64_t)i;
+  const uint4 rnd = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32)), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  int j;
+  if (full) {
+    const int newest = (idx - 1 + mem.size) % mem.size;
+    j = (int)(((uint64_t)rnd.x * (uint64_t)(mem.size - 1)) >> 32);
+    if (j >= newest) j += 1;
+  } else {
+    const int count = idx - 1 > 0 ? idx - 1 : 1;
+    j = (int)(((uint64_t)rnd.x * (uint64_t)count) >> 32);
+  }
+  out[i] = j;
+}
+
+// one thread per float4 of the output
+__global__ void replay_gather_kernel(const float* __restrict__ rows, int64_t mem_rs, int size, int row4, const int32_t* __restrict__ idx, float* __restrict__ out, int64_t out_rs,
+                                     int R, int B) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)R * B * row4) return;
+  const int q = (int)(t % row4);
+  const int64_t rowi = t / row4;
+  const int r = (int)(rowi / B), b = (int)(rowi % B);
+  int src = idx[rowi];
+  src = src < 0 ? 0 : (src >= size ? size - 1 : src);
+  const float4 v = __ldg(reinterpret_cast<const float4*>(rows + (int64_t)r * mem_rs + (int64_t)src * row4 * 4) + q);
+  reinterpret_cast<float4*>(out + (int64_t)r * out_rs + (int64_t)b * row4 * 4)[q] = v;
+}
+
+__global__ void mix_rows_kernel(float* __restrict__ dst, int64_t dst_rs, const float* __restrict__ src, int64_t src_rs, int row4, int half, int R) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)R * half * row4) return;
+  const int q = (int)(t % row4);
+  const int64_t rowi = t / row4;
+  const int r = (int)(rowi / half), b = (int)(rowi % half);
+  reinterpret_cast<float4*>(dst + (int64_t)r * dst_rs + (int64_t)b * row4 * 4)[q] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)r * src_rs + (int64_t)b * row4 * 4) + q);
+}
+
+int check_replay(const il_replay* m, const char* what) {
+  IL_CHECK(m && m->rows && m->idx && m->full && m->num_trajectories, "%s: null replay field", what);
+  IL_CHECK(m->size > 0 && m->S > 0 && m->A > 0, "%s: size=%d S=%d A=%d", what, m->size, m->S, m->A);
+  IL_CHECK(m->row == row_layout(m->S, m->A).len, "%s: row length %d != %d", what, m->row, row_layout(m->S, m->A).len);
+  IL_CHECK((reinterpret_cast<uintptr_t>(m->rows) & 15) == 0 && m->replica_stride % 4 == 0, "%s: rows not 16-byte aligned", what);
+  return 0;
+}
+int check_batch(const il_batch* b, const char* what) {
+  IL_CHECK(b && b->rows, "%s: null batch", what);
+  IL_CHECK(b->B > 0 && b->row == row_layout(b->S, b->A).len, "%s: B=%d row=%d (S=%d A=%d)", what, b->B, b->row, b->S, b->A);
+  IL_CHECK((reinterpret_cast<uintptr_t>(b->rows) & 15) == 0 && b->replica_stride % 4 == 0, "%s: rows not 16-byte aligned", what);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int il_replay_append(il_handle* h, const il_replay* mem, int R, const float* step, const float* state, const float* action, const float* reward,
+                                const float* next_state, const float* terminal, const float* timeout, const int32_t* active, int wrap, void* stream) {
+  IL_CHECK(h, "il_replay_append: null handle");
+  IL_TRY(check_replay(mem, "il_replay_append"));
+  IL_CHECK(step && state && action && reward && next_state && terminal && timeout && R > 0, "il_replay_append: null input");
+  IL_CHECK(!(wrap && mem->size < 2), "il_replay_append: absorbing wrap needs size >= 2");
+  IL_LAUNCH(h, replay_append_kernel, (unsigned)((R * 32 + 127) / 128), 128, 0, (cudaStream_t)stream, *mem, R, step, state, action, reward, next_state, terminal, timeout, active,
+            wrap);
+  return 0;
+}
+
+extern "C" int il_replay_wrap_absorbing(il_handle* h, const il_replay* mem, int R, const int32_t* mask, void* stream) {
+  IL_CHECK(h && R > 0, "il_replay_wrap_absorbing: bad argument");
+  IL_TRY(check_replay(mem, "il_replay_wrap_absorbing"));
+  IL_CHECK(mem->size >= 2, "il_replay_wrap_absorbing: size must be >= 2");
+  IL_LAUNCH(h, replay_wrap_kernel, (unsigned)((R * 32 + 127) / 128), 128, 0, (cudaStream_t)stream, *mem, R, mask);
+  return 0;
+}
+
+extern "C" int il_replay_sample_indices(il_handle* h, const il_replay* mem, int R, int n, int32_t* idx_out, uint64_t seed, uint64_t stream_id, const uint64_t* counter,
+                                        void* stream) {
+  IL_CHECK(h && idx_out && R > 0 && n > 0, "il_replay_sample_indices: bad argument");
+  IL_TRY(check_replay(mem, "il_replay_sample_indices"));
+  IL_LAUNCH(h, replay_sample_idx_kernel, (unsigned)(((int64_t)R * n + 255) / 256), 256, 0, (cudaStream_t)stream, *mem, R, n, idx_out, seed, stream_id, counter);
+  return 0;
+}
+
+extern "C" int il_replay_gather(il_handle* h, const il_replay* mem, int R, const int32_t* idx, const il_batch* out, void* stream) {
+  IL_CHECK(h && idx && R > 0, "il_replay_gather: bad argument");
+  IL_TRY(check_replay(mem, "il_replay_gather"));
+  IL_TRY(check_batch(out, "il_replay_gather"));
+  IL_CHECK(out->row == mem->row && out->S == mem->S && out->A == mem->A, "il_replay_gather: batch/replay shape mismatch");
+  const int row4 = mem->row / 4;
+  const int64_t total = (int64_t)R * out->B * row4;
+  IL_LAUNCH(h, replay_gather_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, mem->rows, mem->replica_stride, mem->size, row4, idx, out->rows,
+            out->replica_stride, R, out->B);
+  return 0;
+}
+
+extern "C" int il_mix_expert_rows(il_handle* h, const il_batch* batch, const il_batch* expert, int R, void* stream) {
+  IL_CHECK(h && R > 0, "il_mix_expert_rows: bad argument");
+  IL_TRY(check_batch(batch, "il_mix_expert_rows(batch)"));
+  IL_TRY(check_batch(expert, "il_mix_expert_rows(expert)"));
+  IL_CHECK(batch->row == expert->row && expert->B >= batch->B / 2, "il_mix_expert_rows: shape mismatch");
+  const int half = batch->B / 2, row4 = batch->row / 4;
+  if (half == 0) return 0;
+  const int64_t total = (int64_t)R * half * row4;
+  IL_LAUNCH(h, mix_rows_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, batch->rows, batch->replica_stride, expert->rows, expert->replica_stride, row4,
+            half, R);
+  return 0;
+}

@@ -1,0 +1,446 @@
+"""Host-side mirror of the reference's models.py surface (same names / arguments / behaviour) over the sm_100a
+kernels. Every class takes an extra `replicas` axis (default 1 = the reference's shapes).
+
+Cited lines are in the reference's models.py unless noted.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+from math import sqrt
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from .memory import ReplayMemory, TransitionBatch
+from .net import ReplicaMLP, ReplicaRNG, init_fcnn_params, _null_ctx
+
+
+def _cfg_get(cfg, key, default=None):
+  if hasattr(cfg, 'get'): return cfg.get(key, default)
+  return getattr(cfg, key, default)
+
+
+def _as_rns(x: Tensor, R: int, width: int, device) -> Tensor:
+  """[n, w] (R == 1) or [R, n, w] -> contiguous [R, n, w] on the device."""
+  x = torch.as_tensor(x, dtype=torch.float32).to(device)
+  if x.dim() == 2:
+    assert R == 1, f'expected a [R={R}, n, {width}] tensor'
+    x = x.unsqueeze(0)
+  assert x.dim() == 3 and x.size(0) == R and x.size(2) == width, f'bad shape {tuple(x.shape)}; expected [{R}, n, {width}]'
+  return x.contiguous()
+
+
+class _RNG:
+  """Device noise source (Philox, il_fill_normal / il_fill_uniform) standing in for torch's global RNG draws."""
+
+  def __init__(self, seed: int = 0, device=None):
+    self.seed = seed
+    self.counter = None
+    self.device = device
+
+  def _ctr(self, device):
+    if self.counter is None: self.counter = torch.zeros(1, dtype=torch.int64, device=device)
+    return self.counter
+
+  def normal(self, shape, device, stream_id: int = 1, out: Optional[Tensor] = None) -> Tensor:
+    out = torch.empty(shape, device=device, dtype=torch.float32) if out is None else out
+    ctr = self._ctr(device)
+    _lib.check(_lib.lib().il_fill_normal(_lib.handle(), out.data_ptr(), out.numel(), self.seed, stream_id, ctr.data_ptr(), _lib.stream()))
+    _lib.check(_lib.lib().il_counter_add(_lib.handle(), ctr.data_ptr(), (out.numel() + 3) // 4, _lib.stream()))
+    return out
+
+  def uniform(self, shape, device, stream_id: int = 2, out: Optional[Tensor] = None) -> Tensor:
+    out = torch.empty(shape, device=device, dtype=torch.float32) if out is None else out
+    ctr = self._ctr(device)
+    _lib.check(_lib.lib().il_fill_uniform(_lib.handle(), out.data_ptr(), out.numel(), self.seed, stream_id, ctr.data_ptr(), _lib.stream()))
+    _lib.check(_lib.lib().il_counter_add(_lib.handle(), ctr.data_ptr(), (out.numel() + 3) // 4, _lib.stream()))
+    return out
+
+
+default_rng = _RNG(0)
+
+
+def manual_seed(seed: int):
+  """Seeds the device noise source used when noise is not injected."""
+  default_rng.seed, default_rng.counter = seed, None
+
+
+class _Module:
+  """Minimal nn.Module-like surface (parameters / state_dict / train / eval) over flat replica buffers."""
+  training = True
+
+  def train(self, mode: bool = True):
+    self.training = mode
+    return self
+
+  def eval(self):
+    return self.train(False)
+
+  def parameters(self) -> List[Tensor]:
+    return [self.mlp.flat]
+
+  def _state_items(self) -> List[Tuple[str, Tensor]]:
+    raise NotImplementedError
+
+  def state_dict(self) -> Dict[str, Tensor]:
+    """Reference key names. R == 1: the reference's shapes; R > 1: a leading replica axis."""
+    return {k: (v[0] if v.size(0) == 1 else v).detach().clone() for k, v in self._state_items()}
+
+  def load_state_dict(self, sd: Dict[str, Tensor]):
+    for k, v in self._state_items():
+      src = torch.as_tensor(sd[k]).to(v.device, torch.float32)
+      v.copy_(src.reshape(v.shape) if src.numel() == v.numel() else src.unsqueeze(0).expand_as(v))
+
+
+class TanhNormalPolicy:
+  """What `SoftActor.forward` returns (:90-94): the TransformedDistribution surface the reference uses —
+  .sample() / .rsample() / .log_prob(a) / .base_dist.mean — evaluated by the fused actor-head kernel."""
+
+  def __init__(self, actor: 'SoftActor', state: Tensor):
+    self.actor, self.state = actor, state
+    self._cached_action, self._cached_log_prob = None, None
+
+  class _Base:
+    def __init__(self, outer): self.outer = outer
+
+    @property
+    def mean(self) -> Tensor:
+      o = self.outer
+      return o.actor._squeeze(o.actor._run(o.state, want=('mean', ))['mean'])
+
+    @property
+    def stddev(self) -> Tensor:
+      o = self.outer
+      return o.actor._squeeze(o.actor._run(o.state, want=('log_std', ))['log_std'].exp())
+
+  @property
+  def base_dist(self): return TanhNormalPolicy._Base(self)
+
+  def sample(self, eps: Optional[Tensor] = None) -> Tensor:
+    a = self.actor
+    if eps is None: eps = default_rng.normal((a.replicas, self.state.size(1), a.action_size), a.device)
+    out = a._run(self.state, eps=eps, want=('action', 'log_prob'))
+    self._cached_action, self._cached_log_prob = a._squeeze(out['action']), a._squeeze(out['log_prob'])  # TanhTransform(cache_size=1)
+    return self._cached_action
+
+  rsample = sample
+
+  def log_prob(self, action: Tensor) -> Tensor:
+    if action is self._cached_action: return self._cached_log_prob
+    a = self.actor
+    return a._squeeze(a._run(self.state, given=action, want=('log_prob', ))['log_prob'])
+
+
+class SoftActor(_Module):
+  """:84-102. `actor(state)` returns a TanhNormalPolicy; state is [n, S] (R == 1) or [R, n, S]."""
+
+  def __init__(self, state_size: int, action_size: int, model_cfg, replicas: int = 1, rng: Optional[ReplicaRNG] = None, device=None):
+    assert _cfg_get(model_cfg, 'input_dropout', 0) == 0 and _cfg_get(model_cfg, 'dropout', 0) == 0, 'dropout actors (DRIL) are outside the accelerated path'
+    self.state_size, self.action_size, self.replicas = state_size, action_size, replicas
+    self.log_std_dev_min, self.log_std_dev_max = -20, 2  # :87 (the kernel hard-codes the same clamp)
+    dims = [state_size] + [model_cfg.hidden_size] * model_cfg.depth + [2 * action_size]
+    self.mlp = ReplicaMLP(dims, model_cfg.activation, replicas, 1, device)
+    self.device = self.mlp.device
+    for r in range(replicas):
+      with (rng.replica(r) if rng is not None else _null_ctx()):
+        self.mlp.load_params(r, 0, init_fcnn_params(dims, model_cfg.activation))
+    self._ws = None
+
+  def _squeeze(self, t: Tensor) -> Tensor:
+    return t[0] if self.replicas == 1 else t
+
+  def _state_items(self):
+    v = self.mlp.layer_views()[0]
+    return [(f'actor.{2 * l}.{n}', v[2 * l + i]) for l in range(self.mlp.n_layers) for i, n in enumerate(('weight', 'bias'))]
+
+  def _run(self, state: Tensor, eps: Optional[Tensor] = None, given: Optional[Tensor] = None, want=('action', )) -> Dict[str, Tensor]:
+    R, A = self.replicas, self.action_size
+    s = _as_rns(state, R, self.state_size, self.device)
+    n = s.size(1)
+    m = self.mlp.c_struct()
+    need = _lib.lib().il_actor_workspace_bytes(C.byref(m), R, n)
+    if self._ws is None or self._ws.numel() < need: self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+    out = {k: torch.empty((R, n, A) if k in ('action', 'mean', 'log_std') else (R, n), device=self.device) for k in want}
+    eps_t = None if eps is None else _as_rns(eps, R, A, self.device)
+    given_t = None if given is None else _as_rns(given, R, A, self.device)
+    _lib.check(_lib.lib().il_actor_forward(_lib.handle(), C.byref(m), R, n, s.data_ptr(), s.stride(0), s.stride(1), _lib.ptr(eps_t), _lib.ptr(given_t), _lib.ptr(out.get('action')),
+                                           _lib.ptr(out.get('log_prob')), _lib.ptr(out.get('mean')), _lib.ptr(out.get('log_std')), self._ws.data_ptr(), self._ws.numel(),
+                                           _lib.stream()))
+    return out
+
+  def forward(self, state: Tensor) -> TanhNormalPolicy:
+    return TanhNormalPolicy(self, _as_rns(state, self.replicas, self.state_size, self.device))
+
+  __call__ = forward
+
+  def log_prob(self, state: Tensor, action: Tensor) -> Tensor:  # :97-99
+    return self._squeeze(self._run(state, given=action, want=('log_prob', ))['log_prob'])
+
+  def get_greedy_action(self, state: Tensor) -> Tensor:  # :101-102
+    return self._squeeze(self._run(state, want=('action', ))['action'])
+
+
+class TwinCritic(_Module):
+  """:123-141; parameters of critic_1 then critic_2 per replica in one flat buffer (2R nets)."""
+
+  def __init__(self, state_size: int, action_size: int, model_cfg, replicas: int = 1, rng: Optional[ReplicaRNG] = None, device=None):
+    self.state_size, self.action_size, self.replicas = state_size, action_size, replicas
+    dims = [state_size + action_size] + [model_cfg.hidden_size] * model_cfg.depth + [1]
+    self.mlp = ReplicaMLP(dims, model_cfg.activation, replicas, 2, device)
+    self.device = self.mlp.device
+    for r in range(replicas):
+      with (rng.replica(r) if rng is not None else _null_ctx()):
+        self.mlp.load_params(r, 0, init_fcnn_params(dims, model_cfg.activation))  # critic_1 (:136)
+        self.mlp.load_params(r, 1, init_fcnn_params(dims, model_cfg.activation))  # critic_2 (:137)
+    self._ws = None
+
+  def c_struct(self) -> _lib.Mlp:
+    return self.mlp.c_struct()
+
+  def _state_items(self):
+    out = []
+    for t in (0, 1):
+      v = self.mlp.layer_views()[t]
+      out += [(f'critic_{t + 1}.critic.{2 * l}.{n}', v[2 * l + i]) for l in range(self.mlp.n_layers) for i, n in enumerate(('weight', 'bias'))]
+    return out
+
+  def forward(self, state: Tensor, action: Tensor) -> Tuple[Tensor, Tensor]:
+    R = self.replicas
+    s, a = _as_rns(state, R, self.state_size, self.device), _as_rns(action, R, self.action_size, self.device)
+    n = s.size(1)
+    m = self.mlp.c_struct()
+    need = _lib.lib().il_critic_workspace_bytes(C.byref(m), R, n)
+    if self._ws is None or self._ws.numel() < need: self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+    q1, q2 = torch.empty(R, n, device=self.device), torch.empty(R, n, device=self.device)
+    _lib.check(_lib.lib().il_critic_forward(_lib.handle(), C.byref(m), R, n, self.state_size, s.data_ptr(), s.stride(0), s.stride(1), a.data_ptr(), a.stride(0), a.stride(1),
+                                            q1.data_ptr(), q2.data_ptr(), self._ws.data_ptr(), self._ws.numel(), _lib.stream()))
+    return (q1[0], q2[0]) if R == 1 else (q1, q2)
+
+  __call__ = forward
+
+
+def create_target_network(network):
+  """:72-76."""
+  target = copy.copy(network)
+  target.mlp = copy.copy(network.mlp)
+  target.mlp.flat = network.mlp.flat.clone()
+  target._ws = None
+  return target
+
+
+def update_target_network(network, target_network, polyak_factor: float):
+  """:79-81."""
+  t, o = target_network.mlp.flat, network.mlp.flat
+  _lib.check(_lib.lib().il_polyak(_lib.handle(), t.data_ptr(), o.data_ptr(), t.numel(), polyak_factor, _lib.stream()))
+
+
+def make_gail_input(state: Tensor, action: Tensor, next_state: Tensor, terminal: Tensor, actor: SoftActor, reward_shaping: bool, subtract_log_policy: bool) -> Dict[str, Tensor]:
+  """:145-149."""
+  inp = {'state': state, 'action': action}
+  if reward_shaping: inp.update({'next_state': next_state, 'terminal': terminal})
+  if subtract_log_policy: inp.update({'log_policy': actor.log_prob(state, action)})
+  return inp
+
+
+def _spectral_norm_init(weight: Tensor) -> Tuple[Tensor, Tensor]:
+  """torch parametrizations.spectral_norm construction (_SpectralNorm.__init__): u, v ~ N(0, 1) from the global RNG,
+  normalised, then 15 power iterations (sites :58,66,159)."""
+  h, w = weight.shape
+  nz = lambda x: x / x.norm().clamp_min(1e-12)
+  u, v = nz(weight.new_empty(h).normal_(0, 1)), nz(weight.new_empty(w).normal_(0, 1))
+  for _ in range(15):
+    u = nz(torch.mv(weight, v))
+    v = nz(torch.mv(weight.t(), u))
+  return u, v
+
+
+class GAILDiscriminator(_Module):
+  """:152-180. Accelerated configuration: the depth-1 relu `g` network of conf/algorithm/GAIL.yaml (no reward
+  shaping / log-policy subtraction), with or without spectral norm."""
+
+  def __init__(self, state_size: int, action_size: int, imitation_cfg, discount: float, replicas: int = 1, rng: Optional[ReplicaRNG] = None, device=None):
+    model_cfg = imitation_cfg.discriminator
+    self.discount, self.state_only = discount, bool(imitation_cfg.state_only)
+    self.reward_shaping, self.subtract_log_policy, self.reward_function = model_cfg.reward_shaping, model_cfg.subtract_log_policy, model_cfg.reward_function
+    if self.reward_shaping or self.subtract_log_policy: raise NotImplementedError('reward_shaping / subtract_log_policy discriminators are not on the accelerated path yet (SURVEY §8f)')
+    if model_cfg.depth != 1 or model_cfg.activation != 'relu': raise NotImplementedError('only the depth-1 relu discriminator (GAIL.yaml:10-13) is accelerated (SURVEY §8f)')
+    self.state_size, self.action_size, self.replicas = state_size, action_size, replicas
+    self.spectral_norm = bool(imitation_cfg.spectral_norm)
+    d, H = (state_size if self.state_only else state_size + action_size), model_cfg.hidden_size
+    dims = [d, H, 1]
+    self.mlp = ReplicaMLP(dims, 'relu', replicas, 1, device)
+    self.device = self.mlp.device
+    self.u = torch.zeros(replicas, H + 1, device=self.device) if self.spectral_norm else None  # layer0 u [H], layer1 u [1]
+    self.v = torch.zeros(replicas, d + H, device=self.device) if self.spectral_norm else None  # layer0 v [d], layer1 v [H]
+    for r in range(replicas):
+      with (rng.replica(r) if rng is not None else _null_ctx()):
+        params, us, vs = [], [], []
+        for l in range(2):  # _create_fcnn order (:52-59,:62-67): Linear, orthogonal_, zero bias, then spectral_norm
+          layer = torch.nn.Linear(dims[l], dims[l + 1])
+          torch.nn.init.orthogonal_(layer.weight, gain=torch.nn.init.calculate_gain('relu') if l == 0 else 1)
+          torch.nn.init.constant_(layer.bias, 0)
+          w = layer.weight.detach()
+          if self.spectral_norm:
+            u_, v_ = _spectral_norm_init(w)
+            us.append(u_)
+            vs.append(v_)
+          params += [w, layer.bias.detach()]
+        self.mlp.load_params(r, 0, params)
+        if self.spectral_norm:
+          self.u[r].copy_(torch.cat(us))
+          self.v[r].copy_(torch.cat(vs))
+    self.training = True
+
+  def c_struct(self) -> _lib.Gail:
+    g = _lib.Gail()
+    g.g = self.mlp.c_struct()
+    if self.spectral_norm:
+      g.u, g.v, g.u_stride, g.v_stride = self.u.data_ptr(), self.v.data_ptr(), self.u.stride(0), self.v.stride(0)
+    g.state_only, g.reward_function = int(self.state_only), _lib.REWARD[self.reward_function]
+    return g
+
+  def _state_items(self):
+    v = self.mlp.layer_views()[0]
+    d, H = self.mlp.dims[0], self.mlp.dims[1]
+    if not self.spectral_norm:
+      return [(f'g.{2 * l}.{n}', v[2 * l + i]) for l in range(2) for i, n in enumerate(('weight', 'bias'))]
+    return [('g.0.bias', v[1]), ('g.0.parametrizations.weight.original', v[0]), ('g.0.parametrizations.weight.0._u', self.u[:, :H]), ('g.0.parametrizations.weight.0._v', self.v[:, :d]),
+            ('g.2.bias', v[3]), ('g.2.parametrizations.weight.original', v[2]), ('g.2.parametrizations.weight.0._u', self.u[:, H:H + 1]),
+            ('g.2.parametrizations.weight.0._v', self.v[:, d:d + H])]
+
+  def _batch_of(self, state: Tensor, action: Tensor) -> TransitionBatch:
+    R = self.replicas
+    s, a = _as_rns(state, R, self.state_size, self.device), _as_rns(action, R, self.action_size, self.device)
+    _, row = _lib.py_row_layout(self.state_size, self.action_size)
+    tb = TransitionBatch(torch.zeros(R, s.size(1), row, device=self.device), self.state_size, self.action_size, False)
+    tb.rows[..., :self.state_size], tb.rows[..., self.state_size:self.state_size + self.action_size] = s, a
+    return tb
+
+  def _run(self, batch: TransitionBatch, reward_out: Optional[Tensor] = None, want_logits: bool = False) -> Dict[str, Tensor]:
+    if self.training and self.spectral_norm: raise RuntimeError('train-mode forward outside adversarial_imitation_update is not supported; call .eval() (train.py:147,180)')
+    R, B = self.replicas, batch.B
+    g, b = self.c_struct(), batch.c_struct()
+    out = {}
+    if reward_out is None: reward_out = torch.empty(R, B, device=self.device)
+    out['reward'] = reward_out
+    if want_logits: out['logits'] = torch.empty(R, B, device=self.device)
+    _lib.check(_lib.lib().il_gail_reward(_lib.handle(), C.byref(g), R, C.byref(b), reward_out.data_ptr(), reward_out.stride(0), reward_out.stride(1), _lib.ptr(out.get('logits')),
+                                         _lib.stream()))
+    return out
+
+  def forward(self, state: Tensor, action: Tensor, next_state=None, terminal=None, log_policy=None) -> Tensor:  # :172-175
+    out = self._run(self._batch_of(state, action), want_logits=True)['logits']
+    return out[0] if self.replicas == 1 else out
+
+  __call__ = forward
+
+  def predict_reward(self, state: Tensor, action: Tensor, next_state=None, terminal=None, log_policy=None) -> Tensor:  # :177-180
+    out = self._run(self._batch_of(state, action))['reward']
+    return out[0] if self.replicas == 1 else out
+
+  def predict_reward_batch(self, batch: TransitionBatch, write_rewards: bool = True) -> Tensor:
+    """Fast path of train.py:194: rewards of a packed batch, written straight into its reward column."""
+    if write_rewards:
+      view = batch.rows[..., batch.off['rewards']]
+      self._run(batch, reward_out=view)
+      return view
+    return self._run(batch)['reward']
+
+
+class GMMILDiscriminator:
+  """:183-201."""
+
+  def __init__(self, state_size: int, action_size: int, imitation_cfg, replicas: int = 1, device=None):
+    self.state_only, self.replicas = bool(imitation_cfg.state_only), replicas
+    self.state_size, self.action_size = state_size, action_size
+    self.device = torch.device('cuda') if device is None else torch.device(device)
+    self.gamma = None  # [R, 2] once set (gamma_1, gamma_2 of :187)
+    self._ws = None
+
+  @property
+  def gamma_1(self): return None if self.gamma is None else (float(self.gamma[0, 0]) if self.replicas == 1 else self.gamma[:, 0])
+
+  @property
+  def gamma_2(self): return None if self.gamma is None else (float(self.gamma[0, 1]) if self.replicas == 1 else self.gamma[:, 1])
+
+  def _pack(self, state, action, weight) -> TransitionBatch:
+    R = self.replicas
+    s, a = _as_rns(state, R, self.state_size, self.device), _as_rns(action, R, self.action_size, self.device)
+    off, row = _lib.py_row_layout(self.state_size, self.action_size)
+    tb = TransitionBatch(torch.zeros(R, s.size(1), row, device=self.device), self.state_size, self.action_size, False)
+    tb.rows[..., :self.state_size], tb.rows[..., self.state_size:self.state_size + self.action_size] = s, a
+    tb.rows[..., off['weights']] = torch.as_tensor(weight, dtype=torch.float32).to(self.device).reshape(R, -1)
+    return tb
+
+  def predict_reward_batch(self, policy: TransitionBatch, expert: TransitionBatch, reward_out: Optional[Tensor] = None) -> Tensor:
+    R, B = self.replicas, policy.B
+    lib, h, p, e = _lib.lib(), _lib.handle(), policy.c_struct(), expert.c_struct()
+    if self.gamma is None:  # :193-195: bandwidths from the first batch, then frozen
+      need = lib.il_gmmil_workspace_bytes(R, B)
+      ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+      self.gamma = torch.empty(R, 2, device=self.device)
+      _lib.check(lib.il_gmmil_bandwidth(h, R, C.byref(p), C.byref(e), int(self.state_only), self.gamma.data_ptr(), ws.data_ptr(), need, _lib.stream()))
+    if reward_out is None: reward_out = torch.empty(R, B, device=self.device)
+    _lib.check(lib.il_gmmil_reward(h, R, C.byref(p), C.byref(e), int(self.state_only), self.gamma.data_ptr(), reward_out.data_ptr(), reward_out.stride(0), reward_out.stride(1),
+                                   _lib.stream()))
+    return reward_out
+
+  def predict_reward(self, state, action, expert_state, expert_action, weight, expert_weight) -> Tensor:
+    out = self.predict_reward_batch(self._pack(state, action, weight), self._pack(expert_state, expert_action, expert_weight))
+    return out[0] if self.replicas == 1 else out
+
+
+class PWILDiscriminator:
+  """:216-249. The expert atoms are shared by all replicas; the remaining-weight vector is per replica."""
+
+  def __init__(self, state_size: int, action_size: int, imitation_cfg, expert_memory: ReplayMemory, time_horizon: int, replicas: int = 1, device=None):
+    self.state_only, self.replicas = bool(imitation_cfg.state_only), replicas
+    self.state_size, self.action_size, self.time_horizon = state_size, action_size, time_horizon
+    self.expert_memory = expert_memory
+    self.device = torch.device('cuda') if device is None else torch.device(device)
+    atoms = self._get_expert_atoms().to(self.device)
+    inv_scale, offset = atoms.std(dim=0, keepdim=True), -atoms.mean(dim=0, keepdim=True)  # :205-208 (one-off setup)
+    inv_scale[inv_scale == 0] = 1
+    self.data_scale, self.data_offset = (1 / inv_scale).contiguous(), offset.contiguous()
+    self.atoms = (self.data_scale * (atoms + self.data_offset)).contiguous()  # :229
+    self.reward_scale = imitation_cfg.reward_scale
+    self.reward_bandwidth = imitation_cfg.reward_bandwidth_scale * time_horizon / sqrt(state_size if self.state_only else state_size + action_size)  # :222
+    self.expert_weights = torch.empty(replicas, self.atoms.size(0), device=self.device)
+    self.reset()
+
+  def _get_expert_atoms(self) -> Tensor:  # :225-226
+    s, a = self.expert_memory['states'], self.expert_memory['actions']
+    return (s if self.state_only else torch.cat([s, a], dim=1)).clone()
+
+  def c_struct(self) -> _lib.Pwil:
+    p = _lib.Pwil()
+    p.atoms, p.scale, p.offset, p.weights = self.atoms.data_ptr(), self.data_scale.data_ptr(), self.data_offset.data_ptr(), self.expert_weights.data_ptr()
+    p.N, p.d, p.S, p.A = self.atoms.size(0), self.atoms.size(1), self.state_size, self.action_size
+    p.state_only, p.time_horizon, p.reward_scale, p.reward_bandwidth = int(self.state_only), self.time_horizon, self.reward_scale, self.reward_bandwidth
+    return p
+
+  def reset(self, mask: Optional[Tensor] = None):  # :228-230
+    p = self.c_struct()
+    _lib.check(_lib.lib().il_pwil_reset(_lib.handle(), C.byref(p), self.replicas, _lib.ptr(mask), _lib.stream()))
+
+  def compute_reward_batch(self, state: Tensor, action: Tensor, out: Optional[Tensor] = None, active: Optional[Tensor] = None) -> Tensor:
+    R = self.replicas
+    s = torch.as_tensor(state, dtype=torch.float32).to(self.device).reshape(R, self.state_size).contiguous()
+    a = torch.as_tensor(action, dtype=torch.float32).to(self.device).reshape(R, self.action_size).contiguous()
+    if out is None: out = torch.empty(R, device=self.device)
+    p = self.c_struct()
+    _lib.check(_lib.lib().il_pwil_reward(_lib.handle(), C.byref(p), R, s.data_ptr(), a.data_ptr(), out.data_ptr(), _lib.ptr(active), _lib.stream()))
+    return out
+
+  def compute_reward(self, state: Tensor, action: Tensor):  # :232-249
+    out = self.compute_reward_batch(state, action)
+    return float(out[0]) if self.replicas == 1 else out
+
+
+def mix_expert_agent_transitions(transitions: TransitionBatch, expert_transitions: TransitionBatch):
+  """:287-290 — first B // 2 rows of every field replaced by expert rows."""
+  b, e = transitions.c_struct(), expert_transitions.c_struct()
+  _lib.check(_lib.lib().il_mix_expert_rows(_lib.handle(), C.byref(b), C.byref(e), transitions.R, _lib.stream()))

@@ -1,0 +1,241 @@
+/*
+ * il_b200.h — C ABI of the B200-native (sm_100a) hot path of Kaixhin/imitation-learning.
+ *
+ * The reference has no FFI: its hot path sits behind Python signatures. Each entry point
+ * below is what a binding for that path would call; the comment on each cites the reference interface it
+ * replaces (paths relative to the reference tree). INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise. fp32 data,
+ *    row-major. All tensors carry a leading REPLICA axis R: replica r is one reference-equivalent run
+ *    (own actor / critic / target / log_alpha / optimiser state / discriminator / replay ring / env);
+ *    R = 1 is exactly the reference's shapes.
+ *  - No allocation, no host synchronisation, CUDA-graph capturable: callers pass workspaces (sizes from the
+ *    *_workspace_bytes queries) and a cudaStream_t (as void*).
+ *  - Return value: 0 on success, non-zero on error (message via il_last_error()). There is NO CPU fallback.
+ *  - All randomness is an explicit input (noise / index tensors). il_fill_normal / il_fill_uniform /
+ *    il_replay_sample_indices generate them on the device (Philox4x32-10) when the caller does not inject.
+ */
+#ifndef IL_B200_H
+#define IL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IL_MAX_LAYERS 6
+
+enum { IL_ACT_RELU = 0, IL_ACT_TANH = 1, IL_ACT_SIGMOID = 2 };          /* models.py:17 ACTIVATION_FUNCTIONS */
+enum { IL_REWARD_AIRL = 0, IL_REWARD_GAIL = 1, IL_REWARD_FAIRL = 2 };    /* models.py:179-180 */
+enum { IL_LOSS_BCE = 0, IL_LOSS_MIXUP = 1, IL_LOSS_PUGAIL = 2 };         /* training.py:94-114 */
+enum { IL_GEMM_FP32 = 0, IL_GEMM_TF32X3 = 1, IL_GEMM_TF32 = 2 };         /* arithmetic of the dense HxH layers */
+
+typedef struct il_handle il_handle;
+
+/* G independent MLPs (`_create_fcnn`, models.py:48-69) in one flat buffer: per net, per layer l:
+ * W_l [dims[l+1], dims[l]] row-major then b_l [dims[l+1]]; every tensor starts on a 4-float boundary
+ * (il_mlp_param_offsets). Net g starts at params + g * stride. A TwinCritic is two consecutive nets. */
+typedef struct il_mlp {
+  float*  params;
+  int64_t stride;
+  int32_t n_layers;                 /* Linear layers = reference depth + 1 */
+  int32_t activation;               /* IL_ACT_* */
+  int32_t dims[IL_MAX_LAYERS + 1];
+  int32_t _pad;
+} il_mlp;
+
+/* torch.optim.Adam / AdamW (decoupled decay) state over one flat parameter buffer (train.py:66,84). */
+typedef struct il_adam {
+  float*   m;                       /* exp_avg, same shape as the parameter buffer */
+  float*   v;                       /* exp_avg_sq */
+  int64_t* step;                    /* device scalar, incremented by every update */
+  double lr, beta1, beta2, eps, weight_decay;  /* Python floats in the reference; kept in double like torch does */
+} il_adam;
+
+/* Packed transitions [R, B, row]: row = [state S | action A | reward | next_state S | terminal | timeout |
+ * weight | step | pad to 4 floats]  (the 8 fields of memory.py:17 as one 128 B row for hopper). */
+typedef struct il_batch {
+  float*  rows;
+  int64_t replica_stride;           /* floats between replicas (0 = one batch shared by all replicas) */
+  int32_t B, S, A, row;
+} il_batch;
+
+/* Replay ring per replica (memory.py:13-23): rows [R, size, row]; idx/full/num_trajectories per replica. */
+typedef struct il_replay {
+  float*   rows;
+  int64_t  replica_stride;          /* 0 = one memory shared by all replicas (expert buffer) */
+  int32_t* idx;                     /* [R] next write position (memory.py:15) */
+  int32_t* full;                    /* [R] ring wrapped (memory.py:43) */
+  int32_t* num_trajectories;        /* [R] (memory.py:44) */
+  int32_t  size, S, A, row;
+  int32_t  absorbing;               /* memory.py:16 */
+  int32_t  shared;                  /* 1: idx/full/num_trajectories have one entry used by all replicas */
+} il_replay;
+
+/* ---- library ----------------------------------------------------------------------------------------- */
+int         il_create(int device, il_handle** out);
+int         il_destroy(il_handle* h);
+const char* il_last_error(void);
+int         il_version(void);
+int         il_set_gemm_mode(il_handle* h, int mode);              /* IL_GEMM_* for the dense hidden layers */
+int64_t     il_launch_count(il_handle* h);                         /* kernels launched by this library so far */
+int         il_struct_sizes(int32_t* out9);                        /* sizeof il_mlp, il_adam, il_batch, il_replay, il_sac_args, il_gail, il_gail_update_args, il_pwil, il_env */
+int         il_mlp_param_offsets(const int32_t* dims, int n_layers, int64_t* w_off, int64_t* b_off, int64_t* total);
+int         il_row_layout(int S, int A, int32_t* offsets8, int32_t* row_len); /* state, action, reward, next_state, terminal, timeout, weight, step */
+
+/* ---- random inputs (replace torch / numpy global RNG draws when noise is not injected) ---------------- */
+int il_fill_normal(il_handle* h, float* out, int64_t n, uint64_t seed, uint64_t stream_id, const uint64_t* counter, void* stream);
+int il_fill_uniform(il_handle* h, float* out, int64_t n, uint64_t seed, uint64_t stream_id, const uint64_t* counter, void* stream);
+int il_counter_add(il_handle* h, uint64_t* counter, uint64_t inc, void* stream);
+
+/* ---- SoftActor (models.py:84-102) --------------------------------------------------------------------- */
+/* forward + tanh-Gaussian head for n states per replica. eps == NULL: greedy (tanh(mean), models.py:101-102).
+ * eps != NULL: action = tanh(mean + std*eps) and log_prob via the cached pre-tanh value (train.py:152,
+ * training.py:20-22,34-36). given_action != NULL: log_prob of that action (models.py:97-99, atanh path).
+ * Outputs may be NULL. workspace: il_actor_workspace_bytes. */
+int64_t il_actor_workspace_bytes(const il_mlp* actor, int R, int n);
+int il_actor_forward(il_handle* h, const il_mlp* actor, int R, int n,
+                     const float* states, int64_t states_rs, int ld_states,
+                     const float* eps, const float* given_action,
+                     float* action, float* log_prob, float* mean, float* log_std,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- TwinCritic (models.py:123-141) -------------------------------------------------------------------- */
+int64_t il_critic_workspace_bytes(const il_mlp* critic, int R, int n);
+int il_critic_forward(il_handle* h, const il_mlp* twin, int R, int n, int S,
+                      const float* states, int64_t states_rs, int ld_states,
+                      const float* actions, int64_t actions_rs, int ld_actions,
+                      float* q1, float* q2, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* update_target_network (models.py:79-81): target = tau*target + (1-tau)*online over n floats. */
+int il_polyak(il_handle* h, float* target, const float* online, int64_t n, float polyak_factor, void* stream);
+
+/* ---- sac_update (training.py:14-54) -------------------------------------------------------------------- */
+typedef struct il_sac_args {
+  il_mlp  actor, critic, target;    /* critic/target: 2R nets (twin), stride = per-net stride */
+  il_adam actor_opt, critic_opt, alpha_opt;
+  float*  log_alpha;                /* [R] */
+  il_batch batch;                   /* transitions (rewards already relabelled by the caller, train.py:194) */
+  const float* absorbing;           /* [R, B] or NULL = states[:, -1] of the batch when batch has absorbing bit */
+  int32_t absorbing_from_state;     /* 1: take absorbing = state[S-1] (memory.py:62); 0 with absorbing == NULL: zeros */
+  int32_t R;
+  const float* eps_next;            /* [R, B, A] noise for training.py:21 */
+  const float* eps_new;             /* [R, B, A] noise for training.py:35 */
+  float discount, entropy_target, polyak_factor;
+  float _pad0;
+  float* out_log_probs;             /* [R, B] new_log_probs (training.py:54) */
+  float* out_q_values;              /* [R, B] min(values_1, values_2) (training.py:54) */
+  float* out_losses;                /* [R, 3] value, policy, temperature loss (may be NULL) */
+  void*   workspace;
+  int64_t workspace_bytes;
+} il_sac_args;
+int64_t il_sac_workspace_bytes(const il_sac_args* a);
+int il_sac_update(il_handle* h, const il_sac_args* a, void* stream);
+
+/* AdamW step over a flat buffer (used by the fused updates; exposed for tests): torch _single_tensor_adam. */
+int il_adam_step(il_handle* h, float* params, const float* grads, const il_adam* opt, int64_t n, void* stream);
+
+/* ---- ReplayMemory (memory.py:12-68) --------------------------------------------------------------------- */
+/* append (memory.py:40-44) of one transition per replica, with the train.py:157-162 flags: `terminal`
+ * (early termination, stored), `timeout`; wrap != 0 applies wrap_for_absorbing_states (memory.py:65-68) to
+ * replicas whose terminal flag is set. active[r] == 0 skips replica r (may be NULL). */
+int il_replay_append(il_handle* h, const il_replay* mem, int R, const float* step, const float* state, const float* action,
+                     const float* reward, const float* next_state, const float* terminal, const float* timeout,
+                     const int32_t* active, int wrap, void* stream);
+/* wrap_for_absorbing_states (memory.py:65-68) on the last appended row of every replica with mask != 0 (NULL = all). */
+int il_replay_wrap_absorbing(il_handle* h, const il_replay* mem, int R, const int32_t* mask, void* stream);
+/* _sample_idx x n (memory.py:51-59): uniform over valid rows, never the newest row. */
+int il_replay_sample_indices(il_handle* h, const il_replay* mem, int R, int n, int32_t* idx_out,
+                             uint64_t seed, uint64_t stream_id, const uint64_t* counter, void* stream);
+/* sample's gather (memory.py:60-62): out.rows[r, i, :] = mem.rows[r, idx[r, i], :] */
+int il_replay_gather(il_handle* h, const il_replay* mem, int R, const int32_t* idx, const il_batch* out, void* stream);
+/* mix_expert_agent_transitions (models.py:287-290): first B/2 rows <- expert rows (all fields). */
+int il_mix_expert_rows(il_handle* h, const il_batch* batch, const il_batch* expert, int R, void* stream);
+
+/* ---- GAILDiscriminator (models.py:152-180), depth-1 `g` network, optional spectral norm ------------------- */
+typedef struct il_gail {
+  il_mlp  g;                        /* R nets, n_layers == 2 (hidden_size x 1), `original` weights */
+  float*  u;                        /* [R, u_stride] spectral-norm left vectors: layer0 [H], layer1 [1] (NULL = no SN) */
+  float*  v;                        /* [R, v_stride] right vectors: layer0 [d], layer1 [H] */
+  int32_t u_stride, v_stride;
+  int32_t state_only;               /* imitation.state_only (models.py:156) */
+  int32_t reward_function;          /* IL_REWARD_* */
+} il_gail;
+typedef struct il_gail_update_args {
+  il_gail  disc;
+  il_adam  opt;                     /* AdamW(imitation.learning_rate, imitation.weight_decay) train.py:84 */
+  il_batch policy, expert;          /* transitions / expert_transitions (train.py:173) */
+  const float* eps_gp;              /* [R, B] U(0,1) (training.py:118); required when grad_penalty > 0 */
+  const float* eps_mix;             /* [R, B] Beta(a,a) draws (training.py:106); required for IL_LOSS_MIXUP */
+  int32_t R;
+  int32_t loss_function;            /* IL_LOSS_* */
+  int32_t training;                 /* discriminator.train() (train.py:178): run the power iterations; 0 = eval-mode forwards */
+  int32_t _pad;
+  float grad_penalty, entropy_bonus, pos_class_prior, nonnegative_margin;
+  float* out_losses;                /* [R, 2] bce/mixup loss, gp loss (may be NULL) */
+  void*   workspace;                /* il_gail_workspace_bytes */
+  int64_t workspace_bytes;
+} il_gail_update_args;
+int64_t il_gail_workspace_bytes(const il_gail_update_args* a);
+/* adversarial_imitation_update (training.py:85-134) incl. the train()/eval() power-iteration semantics. */
+int il_gail_update(il_handle* h, const il_gail_update_args* a, void* stream);
+/* forward logits (models.py:164-175, eval mode) and predict_reward (models.py:177-180); reward/logits may be NULL. */
+int il_gail_reward(il_handle* h, const il_gail* disc, int R, const il_batch* batch, float* reward, int64_t reward_rs, int reward_ld,
+                   float* logits, void* stream);
+
+/* ---- GMMILDiscriminator (models.py:183-201) ------------------------------------------------------------- */
+/* bandwidths (models.py:193-195): gamma[r, 0:2] = 1 / (weighted median + 1e-8). workspace: il_gmmil_workspace_bytes. */
+int64_t il_gmmil_workspace_bytes(int R, int B);
+int il_gmmil_bandwidth(il_handle* h, int R, const il_batch* policy, const il_batch* expert, int state_only, float* gamma,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+int il_gmmil_reward(il_handle* h, int R, const il_batch* policy, const il_batch* expert, int state_only, const float* gamma,
+                    float* reward, int64_t reward_rs, int reward_ld, void* stream);
+
+/* ---- PWILDiscriminator (models.py:216-249) -------------------------------------------------------------- */
+typedef struct il_pwil {
+  const float* atoms;               /* [N, d] normalised expert atoms (models.py:229), shared by all replicas */
+  const float* scale;               /* [d]  (models.py:205-208) */
+  const float* offset;              /* [d] */
+  float*   weights;                 /* [R, N] remaining expert weights; consumed atoms have weight < 0 */
+  int32_t  N, d, S, A;
+  int32_t  state_only, time_horizon;
+  float    reward_scale, reward_bandwidth;
+} il_pwil;
+int il_pwil_reset(il_handle* h, const il_pwil* p, int R, const int32_t* mask, void* stream);   /* models.py:228-230 */
+int il_pwil_reward(il_handle* h, const il_pwil* p, int R, const float* state, const float* action, float* reward,
+                   const int32_t* active, void* stream);                                           /* models.py:232-249 */
+
+/* ---- synthetic batched environment (stands in for environments.py:29-40 gym/MuJoCo stepping) ------------- */
+typedef struct il_env {
+  const float* M;                   /* [obs, obs] */
+  const float* N;                   /* [act, obs] */
+  const float* c;                   /* [obs] */
+  const float* w_r;                 /* [obs] */
+  float*   x;                       /* [n_envs, obs] physical state */
+  int32_t* t;                       /* [n_envs] steps in the current episode */
+  int32_t  obs, act, absorbing, max_episode_steps, early_termination;
+  float    term_threshold;
+} il_env;
+/* reset (environments.py:29-33): x = (2u-1)*0.1 for envs with mask != 0 (mask NULL = all); writes state [n, S].
+ * Envs with mask == 0 keep their state, or receive else_state[i] when else_state != NULL (state <- next_state). */
+int il_env_reset(il_handle* h, const il_env* env, int n_envs, const float* u, const int32_t* mask, float* state, const float* else_state, void* stream);
+/* step (environments.py:35-40): clamp action to [-1,1], advance, reward, done (= terminated OR time limit).
+ * terminal_f / timeout_f (nullable) are the floats train.py:157 stores: done && t != max, t == max.
+ * frozen[i] != 0 leaves env i untouched (finished evaluation episodes). */
+int il_env_step(il_handle* h, const il_env* env, int n_envs, const float* action, float* next_state, float* reward,
+                int32_t* done, int32_t* timeout, float* terminal_f, float* timeout_f, const int32_t* frozen, void* stream);
+
+/* ---- evaluation (evaluation.py:11-35) --------------------------------------------------------------------- */
+/* return accumulation for batched greedy episodes: returns[i] += reward[i] for non-finished episodes, then
+ * finished[i] |= done[i]. n_unfinished (device scalar) receives the number of running episodes. */
+int il_eval_accumulate(il_handle* h, int n_envs, const float* reward, const int32_t* done, float* returns, int32_t* finished,
+                       int32_t* n_unfinished, void* stream);
+/* per-rank statistics vector for the NCCL reduction: out[0:3] = sum, sum of squares, count. */
+int il_return_stats(il_handle* h, const float* returns, int64_t n, float* out3, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IL_B200_H */

@@ -60,9 +60,10 @@ def _batch(rs, B, S, A, absorbing_frac=0.1) -> Dict[str, np.ndarray]:
               weights=np.where(rs.uniform(size=B) < 0.2, 0.5, 1.0).astype(np.float32), absorbing=absb)
 
 
-def make_inputs(name: str) -> Dict[str, np.ndarray]:
+def make_inputs(name: str, seed_offset: int = 0) -> Dict[str, np.ndarray]:
+  """seed_offset != 0 gives an independent input set of the same shapes (used to fill the replica axis)."""
   c = CASES[name]
-  rs = _rs(c['seed'])
+  rs = _rs(c['seed'] + 1000 * seed_offset)
   inp: Dict[str, np.ndarray] = {}
   k = c['kind']
   if k == 'actor':

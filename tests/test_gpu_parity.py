@@ -1,0 +1,61 @@
+"""GPU parity: the CUDA path (through the C ABI) against (1) the committed fixtures generated from the
+unmodified reference and (2) the oracle port on further seeds, with several replicas batched in one call.
+
+Tolerances (fp32, stated per SURVEY §8c): single calls rtol 1e-4 / atol 1e-5 (GEMM summation order and
+CUDA-vs-CPU libm differences); Adam second moments are squares of gradients -> atol scaled down.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import cases
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 2e-4, 2e-5
+
+
+def _tol(name):
+  # the multi-step SAC cases chain updates; q-values / losses are O(1-10), parameters O(0.1)
+  return (RTOL, ATOL)
+
+
+@pytest.mark.parametrize('name', list(cases.CASES))
+def test_cuda_matches_reference_fixture(name):
+  from cuda_cases import run_cuda
+  out = run_cuda(name, [cases.make_inputs(name)])[0]
+  g = load_golden(name)
+  keys = {k.split('@')[0] for k in g} & set(out)
+  assert keys, 'no comparable outputs'
+  rtol, atol = _tol(name)
+  bad = cases.compare(g, out, rtol=rtol, atol=atol, keys=keys)
+  assert not bad, '\n'.join(bad)
+
+
+@pytest.mark.parametrize('name', ['actor_small', 'sac_small', 'sac_small_wd', 'gail_default', 'gail_entropy_nosn', 'gail_pugail', 'gail_mixup', 'gmmil_hopper', 'replay_ring'])
+def test_cuda_matches_oracle_across_replicas(name):
+  """3 replicas with independent inputs in ONE batched call == 3 independent oracle runs."""
+  from cuda_cases import run_cuda
+  inps = [cases.make_inputs(name, seed_offset=r) for r in range(3)]
+  outs = run_cuda(name, inps)
+  rtol, atol = _tol(name)
+  for r in range(3):
+    ref = cases.run_port(name, inps[r])
+    keys = set(ref) & set(outs[r])
+    bad = cases.compare(cases.compress({k: ref[k] for k in keys}), outs[r], rtol=rtol, atol=atol)
+    assert not bad, f'replica {r}:\n' + '\n'.join(bad)
+
+
+def test_pwil_replicas_share_atoms():
+  from cuda_cases import run_cuda
+  name = 'pwil_small'
+  base = cases.make_inputs(name)
+  inps = [base]
+  for r in (1, 2):
+    alt = cases.make_inputs(name, seed_offset=r)
+    inps.append(dict(base, states=alt['states'], actions=alt['actions']))
+  outs = run_cuda(name, inps)
+  for r in range(3):
+    ref = cases.run_port(name, inps[r])
+    np.testing.assert_allclose(outs[r]['rewards'], ref['rewards'], rtol=1e-4, atol=1e-6)
