@@ -1,0 +1,229 @@
+"""Benchmark of the hot path named by BASELINE.json: GAIL Hopper, 1024 replica-envs per GPU (weak scaling over the
+replica axis), one full loop iteration per step = rollout (actor forward, env step, replay append) + replay gather x2
++ discriminator update + reward relabel + SAC update, for every replica. Prints ONE JSON line (see the task contract).
+
+  python bench.py --gpus 1 --steps 20 --warmup 3                      # this arm (B200 kernels)
+  python bench.py --impl reference --gpus 1 --steps 20 --warmup 3     # the reference's CPU path (oracle port loop)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path: sys.path.insert(0, ROOT)
+
+METRIC, UNIT = 'env_steps_per_s', 'env-steps/s'
+
+
+def parse():
+  p = argparse.ArgumentParser()
+  p.add_argument('--gpus', type=int, default=1)
+  p.add_argument('--steps', type=int, default=20)
+  p.add_argument('--warmup', type=int, default=3)
+  p.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  p.add_argument('--algorithm', default='GAIL')
+  p.add_argument('--env', default='hopper')
+  p.add_argument('--replicas', type=int, default=1024, help='replica-envs per GPU')
+  p.add_argument('--batch-size', type=int, default=256)
+  p.add_argument('--start', type=int, default=300, help='update-free prefill steps before the timed region (training.start)')
+  p.add_argument('--gemm-mode', default=os.environ.get('IL_GEMM_MODE', 'fp32'))
+  p.add_argument('--no-e2e', action='store_true')
+  p.add_argument('--no-cpu-baseline', action='store_true')
+  p.add_argument('--ref-steps-per-step', type=int, default=10, help='reference arm: oracle loop iterations per bench step and worker')
+  return p.parse_args()
+
+
+def workload(a):
+  return dict(workload=f'{a.algorithm} {a.env}, {a.replicas} replica-envs per GPU (one reference-equivalent agent + env + replay each), batch {a.batch_size}, '
+                       f'256x2 actor/critic, conf/algorithm/{a.algorithm}.yaml defaults',
+              algorithm=a.algorithm, env=a.env, replicas_per_gpu=a.replicas, batch_size=a.batch_size, parallelism=f'replica-sharded x{a.gpus} (no data-path collective)',
+              l2='working set per step (parameters + Adam state + activations, > 8 GB at 1024 replicas) exceeds the 126 MB L2; no flush needed')
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port loop on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference(a, steps, warmup, procs=None):
+  from oracle import loop
+  procs = procs or (os.cpu_count() or 1)
+  per_worker = max(steps * a.ref_steps_per_step, 1)
+  r = loop.measure_multiprocess(procs, a.algorithm, a.env, steps=per_worker, warmup=max(warmup, 1), batch_size=a.batch_size, prefill=a.start)
+  return r, procs, per_worker
+
+
+def run_reference(a):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0: return
+  import torch
+  r, procs, per_worker = cpu_reference(a, a.steps, a.warmup)
+  value = r['steps_per_s']
+  line = dict(impl='reference', metric=METRIC, value=value, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup, ms_per_step=1e3 * r['seconds'] / a.steps,
+              higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', config=workload(a), grad_updates_per_s=value,
+              cpu_baseline=dict(value=value, unit=UNIT, cores=procs, kind='port',
+                                sample=f'{procs} independent single-thread processes (the reference scaling model, train_all.py:26) x {per_worker} loop iterations each of the oracle port '
+                                       f'(oracle/loop.py) after {a.start} prefill steps; torch {torch.__version__} CPU'),
+              e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+  print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks sampling
+# ------------------------------------------------------------------------------------------------------------------
+class Clocks:
+  FIELDS = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+  def __init__(self, gpu_index):
+    self.rows, self.proc, self.gpu = [], None, gpu_index
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits', '-lms', '100', '-i', str(self.gpu)], stdout=subprocess.PIPE,
+                                   stderr=subprocess.DEVNULL, text=True)
+      threading.Thread(target=self._read, daemon=True).start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout: self.rows.append(line.strip())
+
+  def stop(self):
+    if self.proc is None: return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+    time.sleep(0.15)
+    self.proc.terminate()
+    sm, mx, reasons = [], [], set()
+    for r in self.rows:
+      f = [x.strip() for x in r.split(',')]
+      if len(f) < 9: continue
+      try:
+        sm.append(float(f[1])); mx.append(float(f[2]))
+      except ValueError:
+        continue
+      for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+        if v.lower().startswith('active'): reasons.add(name)
+    sm.sort()
+    return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# this arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_b200(a):
+  import torch
+  import torch.distributed as dist
+  import il_b200
+  from il_b200 import _lib, distributed
+  from il_b200.config import load_config
+  from il_b200.train import Trainer
+  rank, world = distributed.init('nccl')
+  assert world == a.gpus, f'--gpus {a.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run for N > 1)'
+  dev = torch.cuda.current_device()
+  K, W, R = a.steps, max(a.warmup, 3), a.replicas
+  total_steps = a.start + 2 * (W + K) + 64
+  cfg = load_config([f'algorithm={a.algorithm}', f'env={a.env}', f'steps={total_steps}', f'training.start={a.start}', f'training.batch_size={a.batch_size}', 'imitation.trajectories=5',
+                     f'replicas={R}', f'gemm_mode={a.gemm_mode}', f'memory.size={max(total_steps * 2, 4096)}', 'seed=0'])
+  lo, hi = distributed.shard(R * world, rank, world)
+  tr = Trainer(cfg, replicas=R, seed_offset=lo, fast_init=True)
+  for _ in range(a.start - 1): tr.train_step()  # update-free prefill (train.py:171), untimed setup
+  for _ in range(W): tr.train_step()            # warm-up incl. CUDA-graph capture
+  torch.cuda.synchronize()
+
+  def timed(n, e2e=False):
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    distributed.barrier(); torch.cuda.synchronize()
+    launches0 = tr.total_launches()
+    ev0.record()
+    host = None
+    for _ in range(n):
+      tr.train_step()
+      if e2e:  # device -> host read of the step's results (losses, returns)
+        host = (tr.sac_out['losses'].cpu(), tr.gail_losses.cpu(), tr.last_return.cpu())
+    ev1.record()
+    torch.cuda.synchronize(); distributed.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device='cuda')
+    if world > 1: dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()), tr.total_launches() - launches0
+
+  clocks = Clocks(dev)
+  clocks.start()
+  ms, launches = timed(K)
+  clk = clocks.stop()
+  value = R * world * K / (ms / 1e3)
+
+  # ---- per-kernel roofline of the dominant kernel (the dense 256x256 grouped GEMMs), measured with CUDA events around
+  # each launch on the launching stream during 2 extra eager steps
+  roof = None
+  try:
+    roof = measure_dense_gemm(tr, a)
+  except Exception as e:  # never lose the headline number to the diagnostic
+    roof = dict(bound='tensor', achieved=None, peak=None, unit='TFLOP/s', frac=None, traffic=None, error=str(e))
+
+  # ---- end-to-end arm: indices' uniforms drawn by numpy on the host and copied H2D every step, results read back every step
+  e2e = None
+  if not a.no_e2e:
+    tr.device_rng = False
+    tr.graphs.clear()
+    tr.graph_launches = {k: v for k, v in tr.graph_launches.items() if k.endswith('#eager')}
+    for _ in range(W): tr.train_step()
+    ms_e, _ = timed(K, e2e=True)
+    e2e = dict(value=R * world * K / (ms_e / 1e3), unit=UNIT, h2d_bytes_per_step=2 * R * a.batch_size * 4, d2h_bytes_per_step=R * (3 + 2 + 1) * 4, ms_per_step=ms_e / K)
+
+  cpu = None
+  if rank == 0 and world == 1 and not a.no_cpu_baseline:
+    r, procs, per_worker = cpu_reference(a, steps=4, warmup=1)
+    cpu = dict(value=r['steps_per_s'], unit=UNIT, cores=procs, kind='port',
+               sample=f'{procs} single-thread processes x {per_worker} loop iterations of oracle/loop.py ({a.algorithm} {a.env}, batch {a.batch_size}) after {a.start} prefill steps')
+  if rank == 0:
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                data='synthetic', config=workload(a), grad_updates_per_s=value, clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
+                gemm_mode=a.gemm_mode)
+    print(json.dumps(line), flush=True)
+  distributed.barrier()
+
+
+def measure_dense_gemm(tr, a):
+  import ctypes as C
+  import torch
+  from il_b200 import _lib
+  lib, h = _lib.lib(), tr.h
+  if not hasattr(lib, 'il_profile_begin'): return None
+  lib.il_profile_begin.argtypes, lib.il_profile_end.argtypes = [C.c_void_p], [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+  saved = tr.use_graphs
+  tr.use_graphs = False
+  torch.cuda.synchronize()
+  lib.il_profile_begin(h)
+  for _ in range(2): tr.train_step()
+  torch.cuda.synchronize()
+  ms, flops, n = C.c_double(), C.c_double(), C.c_int64()
+  lib.il_profile_end(h, C.byref(ms), C.byref(flops), C.byref(n))
+  tr.use_graphs = saved
+  peaks = {}
+  try:
+    peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+  except Exception:
+    pass
+  bf16 = peaks.get('bf16_tflops_sustained')
+  peak, src = (bf16, 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)') if bf16 else (1400.0, 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)')
+  achieved = flops.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else None
+  traffic = None
+  try:
+    traffic = json.load(open(os.path.join(ROOT, 'profiles', 'dense_gemm_traffic.json'))).get('dram_bytes_per_launch')
+  except Exception:
+    pass
+  return dict(bound='tensor', kernel='grouped dense-layer GEMM (256x256x256 per net, fwd / dX / dW) of the SAC update', achieved=achieved, peak=peak, unit='TFLOP/s',
+              frac=(achieved / peak) if achieved else None, traffic=traffic, launches=int(n.value), avg_launch_ms=ms.value / max(n.value, 1),
+              algorithmic_flops_per_launch=flops.value / max(n.value, 1), peak_source=src, arithmetic=a.gemm_mode)
+
+
+def main():
+  a = parse()
+  if a.impl == 'reference': run_reference(a)
+  else: run_b200(a)
+
+
+if __name__ == '__main__':
+  main()

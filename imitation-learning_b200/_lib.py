@@ -81,6 +81,8 @@ SIGNATURES = {
   'il_struct_sizes': (C.c_int, [P(i32)]),
   'il_mlp_param_offsets': (C.c_int, [P(i32), C.c_int, P(i64), P(i64), P(i64)]),
   'il_row_layout': (C.c_int, [C.c_int, C.c_int, P(i32), P(i32)]),
+  'il_profile_begin': (C.c_int, [vp]),
+  'il_profile_end': (C.c_int, [vp, P(C.c_double), P(C.c_double), P(i64)]),
   'il_fill_normal': (C.c_int, [vp, vp, i64, u64, u64, vp, vp]),
   'il_fill_uniform': (C.c_int, [vp, vp, i64, u64, u64, vp, vp]),
   'il_counter_add': (C.c_int, [vp, vp, u64, vp]),
@@ -94,7 +96,7 @@ SIGNATURES = {
   'il_adam_step': (C.c_int, [vp, vp, vp, P(Adam), i64, vp]),
   'il_replay_append': (C.c_int, [vp, P(Replay), C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]),
   'il_replay_wrap_absorbing': (C.c_int, [vp, P(Replay), C.c_int, vp, vp]),
-  'il_replay_sample_indices': (C.c_int, [vp, P(Replay), C.c_int, C.c_int, vp, u64, u64, vp, vp]),
+  'il_replay_sample_indices': (C.c_int, [vp, P(Replay), C.c_int, C.c_int, vp, vp, u64, u64, vp, vp]),
   'il_replay_gather': (C.c_int, [vp, P(Replay), C.c_int, vp, P(Batch), vp]),
   'il_mix_expert_rows': (C.c_int, [vp, P(Batch), P(Batch), C.c_int, vp]),
   'il_gail_workspace_bytes': (i64, [P(GailUpdateArgs)]),
@@ -107,6 +109,7 @@ SIGNATURES = {
   'il_pwil_reward': (C.c_int, [vp, P(Pwil), C.c_int, vp, vp, vp, vp, vp]),
   'il_env_reset': (C.c_int, [vp, P(Env), C.c_int, vp, vp, vp, vp, vp]),
   'il_env_step': (C.c_int, [vp, P(Env), C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+  'il_rollout_bookkeep': (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
   'il_eval_accumulate': (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp]),
   'il_return_stats': (C.c_int, [vp, vp, i64, vp, vp]),
 }

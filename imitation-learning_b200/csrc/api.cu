@@ -25,6 +25,7 @@ extern "C" int il_create(int device, il_handle** out) {
   h->sm_count = prop.multiProcessorCount;
   h->gemm_mode = IL_GEMM_FP32;
   h->launches = 0;
+  h->profiling = 0;
   *out = h;
   return 0;
 }

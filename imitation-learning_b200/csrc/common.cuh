@@ -5,13 +5,21 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/il_b200.h"
 
+struct ProfiledLaunch {
+  cudaEvent_t start, stop;
+  double flops;
+};
 struct il_handle {
   int device;
   int sm_count;
   int gemm_mode;
   long long launches;
+  int profiling;                        // il_profile_begin/end: CUDA events around every dense-layer GEMM launch
+  std::vector<ProfiledLaunch> profiled;
 };
 
 extern thread_local char g_il_error[512];

@@ -99,6 +99,21 @@ __global__ void eval_accumulate_kernel(int n, const float* __restrict__ reward, 
   if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(n_unfinished, __popc(ballot));
 }
 
+__global__ void rollout_bookkeep_kernel(int n, const float* __restrict__ reward, const int32_t* __restrict__ done, float* __restrict__ running, float* __restrict__ last_return,
+                                        float* __restrict__ return_sum, int32_t* __restrict__ episodes, float* __restrict__ step_f) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float run = running[i] + reward[i];  // train.py:155
+  if (done[i]) {                         // train.py:160-168
+    if (last_return) last_return[i] = run;
+    if (return_sum) return_sum[i] += run;
+    if (episodes) episodes[i] += 1;
+    run = 0.f;
+  }
+  running[i] = run;
+  if (step_f) step_f[i] += 1.f;
+}
+
 __global__ void zero_int_kernel(int32_t* p) { *p = 0; }
 
 // single block: deterministic (sum, sum of squares, count)
@@ -141,6 +156,13 @@ extern "C" int il_env_step(il_handle* h, const il_env* env, int n_envs, const fl
   IL_TRY(check_env(env, "il_env_step"));
   IL_LAUNCH(h, env_step_kernel, (unsigned)(((int64_t)n_envs * 32 + 127) / 128), 128, 0, (cudaStream_t)stream, *env, n_envs, action, next_state, reward, done, timeout, terminal_f,
             timeout_f, frozen);
+  return 0;
+}
+
+extern "C" int il_rollout_bookkeep(il_handle* h, int n_envs, const float* reward, const int32_t* done, float* running, float* last_return, float* return_sum,
+                                   int32_t* episodes, float* step_f, void* stream) {
+  IL_CHECK(h && reward && done && running && n_envs > 0, "il_rollout_bookkeep: bad argument");
+  IL_LAUNCH(h, rollout_bookkeep_kernel, (unsigned)((n_envs + 255) / 256), 256, 0, (cudaStream_t)stream, n_envs, reward, done, running, last_return, return_sum, episodes, step_f);
   return 0;
 }
 

@@ -268,5 +268,42 @@ int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 16) return launch_cfg<16, 128, 1, 8>(h, a, stream);
   if (a.N <= 16) return launch_cfg<128, 16, 8, 1>(h, a, stream);
   if (a.M <= 32) return launch_cfg<32, 128, 2, 8>(h, a, stream);
+  const bool dense = a.M >= 128 && a.N >= 128 && a.K >= 128;  // the H x H hidden-layer contractions
+  if (h->profiling && dense) {
+    ProfiledLaunch pl;
+    IL_CUDA(cudaEventCreate(&pl.start));
+    IL_CUDA(cudaEventCreate(&pl.stop));
+    pl.flops = 2.0 * a.M * a.N * a.K * a.G;
+    IL_CUDA(cudaEventRecord(pl.start, stream));
+    const int rc = launch_cfg<128, 128, 8, 8>(h, a, stream);
+    IL_CUDA(cudaEventRecord(pl.stop, stream));
+    h->profiled.push_back(pl);
+    return rc;
+  }
   return launch_cfg<128, 128, 8, 8>(h, a, stream);
+}
+
+extern "C" int il_profile_begin(il_handle* h) {
+  IL_CHECK(h, "il_profile_begin: null handle");
+  h->profiled.clear();
+  h->profiling = 1;
+  return 0;
+}
+
+extern "C" int il_profile_end(il_handle* h, double* total_ms, double* total_flops, int64_t* launches) {
+  IL_CHECK(h && total_ms && total_flops && launches, "il_profile_end: null argument");
+  h->profiling = 0;
+  IL_CUDA(cudaDeviceSynchronize());
+  double ms = 0.0, fl = 0.0;
+  for (auto& pl : h->profiled) {
+    float e = 0.f;
+    IL_CUDA(cudaEventElapsedTime(&e, pl.start, pl.stop));
+    ms += e;
+    fl += pl.flops;
+    cudaEventDestroy(pl.start);
+    cudaEventDestroy(pl.stop);
+  }
+  *total_ms = ms; *total_flops = fl; *launches = (int64_t)h->profiled.size();
+  h->profiled.clear();
+  return 0;
 }

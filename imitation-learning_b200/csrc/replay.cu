@@ -80,22 +80,29 @@ __global__ void replay_wrap_kernel(il_replay mem, int R, const int32_t* __restri
 }
 
 // memory.py:51-59: uniform over [0, size) (full) or [0, idx-1) (not full), never the newest row (idx-1) % size.
-__global__ void replay_sample_idx_kernel(il_replay mem, int R, int n, int32_t* __restrict__ out, uint64_t seed, uint64_t stream_id, const uint64_t* __restrict__ counter) {
+__global__ void replay_sample_idx_kernel(il_replay mem, int R, int n, int32_t* __restrict__ out, const float* __restrict__ uniform, uint64_t seed, uint64_t stream_id,
+                                         const uint64_t* __restrict__ counter) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)R * n) return;
   const int r = (int)(i / n);
   const int mi = mem.shared ? 0 : r;
   const int idx = mem.idx[mi], full = mem.full[mi];
-  const uint64_t c = (counter ? *counter : 0ull) + (uint64_t)i;
-  const uint4 rnd = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32)), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  uint32_t bits;
+  if (uniform) {  // host-drawn U[0,1) (the reference draws on the host: memory.py:54)
+    const float u = fminf(fmaxf(uniform[i], 0.f), 0.99999994f);
+    bits = (uint32_t)(u * 4294967296.f);
+  } else {
+    const uint64_t c = (counter ? *counter : 0ull) + (uint64_t)i;
+    bits = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32)), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))).x;
+  }
   int j;
   if (full) {
     const int newest = (idx - 1 + mem.size) % mem.size;
-    j = (int)(((uint64_t)rnd.x * (uint64_t)(mem.size - 1)) >> 32);
+    j = (int)(((uint64_t)bits * (uint64_t)(mem.size - 1)) >> 32);
     if (j >= newest) j += 1;
   } else {
     const int count = idx - 1 > 0 ? idx - 1 : 1;
-    j = (int)(((uint64_t)rnd.x * (uint64_t)count) >> 32);
+    j = (int)(((uint64_t)bits * (uint64_t)count) >> 32);
   }
   out[i] = j;
 }
@@ -158,11 +165,11 @@ extern "C" int il_replay_wrap_absorbing(il_handle* h, const il_replay* mem, int 
   return 0;
 }
 
-extern "C" int il_replay_sample_indices(il_handle* h, const il_replay* mem, int R, int n, int32_t* idx_out, uint64_t seed, uint64_t stream_id, const uint64_t* counter,
-                                        void* stream) {
+extern "C" int il_replay_sample_indices(il_handle* h, const il_replay* mem, int R, int n, int32_t* idx_out, const float* uniform, uint64_t seed, uint64_t stream_id,
+                                        const uint64_t* counter, void* stream) {
   IL_CHECK(h && idx_out && R > 0 && n > 0, "il_replay_sample_indices: bad argument");
   IL_TRY(check_replay(mem, "il_replay_sample_indices"));
-  IL_LAUNCH(h, replay_sample_idx_kernel, (unsigned)(((int64_t)R * n + 255) / 256), 256, 0, (cudaStream_t)stream, *mem, R, n, idx_out, seed, stream_id, counter);
+  IL_LAUNCH(h, replay_sample_idx_kernel, (unsigned)(((int64_t)R * n + 255) / 256), 256, 0, (cudaStream_t)stream, *mem, R, n, idx_out, uniform, seed, stream_id, counter);
   return 0;
 }
 

@@ -208,13 +208,15 @@ class ReplayMemory:
     _lib.check(_lib.lib().il_replay_gather(_lib.handle(), C.byref(m), R, idx.data_ptr(), C.byref(b), _lib.stream()))
     return out
 
-  def sample_indices_device(self, n: int, out: Optional[Tensor] = None, stream_id: int = 0) -> Tensor:
-    """Device Philox version of `_sample_idx` x n (same distribution; used when indices are not injected)."""
+  def sample_indices_device(self, n: int, out: Optional[Tensor] = None, stream_id: int = 0, uniform: Optional[Tensor] = None) -> Tensor:
+    """`_sample_idx` x n on the device (same distribution as memory.py:51-56). `uniform` ([R, n] U[0,1) floats, e.g.
+    drawn by numpy on the host like the reference) replaces the device Philox draws."""
     R = self.replicas
     if out is None: out = torch.empty(R, n, dtype=torch.int32, device=self.device)
     m = self.c_struct()
-    _lib.check(_lib.lib().il_replay_sample_indices(_lib.handle(), C.byref(m), R, n, out.data_ptr(), self.seed, stream_id, self._rng_counter.data_ptr(), _lib.stream()))
-    _lib.check(_lib.lib().il_counter_add(_lib.handle(), self._rng_counter.data_ptr(), R * n, _lib.stream()))
+    _lib.check(_lib.lib().il_replay_sample_indices(_lib.handle(), C.byref(m), R, n, out.data_ptr(), _lib.ptr(uniform), self.seed, stream_id, self._rng_counter.data_ptr(),
+                                                   _lib.stream()))
+    if uniform is None: _lib.check(_lib.lib().il_counter_add(_lib.handle(), self._rng_counter.data_ptr(), R * n, _lib.stream()))
     return out
 
   def sample(self, n: int, device_rng: bool = False) -> TransitionBatch:

@@ -85,6 +85,12 @@ int         il_struct_sizes(int32_t* out9);                        /* sizeof il_
 int         il_mlp_param_offsets(const int32_t* dims, int n_layers, int64_t* w_off, int64_t* b_off, int64_t* total);
 int         il_row_layout(int S, int A, int32_t* offsets8, int32_t* row_len); /* state, action, reward, next_state, terminal, timeout, weight, step */
 
+/* Measurement aid for bench.py: between begin/end (eager launches, no graph capture) every dense hidden-layer GEMM launch
+ * is bracketed by CUDA events on its own stream; end() synchronises and returns the summed device time, the summed
+ * algorithmic FLOPs (2 M N K G per launch) and the number of launches. */
+int il_profile_begin(il_handle* h);
+int il_profile_end(il_handle* h, double* total_ms, double* total_flops, int64_t* launches);
+
 /* ---- random inputs (replace torch / numpy global RNG draws when noise is not injected) ---------------- */
 int il_fill_normal(il_handle* h, float* out, int64_t n, uint64_t seed, uint64_t stream_id, const uint64_t* counter, void* stream);
 int il_fill_uniform(il_handle* h, float* out, int64_t n, uint64_t seed, uint64_t stream_id, const uint64_t* counter, void* stream);
@@ -146,8 +152,9 @@ int il_replay_append(il_handle* h, const il_replay* mem, int R, const float* ste
                      const int32_t* active, int wrap, void* stream);
 /* wrap_for_absorbing_states (memory.py:65-68) on the last appended row of every replica with mask != 0 (NULL = all). */
 int il_replay_wrap_absorbing(il_handle* h, const il_replay* mem, int R, const int32_t* mask, void* stream);
-/* _sample_idx x n (memory.py:51-59): uniform over valid rows, never the newest row. */
-int il_replay_sample_indices(il_handle* h, const il_replay* mem, int R, int n, int32_t* idx_out,
+/* _sample_idx x n (memory.py:51-59): uniform over valid rows, never the newest row. uniform != NULL: [R, n]
+ * U[0,1) draws supplied by the caller (e.g. numpy on the host, like the reference) instead of device Philox. */
+int il_replay_sample_indices(il_handle* h, const il_replay* mem, int R, int n, int32_t* idx_out, const float* uniform,
                              uint64_t seed, uint64_t stream_id, const uint64_t* counter, void* stream);
 /* sample's gather (memory.py:60-62): out.rows[r, i, :] = mem.rows[r, idx[r, i], :] */
 int il_replay_gather(il_handle* h, const il_replay* mem, int R, const int32_t* idx, const il_batch* out, void* stream);
@@ -226,6 +233,12 @@ int il_env_reset(il_handle* h, const il_env* env, int n_envs, const float* u, co
  * frozen[i] != 0 leaves env i untouched (finished evaluation episodes). */
 int il_env_step(il_handle* h, const il_env* env, int n_envs, const float* action, float* next_state, float* reward,
                 int32_t* done, int32_t* timeout, float* terminal_f, float* timeout_f, const int32_t* frozen, void* stream);
+
+/* training-loop bookkeeping of train.py:155,165-168 for R envs: running[i] += reward[i]; where done[i]: last_return[i] =
+ * running[i], return_sum[i] += running[i], episodes[i] += 1, running[i] = 0. Also step_f[i] += 1 (the `step` stored by
+ * memory.append, train.py:157) when step_f != NULL. */
+int il_rollout_bookkeep(il_handle* h, int n_envs, const float* reward, const int32_t* done, float* running, float* last_return,
+                        float* return_sum, int32_t* episodes, float* step_f, void* stream);
 
 /* ---- evaluation (evaluation.py:11-35) --------------------------------------------------------------------- */
 /* return accumulation for batched greedy episodes: returns[i] += reward[i] for non-finished episodes, then

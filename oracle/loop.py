@@ -1,0 +1,179 @@
+"""TEST INFRASTRUCTURE ONLY — the reference's training loop (train.py:146-227) restated around the oracle port
+(oracle/port.py) on the CPU twin of the synthetic environment. One instance = one reference process (one env, one
+agent, one update per env step). Used (a) by the k-step loop parity tests with injected noise and (b) as the CPU
+baseline / `bench.py --impl reference` arm (train.py, environments.py, utils.py of the reference need hydra / gym /
+d4rl / matplotlib, which are not installed, so the loop itself cannot be imported — SURVEY.md §8c)."""
+from __future__ import annotations
+
+import math
+import time
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import port
+
+
+class NoiseSource:
+  """Default noise: the reference's own RNG calls (torch global RNG for policy / GP noise, numpy global RNG for
+  replay indices, a per-env generator for resets). Tests replace the methods to inject recorded noise."""
+
+  def __init__(self, seed: int, obs: int):
+    self.gen = torch.Generator().manual_seed(seed)
+    self.obs = obs
+
+  def reset_u(self): return torch.rand(self.obs, generator=self.gen)
+  def act_eps(self, A): return torch.randn(1, A)
+  def policy_indices(self, mem, n): return mem.draw_indices(n)
+  def expert_indices(self, mem, n): return mem.draw_indices(n)
+  def gp_eps(self, B): return torch.rand(B)
+  def sac_eps(self, B, A): return torch.randn(B, A), torch.randn(B, A)
+
+
+class OracleLoop:
+  def __init__(self, algorithm: str = 'GAIL', env_name: str = 'hopper', seed: int = 0, batch_size: int = 256, start: int = 1000, memory_size: int = 100000,
+               hidden_size: int = 256, depth: int = 2, lr: float = 3e-4, weight_decay: float = 0.0, trajectories: int = 5, subsample: int = 1, absorbing: bool = True,
+               mix_expert_data: str = 'none', imitation: Optional[dict] = None, discount: Optional[float] = None, polyak: Optional[float] = None,
+               target_temperature: Optional[float] = None, max_episode_steps: int = 1000, expert_raw: Optional[Dict[str, torch.Tensor]] = None, init: Optional[dict] = None):
+    gail = algorithm == 'GAIL'
+    self.algorithm, self.B, self.start, self.absorbing, self.mix = algorithm, batch_size, start, absorbing, mix_expert_data
+    self.discount = (0.97 if gail else 0.99) if discount is None else discount  # GAIL.yaml:5 / train_config.yaml:36
+    self.polyak = (0.99 if gail else 0.995) if polyak is None else polyak  # GAIL.yaml:7 / train_config.yaml:38
+    tt = (-0.5 if gail else -1.0) if target_temperature is None else target_temperature  # GAIL.yaml:6 / train_config.yaml:37
+    self.im = dict(hidden_size=64, learning_rate=3e-5, weight_decay=10.0, grad_penalty=1.0, spectral_norm=True, entropy_bonus=0.0, loss_function='BCE', reward_function='AIRL',
+                   reward_scale=5.0, reward_bandwidth_scale=5.0)  # GAIL.yaml:8-27, PWIL.yaml:4-6
+    self.im.update(imitation or {})
+    np.random.seed(seed)
+    torch.manual_seed(seed)  # train.py:51-52
+    self.env = port.SyntheticEnv(env_name, absorbing, max_episode_steps)
+    self.noise = NoiseSource(seed, self.env.obs)
+    S, A = self.env.state_size, self.env.act
+    self.S, self.A = S, A
+    self.expert_memory = None
+    if algorithm != 'SAC':
+      raw = expert_raw if expert_raw is not None else synthesize_raw_dataset(env_name, absorbing, max(trajectories, 5), max_episode_steps)
+      tr = port.build_expert_transitions(raw, trajectories, subsample, absorbing)
+      self.expert_memory = port.Replay(tr['states'].size(0), S, A, absorbing, transitions=tr)
+    # train.py:64-66 (construction order fixes the RNG stream: actor, critic_1, critic_2, then the discriminator)
+    sizes_a, sizes_c = [S] + [hidden_size] * depth + [2 * A], [S + A] + [hidden_size] * depth + [1]
+    if init is None:
+      actor, twin = port.init_mlp(sizes_a), [port.init_mlp(sizes_c), port.init_mlp(sizes_c)]
+    else:
+      actor, twin = init['actor'], init['twin']
+    self.agent = port.SacAgent(actor, twin, lr=lr, weight_decay=weight_decay)
+    self.entropy_target = tt * A  # train.py:65
+    self.memory = port.Replay(memory_size, S, A, absorbing)
+    self.disc = None
+    if gail:
+      H = self.im['hidden_size']
+      if init is None or 'g' not in init:
+        g, sn = [], []
+        for l, (i, o) in enumerate(((S + A, H), (H, 1))):  # models.py:162 via _create_fcnn with spectral_norm
+          p = port.init_mlp([i, o], final_gain=math.sqrt(2) if l == 0 else 1.0)
+          g += p
+          if self.im['spectral_norm']: sn.append(port.spectral_norm_init(p[0]))
+      else:
+        g, sn = init['g'], init.get('sn')
+      self.disc = port.GailDiscriminator(g, sn if self.im['spectral_norm'] else None, self.discount, reward_function=self.im['reward_function'])
+      self.disc_opt = torch.optim.AdamW(self.disc.parameters(), lr=self.im['learning_rate'], weight_decay=self.im['weight_decay'])  # train.py:84
+    elif algorithm == 'GMMIL':
+      self.disc = port.GmmilDiscriminator()
+    elif algorithm == 'PWIL':
+      self.disc = port.PwilDiscriminator(self.expert_memory.data['states'], self.expert_memory.data['actions'], max_episode_steps, self.im['reward_scale'],
+                                         self.im['reward_bandwidth_scale'])
+    self.t, self.train_return, self.step = 0, 0.0, 0
+    self.state = self.env.reset(self.noise.reset_u())  # train.py:146
+    self.episode_returns = []
+    self.last = {}
+
+  def run_step(self):
+    """One iteration of train.py:149-211."""
+    self.step += 1
+    step, env, agent = self.step, self.env, self.agent
+    with torch.inference_mode():  # train.py:151-158
+      action, _ = port.actor_sample(agent.actor, self.state, self.noise.act_eps(self.A))
+      next_state, reward, terminal = env.step(action)
+      self.t += 1
+      self.train_return += reward
+      if self.algorithm == 'PWIL': reward = self.disc.compute_reward(self.state, action)
+      self.memory.append(step, self.state[0], action[0], reward, next_state[0], terminal and self.t != env.max_episode_steps, self.t == env.max_episode_steps)
+      self.state = next_state
+    if terminal:  # train.py:161-168
+      if self.absorbing and self.t != env.max_episode_steps: self.memory.wrap_for_absorbing_states()
+      if self.algorithm == 'PWIL': self.disc.reset()
+      self.episode_returns.append(self.train_return)
+      self.t, self.state, self.train_return = 0, env.reset(self.noise.reset_u()), 0.0
+    if step >= self.start:  # train.py:171 (interval 1)
+      B = self.B
+      transitions = self.memory.gather(self.noise.policy_indices(self.memory, B))
+      expert = self.expert_memory.gather(self.noise.expert_indices(self.expert_memory, B)) if self.expert_memory is not None else None
+      if self.algorithm == 'GAIL':  # train.py:177-180
+        self.last['gail'] = port.gail_update(self.disc, self.disc_opt, transitions, expert, self.noise.gp_eps(B), loss_function=self.im['loss_function'],
+                                             grad_penalty=self.im['grad_penalty'], entropy_bonus=self.im['entropy_bonus'])
+      if self.algorithm in ('GAIL', 'GMMIL'):
+        if self.mix == 'mixed_batch': port.mix_expert_agent_transitions(transitions, expert)  # train.py:183
+        with torch.inference_mode():
+          if self.algorithm == 'GAIL': rewards = self.disc.predict_reward(transitions['states'], transitions['actions'])  # train.py:194
+          else: rewards = self.disc.predict_reward(transitions['states'], transitions['actions'], expert['states'], expert['actions'], transitions['weights'], expert['weights'])
+        transitions['rewards'] = rewards.clone()
+      e1, e2 = self.noise.sac_eps(B, self.A)
+      self.last['sac'] = port.sac_update(agent, transitions, e1, e2, self.discount, self.entropy_target, self.polyak)  # train.py:203
+      self.last['rewards'] = transitions['rewards']
+
+  def prefill(self, n: int):
+    """Runs the warm-up phase of train.py:171 (`training.start` env steps without updates)."""
+    start, self.start = self.start, 1 << 60
+    for _ in range(n): self.run_step()
+    self.start = start
+
+
+def synthesize_raw_dataset(env_name: str, absorbing: bool, episodes: int, max_episode_steps: int = 1000) -> Dict[str, torch.Tensor]:
+  """CPU twin of the product's expert-data synthesis: `episodes` greedy rollouts of the fixed tanh-MLP expert."""
+  env = port.SyntheticEnv(env_name, absorbing, max_episode_steps)
+  expert = port.expert_policy_params(env_name, absorbing)
+  g = torch.Generator().manual_seed(977 + port.ENVS.index(env_name))
+  u = torch.rand(episodes, env.obs, generator=g)
+  obs, act, nobs, rew, term, tout = [], [], [], [], [], []
+  with torch.inference_mode():
+    for e in range(episodes):
+      s, done = env.reset(u[e]), False
+      while not done:
+        a = port.actor_greedy_action(expert, s, 'tanh')
+        ns, r, done = env.step(a)
+        obs.append(s[0, :env.obs]); act.append(a[0]); nobs.append(ns[0, :env.obs]); rew.append(r)
+        term.append(float(done and env.t != env.max_episode_steps)); tout.append(float(env.t == env.max_episode_steps))
+        s = ns
+  return dict(observations=torch.stack(obs), actions=torch.stack(act), next_observations=torch.stack(nobs), rewards=torch.tensor(rew), terminals=torch.tensor(term),
+              timeouts=torch.tensor(tout))
+
+
+def measure_steps_per_second(algorithm: str = 'GAIL', env_name: str = 'hopper', steps: int = 200, warmup: int = 10, seed: int = 0, batch_size: int = 256, prefill: int = 300,
+                             threads: Optional[int] = None, max_episode_steps: int = 1000) -> Dict[str, float]:
+  """Times `steps` full loop iterations (rollout + discriminator update + relabel + SAC update) of ONE reference
+  process after `prefill` update-free steps; returns steps/s (= env-steps/s = grad-updates/s)."""
+  if threads is not None: torch.set_num_threads(threads)
+  loop = OracleLoop(algorithm, env_name, seed=seed, batch_size=batch_size, start=prefill + 1, max_episode_steps=max_episode_steps)
+  loop.prefill(prefill)
+  for _ in range(warmup): loop.run_step()
+  t0 = time.perf_counter()
+  for _ in range(steps): loop.run_step()
+  dt = time.perf_counter() - t0
+  return dict(steps_per_s=steps / dt, seconds=dt, steps=steps, threads=torch.get_num_threads())
+
+
+def _worker(args):
+  algorithm, env_name, steps, warmup, seed, batch_size, prefill = args
+  torch.set_num_threads(1)
+  return measure_steps_per_second(algorithm, env_name, steps, warmup, seed, batch_size, prefill, threads=1)
+
+
+def measure_multiprocess(n_procs: int, algorithm: str = 'GAIL', env_name: str = 'hopper', steps: int = 200, warmup: int = 10, batch_size: int = 256, prefill: int = 300) -> Dict[str, float]:
+  """The reference's own scaling model (train_all.py:26: one process per run): `n_procs` independent single-thread
+  processes; aggregate steps/s = n_procs * steps / slowest wall time."""
+  import torch.multiprocessing as mp
+  ctx = mp.get_context('spawn')
+  with ctx.Pool(n_procs) as pool:
+    res = pool.map(_worker, [(algorithm, env_name, steps, warmup, s, batch_size, prefill) for s in range(n_procs)])
+  slowest = max(r['seconds'] for r in res)
+  return dict(steps_per_s=n_procs * steps / slowest, seconds=slowest, steps=steps, procs=n_procs)

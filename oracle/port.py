@@ -476,6 +476,7 @@ def mix_expert_agent_transitions(transitions: Dict[str, Tensor], expert: Dict[st
 ENV_DIMS = {'ant': (111, 8), 'halfcheetah': (17, 6), 'hopper': (11, 3), 'walker2d': (17, 6)}  # obs (without absorbing bit), act
 ENVS = ['ant', 'halfcheetah', 'hopper', 'walker2d']  # environments.py:17
 EARLY_TERMINATION = {'ant': True, 'halfcheetah': False, 'hopper': True, 'walker2d': True}
+TERM_THRESHOLD = {'ant': 0.85, 'halfcheetah': 2.0, 'hopper': 0.72, 'walker2d': 0.85}  # |x'_0| above this ends the episode early
 
 
 def synthetic_env_params(env_name: str) -> Dict[str, Tensor]:
@@ -492,11 +493,11 @@ def synthetic_env_params(env_name: str) -> Dict[str, Tensor]:
 class SyntheticEnv:
   """CPU twin of the device environment; same call surface as D4RLEnv (environments.py:29-61), B = 1."""
 
-  def __init__(self, env_name: str, absorbing: bool, max_episode_steps: int = 1000, term_threshold: float = 0.98):
+  def __init__(self, env_name: str, absorbing: bool, max_episode_steps: int = 1000, term_threshold: Optional[float] = None):
     self.p = synthetic_env_params(env_name)
     self.obs, self.act = ENV_DIMS[env_name]
     self.absorbing, self.max_episode_steps = absorbing, max_episode_steps
-    self.early, self.thr = EARLY_TERMINATION[env_name], term_threshold
+    self.early, self.thr = EARLY_TERMINATION[env_name], (TERM_THRESHOLD[env_name] if term_threshold is None else term_threshold)
     self.x, self.t = None, 0
     self.reset_noise = None  # iterator of [obs] U(0,1) draws, injected
 

@@ -1,0 +1,103 @@
+"""k-step loop parity (SURVEY §4 "integration"): the replica-batched Trainer (rollout + replay + discriminator
+update + relabel + SAC update, train.py:149-203) against independent oracle loops, every noise draw and replay
+index injected identically on both sides, identical initial weights. fp32 rounding differences amplify through the
+loop (SURVEY §7 "chaotic divergence"), so the tolerance is looser than for single calls."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class _Injected:
+  """Noise source for the oracle loop that replays pre-drawn arrays (one per call, in order)."""
+
+  def __init__(self, seq): self.seq = seq
+  def _pop(self, k): return self.seq[k].pop(0)
+  def reset_u(self): return self._pop('reset_u')
+  def act_eps(self, A): return self._pop('act_eps')
+  def policy_indices(self, mem, n): return self._pop('idx_pol')
+  def expert_indices(self, mem, n): return self._pop('idx_exp')
+  def gp_eps(self, B): return self._pop('eps_gp')
+  def sac_eps(self, B, A): return self._pop('eps_next'), self._pop('eps_new')
+
+
+def _run(algorithm, env_name, steps, start, B, H, extra=()):
+  import il_b200
+  from il_b200.config import load_config
+  from il_b200.train import Trainer
+  from oracle import loop as oloop, port
+  R = 2
+  cfg = load_config([f'algorithm={algorithm}', f'env={env_name}', f'steps={steps}', f'training.start={start}', f'training.batch_size={B}', 'imitation.trajectories=2',
+                     f'reinforcement.actor.hidden_size={H}', f'reinforcement.critic.hidden_size={H}', 'cuda_graphs=false', f'replicas={R}', 'seed=3', *extra])
+  tr = Trainer(cfg, replicas=R)
+  tr.inject = True
+  rs = np.random.RandomState(123)
+  S, A, obs = tr.S, tr.A, tr.env.obs
+  expert_raw = tr.env.synthesize_raw_dataset(5) if algorithm != 'SAC' else None
+  loops = []
+  for r in range(R):
+    init = dict(actor=tr.actor.mlp.export_params(r, 0), twin=[tr.critic.mlp.export_params(r, 0), tr.critic.mlp.export_params(r, 1)])
+    if algorithm == 'GAIL':
+      d, Hd = S + A, tr.discriminator.mlp.dims[1]
+      init['g'] = tr.discriminator.mlp.export_params(r, 0)
+      init['sn'] = [(tr.discriminator.u[r, :Hd].cpu().clone(), tr.discriminator.v[r, :d].cpu().clone()), (tr.discriminator.u[r, Hd:Hd + 1].cpu().clone(), tr.discriminator.v[r, d:d + Hd].cpu().clone())]
+    lp = oloop.OracleLoop(algorithm, env_name, seed=3 + r, batch_size=B, start=start, memory_size=cfg.memory.size, hidden_size=H, trajectories=2, expert_raw=expert_raw, init=init,
+                          mix_expert_data=cfg.imitation.mix_expert_data)
+    loops.append(lp)
+  if algorithm != 'SAC':  # same expert buffer on both sides
+    np.testing.assert_allclose(tr.expert_memory.states.cpu().numpy(), loops[0].expert_memory.data['states'].numpy(), rtol=1e-4, atol=1e-5)
+    Ne = tr.expert_memory.size
+  # identical initial env state
+  u0 = rs.uniform(size=(R, obs)).astype(np.float32)
+  tr.env.batch.reset(torch.from_numpy(u0).cuda(), tr.state)
+  for r, lp in enumerate(loops): lp.state, lp.t = lp.env.reset(torch.from_numpy(u0[r])), 0
+  max_err = {}
+  for step in range(1, steps + 1):
+    noise = dict(act_eps=rs.standard_normal((R, A)).astype(np.float32), reset_u=rs.uniform(size=(R, obs)).astype(np.float32), eps_gp=rs.uniform(size=(R, B)).astype(np.float32),
+                 eps_next=rs.standard_normal((R, B, A)).astype(np.float32), eps_new=rs.standard_normal((R, B, A)).astype(np.float32))
+    upd = step >= start
+    if upd:
+      # indices valid on both sides: below (idx before this step's append) - 1, a subset of the reference's range
+      noise['idx_pol'] = np.stack([rs.randint(0, max(lp.memory.idx - 1, 1), size=B) for lp in loops]).astype(np.int32)
+      if algorithm != 'SAC': noise['idx_exp'] = rs.randint(0, Ne - 1, size=(R, B)).astype(np.int32)
+    tr.eps_act.copy_(torch.from_numpy(noise['act_eps']))
+    tr.u_reset.copy_(torch.from_numpy(noise['reset_u']))
+    if upd:
+      tr.idx_pol.copy_(torch.from_numpy(noise['idx_pol']))
+      if algorithm != 'SAC': tr.idx_exp.copy_(torch.from_numpy(noise['idx_exp']))
+      tr.eps_gp.copy_(torch.from_numpy(noise['eps_gp']))
+      tr.eps_next.copy_(torch.from_numpy(noise['eps_next']))
+      tr.eps_new.copy_(torch.from_numpy(noise['eps_new']))
+    tr.train_step()
+    for r, lp in enumerate(loops):
+      seq = {k: [torch.from_numpy(np.asarray(v[r]))] for k, v in noise.items()}
+      seq['act_eps'] = [torch.from_numpy(noise['act_eps'][r:r + 1])]
+      lp.noise = _Injected(seq)
+      lp.run_step()
+    # compare state trajectories and (after updates) losses / parameters
+    for r, lp in enumerate(loops):
+      err = float((tr.state[r].cpu() - lp.state[0]).abs().max())
+      max_err['state'] = max(max_err.get('state', 0), err)
+      assert int(tr.memory._idx[r]) == lp.memory.idx, f'step {step} replica {r}: ring index {int(tr.memory._idx[r])} vs {lp.memory.idx}'
+      if upd:
+        e = float((tr.sac_out['q_values'][r].cpu() - lp.last['sac']['q_values']).abs().max())
+        max_err['q'] = max(max_err.get('q', 0), e)
+        e = float((tr.batch['rewards'][r].cpu() - lp.last['rewards']).abs().max())
+        max_err['reward'] = max(max_err.get('reward', 0), e)
+  for r, lp in enumerate(loops):
+    for i, p in enumerate(lp.agent.actor):
+      e = float((tr.actor.mlp.layer_views()[0][i][r].cpu() - p.detach()).abs().max())
+      max_err['actor'] = max(max_err.get('actor', 0), e)
+  return max_err
+
+
+@pytest.mark.parametrize('algorithm,env_name,extra', [('GAIL', 'hopper', ()), ('SAC', 'hopper', ()), ('GMMIL', 'halfcheetah', ()), ('PWIL', 'hopper', ()),
+                                                      ('GAIL', 'walker2d', ('imitation.mix_expert_data=mixed_batch', ))])
+def test_loop_matches_oracle(algorithm, env_name, extra):
+  err = _run(algorithm, env_name, steps=60, start=30, B=32, H=64, extra=extra)
+  print(algorithm, env_name, err)
+  assert err['state'] < 2e-3, err
+  assert err.get('q', 0) < 5e-3, err
+  assert err.get('reward', 0) < 5e-3, err
+  assert err['actor'] < 5e-4, err
