@@ -218,7 +218,7 @@ class Trainer:
     self.step += 1
     if self._will_update(self.step):
       if not self.device_rng:  # host-drawn index uniforms, like the reference's np.random draws (memory.py:54)
-        self._pin = getattr(self, '_pin', None) or torch.empty(2, self.R, self.B, pin_memory=True)
+        if getattr(self, '_pin', None) is None: self._pin = torch.empty(2, self.R, self.B, pin_memory=True)
         self._pin.copy_(torch.from_numpy(np.random.random_sample((2, self.R, self.B)).astype(np.float32)))
         self.u_pol.copy_(self._pin[0], non_blocking=True)
         self.u_exp.copy_(self._pin[1], non_blocking=True)
