@@ -20,6 +20,7 @@ extern "C" int il_create(int device, il_handle** out) {
   IL_CUDA(cudaSetDevice(device));
   IL_TRY(gail_init());
   IL_TRY(gmmil_pwil_init());
+  IL_TRY(tc_gemm_init());
   il_handle* h = new il_handle();
   h->device = device;
   h->sm_count = prop.multiProcessorCount;

@@ -176,3 +176,8 @@ struct GemmArgs {
   int M, N, K, G;
 };
 int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream);
+
+// tcgen05 engine (tc_gemm.cu): dense M%128==0, N==256, K%32==0 problems when il_set_gemm_mode != IL_GEMM_FP32
+bool tc_gemm_eligible(const GemmArgs& a);
+int launch_tc_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream);
+int tc_gemm_init();

@@ -269,18 +269,34 @@ int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   if (a.N <= 16) return launch_cfg<128, 16, 8, 1>(h, a, stream);
   if (a.M <= 32) return launch_cfg<32, 128, 2, 8>(h, a, stream);
   const bool dense = a.M >= 128 && a.N >= 128 && a.K >= 128;  // the H x H hidden-layer contractions
+  const bool tc = dense && h->gemm_mode != IL_GEMM_FP32 && tc_gemm_eligible(a);
+  auto run = [&]() { return tc ? launch_tc_gemm(h, a, stream) : launch_cfg<128, 128, 8, 8>(h, a, stream); };
   if (h->profiling && dense) {
     ProfiledLaunch pl;
     IL_CUDA(cudaEventCreate(&pl.start));
     IL_CUDA(cudaEventCreate(&pl.stop));
     pl.flops = 2.0 * a.M * a.N * a.K * a.G;
     IL_CUDA(cudaEventRecord(pl.start, stream));
-    const int rc = launch_cfg<128, 128, 8, 8>(h, a, stream);
+    const int rc = run();
     IL_CUDA(cudaEventRecord(pl.stop, stream));
     h->profiled.push_back(pl);
     return rc;
   }
-  return launch_cfg<128, 128, 8, 8>(h, a, stream);
+  return run();
+}
+
+// Test / diagnostics entry: one grouped GEMM with the fused epilogues, routed like the MLP programs route it.
+extern "C" int il_debug_gemm(il_handle* h, int M, int N, int K, int G, const float* A, int64_t a_gs, int lda, int a_kmajor, const float* B, int64_t b_gs, int ldb, int b_kmajor,
+                             float* C, int64_t c_gs, int ldc, const float* bias, int64_t bias_gs, int act, const float* mask, int64_t mask_gs, int ldmask, int mask_act,
+                             float* colsum, int64_t colsum_gs, void* stream) {
+  IL_CHECK(h && A && B && C, "il_debug_gemm: null argument");
+  GemmArgs a{};
+  a.A = A; a.a_gs = a_gs; a.a_gdiv = 1; a.lda = lda; a.a_kmajor = a_kmajor;
+  a.B = B; a.b_gs = b_gs; a.b_gdiv = 1; a.ldb = ldb; a.b_kmajor = b_kmajor;
+  a.C = C; a.c_gs = c_gs; a.ldc = ldc; a.bias = bias; a.bias_gs = bias_gs; a.act = act;
+  a.mask = mask; a.mask_gs = mask_gs; a.ldmask = ldmask; a.mask_act = mask_act; a.colsum = colsum; a.colsum_gs = colsum_gs;
+  a.M = M; a.N = N; a.K = K; a.G = G;
+  return launch_gemm(h, a, (cudaStream_t)stream);
 }
 
 extern "C" int il_profile_begin(il_handle* h) {

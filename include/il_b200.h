@@ -91,6 +91,15 @@ int         il_row_layout(int S, int A, int32_t* offsets8, int32_t* row_len); /*
 int il_profile_begin(il_handle* h);
 int il_profile_end(il_handle* h, double* total_ms, double* total_flops, int64_t* launches);
 
+/* Test / diagnostics entry: one grouped GEMM C[g] = A[g] B[g] with the fused epilogues (bias, activation act >= 0,
+ * activation-derivative mask, bias-gradient column sums), dispatched exactly like the MLP programs dispatch it
+ * (fp32 FFMA engine, or the tcgen05 engine for eligible dense shapes when the gemm mode is tf32x3 / tf32).
+ * a_kmajor: A stored [M, K] (else [K, M]); b_kmajor: B stored [N, K] (else [K, N]). */
+int il_debug_gemm(il_handle* h, int M, int N, int K, int G, const float* A, int64_t a_gs, int lda, int a_kmajor,
+                  const float* B, int64_t b_gs, int ldb, int b_kmajor, float* C, int64_t c_gs, int ldc,
+                  const float* bias, int64_t bias_gs, int act, const float* mask, int64_t mask_gs, int ldmask, int mask_act,
+                  float* colsum, int64_t colsum_gs, void* stream);
+
 /* ---- random inputs (replace torch / numpy global RNG draws when noise is not injected) ---------------- */
 int il_fill_normal(il_handle* h, float* out, int64_t n, uint64_t seed, uint64_t stream_id, const uint64_t* counter, void* stream);
 int il_fill_uniform(il_handle* h, float* out, int64_t n, uint64_t seed, uint64_t stream_id, const uint64_t* counter, void* stream);

@@ -1,0 +1,84 @@
+"""The tcgen05 (3xTF32 / TF32) dense-layer engine against the exact-fp32 FFMA engine and a float64 reference, on all
+three operand layouts the MLP programs use (forward, input-gradient, weight-gradient) with their fused epilogues."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm(mode, M, N, K, G, A, a_kmajor, B, b_kmajor, bias=None, act=-1, mask=None, colsum=False):
+  import il_b200
+  from il_b200 import _lib
+  lib, h = _lib.lib(), _lib.handle()
+  _lib.check(lib.il_set_gemm_mode(h, _lib.GEMM_MODE[mode]))
+  Cm = torch.full((G, M, N), float('nan'), device='cuda')
+  cs = torch.full((G, M), float('nan'), device='cuda') if colsum else None
+  lda, ldb = A.size(2), B.size(2)
+  _lib.check(lib.il_debug_gemm(h, M, N, K, G, A.data_ptr(), A.stride(0), lda, int(a_kmajor), B.data_ptr(), B.stride(0), ldb, int(b_kmajor), Cm.data_ptr(), Cm.stride(0), N,
+                               _lib.ptr(bias), N if bias is not None else 0, act, _lib.ptr(mask), mask.stride(0) if mask is not None else 0, N, 0, _lib.ptr(cs), M, _lib.stream()))
+  torch.cuda.synchronize()
+  _lib.check(lib.il_set_gemm_mode(h, _lib.GEMM_MODE['fp32']))
+  return Cm, cs
+
+
+@pytest.mark.parametrize('layout', ['fwd', 'dx', 'dw'])
+@pytest.mark.parametrize('mode,tol', [('tf32x3', 8e-6), ('tf32', 2e-3)])
+def test_tc_gemm_matches_fp64(layout, mode, tol):
+  torch.manual_seed(0)
+  G, M, N, K = 5, 256, 256, 256
+  X = torch.randn(G, M, K, device='cuda')
+  W = torch.randn(G, N, K, device='cuda') / 16
+  if layout == 'fwd':    # C = X W^T + b, relu
+    bias = torch.randn(G, N, device='cuda')
+    got, _ = _gemm(mode, M, N, K, G, X, True, W, True, bias=bias, act=0)
+    ref = torch.relu(torch.einsum('gmk,gnk->gmn', X.double(), W.double()) + bias.double()[:, None, :])
+  elif layout == 'dx':   # C = (dY W) * relu'(H)
+    Wkn = torch.randn(G, K, N, device='cuda') / 16  # stored [K, N]
+    Hm = torch.randn(G, M, N, device='cuda')
+    got, _ = _gemm(mode, M, N, K, G, X, True, Wkn, False, mask=Hm)
+    ref = torch.einsum('gmk,gkn->gmn', X.double(), Wkn.double()) * (Hm > 0).double()
+  else:                  # C = dY^T X with column sums
+    dY = torch.randn(G, K, M, device='cuda')  # stored [K = batch, M = out]
+    Xb = torch.randn(G, K, N, device='cuda')  # stored [K = batch, N = in]
+    got, cs = _gemm(mode, M, N, K, G, dY, False, Xb, False, colsum=True)
+    ref = torch.einsum('gkm,gkn->gmn', dY.double(), Xb.double())
+    np.testing.assert_allclose(cs.cpu().numpy(), dY.double().sum(1).cpu().numpy(), rtol=1e-5, atol=1e-4)
+  assert not torch.isnan(got).any(), 'tile(s) never written'
+  err = (got.double() - ref).abs().max().item() / ref.abs().max().item()
+  print(layout, mode, 'max rel err', err)
+  assert err < tol, err
+
+
+def test_tc_gemm_many_groups_persistent():
+  """More tiles than SMs: exercises the persistent tile loop, both TMEM accumulators and the stage ring wrap."""
+  torch.manual_seed(1)
+  G, M, N, K = 200, 256, 256, 256
+  X = torch.randn(G, M, K, device='cuda')
+  W = torch.randn(G, N, K, device='cuda') / 16
+  got, _ = _gemm('tf32x3', M, N, K, G, X, True, W, True)
+  ref, _ = _gemm('fp32', M, N, K, G, X, True, W, True)
+  assert not torch.isnan(got).any()
+  err = (got - ref).abs().max().item() / ref.abs().max().item()
+  assert err < 5e-6, err
+
+
+@pytest.mark.parametrize('name', ['actor_hopper', 'sac_hopper'])
+def test_golden_cases_with_tensor_core_engine(name, monkeypatch):
+  """The reference fixtures at the real 256x256 sizes, hidden layers on the 3xTF32 tensor-core engine."""
+  from conftest import load_golden
+  from cuda_cases import run_cuda
+  from il_b200 import _lib
+  from oracle import cases
+  lib, h = _lib.lib(), _lib.handle()
+  _lib.check(lib.il_set_gemm_mode(h, _lib.GEMM_MODE['tf32x3']))
+  try:
+    out = run_cuda(name, [cases.make_inputs(name)])[0]
+  finally:
+    _lib.check(lib.il_set_gemm_mode(h, _lib.GEMM_MODE['fp32']))
+  g = load_golden(name)
+  keys = {k.split('@')[0] for k in g} & set(out)
+  bad = cases.compare(g, out, rtol=2e-4, atol=2e-5, keys=keys)
+  assert not bad, '\n'.join(bad)
