@@ -66,15 +66,17 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return r;
 }
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO(1) | SBO(1024 B)
-// | version 1 | layout SWIZZLE_128B (2).
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO >> 4 at bit 16 | SBO >> 4 at bit 32 |
+// version 1 at bit 46 | layout type at bit 61 (2 = SWIZZLE_128B for K-major, 1 = SWIZZLE_128B_BASE32B for MN-major tf32).
+//   K-major : LBO unused (1), SBO = 1024 (next 8-row atom).   MN-major: LBO = 512 (next 32-row atom along MN),
+//   SBO = bytes between groups of 4 k rows.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major), in 16 B units
-  d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 // byte offset of 16-byte chunk `c` (0..7) of row `r` inside a K-major SWIZZLE_128B tile
@@ -87,65 +89,53 @@ struct TcParams {
   int split;        // 1: 3xTF32, 0: single TF32
 };
 
-__device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, float4 v, bool split) {
-  uint4 h;
-  h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-  *reinterpret_cast<uint4*>(hi_tile + off) = h;
-  if (split) {
-    uint4 l;
-    l.x = to_tf32(v.x - __uint_as_float(h.x)); l.y = to_tf32(v.y - __uint_as_float(h.y));
-    l.z = to_tf32(v.z - __uint_as_float(h.z)); l.w = to_tf32(v.w - __uint_as_float(h.w));
-    *reinterpret_cast<uint4*>(lo_tile + off) = l;
-  }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// hi = x rounded to tf32 (round-half-away on the 13 dropped bits, two integer ops); lo = x - hi is exact in fp32 and
+// is stored unrounded: the tensor core reads only the top 19 bits of each 32-bit tf32 container.
+__device__ __forceinline__ void store_split(uint32_t hi_addr, uint32_t lo_addr, float4 v, bool split) {
+  const uint32_t hx = (__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u, hy = (__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u;
+  const uint32_t hz = (__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u, hw = (__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u;
+  sts128(hi_addr, hx, hy, hz, hw);
+  if (split)
+    sts128(lo_addr, __float_as_uint(v.x - __uint_as_float(hx)), __float_as_uint(v.y - __uint_as_float(hy)), __float_as_uint(v.z - __uint_as_float(hz)),
+           __float_as_uint(v.w - __uint_as_float(hw)));
 }
 
-// Fills one operand tile (ROWS x 32 k) of the current stage. kmajor: element (r, k) at src[r * ld + k]; else src[k * ld + r].
+// Per-thread, kernel-invariant addressing of one operand tile (ROWS x 32 k floats per stage):
+//  K-major source  (element (r, k) at src[r * ld + k]) -> canonical K-major SWIZZLE_128B tile: row r = 128 B, 8-row atoms
+//                   1024 B apart (SBO), 16-byte chunk c stored at c ^ (r % 8).
+//  MN-major source (element (r, k) at src[k * ld + r]) -> no transpose: the canonical MN-major layout for 32-bit
+//                   operands, SWIZZLE_128B_BASE32B (cute Layout_MN_SW128_32B_Atom, the only MN-major layout tf32 has):
+//                   atom = 4 k-rows x 128 B (32 consecutive r), 32-byte chunk q of a row stored at q ^ (k % 4);
+//                   atoms along r 512 B apart (LBO), groups of 4 k (ROWS / 32) * 512 B apart (SBO).
 template <int ROWS>
-__device__ __forceinline__ void produce_tile(const float* __restrict__ src, int ld, bool kmajor, int row0, int k0, uint8_t* hi_tile, uint8_t* lo_tile, bool split, int ptid) {
-  constexpr int PER_THREAD = ROWS * 8 / (N_PRODUCER_WARPS * 32);  // float4 per thread: 4 (A) or 8 (B)
-  float4 v[PER_THREAD];
-  if (kmajor) {
+struct TileMap {
+  static constexpr int PER_THREAD = ROWS * 8 / (N_PRODUCER_WARPS * 32);  // float4 per thread per k-block: 4 (A) or 8 (B)
+  uint32_t goff[PER_THREAD];   // global offset (floats) relative to the tile origin at k-block 0
+  uint32_t soff[PER_THREAD];   // byte offset inside the stage tile
+  __device__ __forceinline__ void init(int ld, bool kmajor, int ptid) {
 #pragma unroll
     for (int j = 0; j < PER_THREAD; ++j) {
       const int i = ptid + j * (N_PRODUCER_WARPS * 32);
-      const int r = i >> 3, c = i & 7;
-      v[j] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)(row0 + r) * ld + k0 + c * 4));
-    }
-#pragma unroll
-    for (int j = 0; j < PER_THREAD; ++j) {
-      const int i = ptid + j * (N_PRODUCER_WARPS * 32);
-      store_split(hi_tile, lo_tile, sw128(i >> 3, i & 7), v[j], split);
-    }
-  } else {
-    const int pw = ptid >> 5, lane = ptid & 31, q = lane >> 2, t = lane & 3;
-#pragma unroll
-    for (int j = 0; j < PER_THREAD; ++j) {
-      const int it = pw + j * N_PRODUCER_WARPS;  // warp-iteration: 4 k x 32 rows
-      const int kq = it & 7, rb = it >> 3;
-      v[j] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)(k0 + kq * 4 + t) * ld + row0 + rb * 32 + q * 4));
-    }
-#pragma unroll
-    for (int j = 0; j < PER_THREAD; ++j) {
-      const int it = pw + j * N_PRODUCER_WARPS;
-      const int kq = it & 7, rb = it >> 3;
-      // 4x4 transpose inside the quad: lane t ends with (row r0 + t, k0..k0+3)
-      const float e[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-      float o[4];
-#pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const int give = t ^ s;  // element index this lane supplies in round s
-        const float mine = give == 0 ? e[0] : (give == 1 ? e[1] : (give == 2 ? e[2] : e[3]));
-        const float got = __shfl_xor_sync(0xffffffffu, mine, s, 4);
-        if ((t ^ s) == 0) o[0] = got;
-        if ((t ^ s) == 1) o[1] = got;
-        if ((t ^ s) == 2) o[2] = got;
-        if ((t ^ s) == 3) o[3] = got;
+      if (kmajor) {
+        const int r = i >> 3, c = i & 7;
+        goff[j] = (uint32_t)(r * ld + c * 4);
+        soff[j] = sw128(r, c);
+      } else {
+        constexpr int CH = ROWS / 4;            // 16-byte chunks per k row
+        const int k = i / CH, c = i % CH;       // consecutive threads -> consecutive chunks of one k row (coalesced)
+        const int atom = c >> 3, q = (c & 7) >> 1, half = c & 1;  // 32-row atom along r, 32-byte chunk, 16-byte half
+        goff[j] = (uint32_t)(k * ld + c * 4);
+        soff[j] = (uint32_t)((k >> 2) * (ROWS / 32) * 512 + atom * 512 + (k & 3) * 128 + ((q ^ (k & 3)) << 5) + (half << 4));
       }
-      store_split(hi_tile, lo_tile, sw128(rb * 32 + q * 4 + t, kq), make_float4(o[0], o[1], o[2], o[3]), split);
     }
   }
-}
+};
 
+// EPI: 0 plain store, 1 bias + relu, 2 relu-derivative mask, 3 generic (runtime bias / activation / mask)
+template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -181,19 +171,32 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
   if (warp > N_EPI_WARPS) {
     // ================= producers =================
     const int ptid = threadIdx.x - (N_EPI_WARPS + 1) * 32;
+    const bool a_km = g.a_kmajor != 0, b_km = g.b_kmajor != 0, split = p.split != 0;
+    TileMap<BM> ma;
+    TileMap<BN> mb;
+    ma.init(g.lda, a_km, ptid);
+    mb.init(g.ldb, b_km, ptid);
+    const int64_t a_kstep = a_km ? BK : (int64_t)BK * g.lda, b_kstep = b_km ? BK : (int64_t)BK * g.ldb;  // floats per k-block
+    const uint32_t stage0 = smem_u32(stage_base);
     uint32_t kb_global = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int grp = tile / p.tiles_m, m0 = (tile % p.tiles_m) * BM;
-      const float* A = g.A + (int64_t)(grp / g.a_gdiv) * g.a_gs;
+      const float* A = g.A + (int64_t)(grp / g.a_gdiv) * g.a_gs + (a_km ? (int64_t)m0 * g.lda : (int64_t)m0);
       const float* B = g.B + (int64_t)(grp / g.b_gdiv) * g.b_gs;
-      for (int kb = 0; kb < nkb; ++kb, ++kb_global) {
+      for (int kb = 0; kb < nkb; ++kb, ++kb_global, A += a_kstep, B += b_kstep) {
+        float4 va[TileMap<BM>::PER_THREAD], vb[TileMap<BN>::PER_THREAD];
+#pragma unroll
+        for (int j = 0; j < TileMap<BM>::PER_THREAD; ++j) va[j] = __ldg(reinterpret_cast<const float4*>(A + ma.goff[j]));
+#pragma unroll
+        for (int j = 0; j < TileMap<BN>::PER_THREAD; ++j) vb[j] = __ldg(reinterpret_cast<const float4*>(B + mb.goff[j]));
         const int s = kb_global % STAGES;
-        const uint32_t ph = (kb_global / STAGES) & 1;
-        if (lane == 0) mbar_wait(empty_bar(s), ph ^ 1);
+        if (lane == 0) mbar_wait(empty_bar(s), ((kb_global / STAGES) & 1) ^ 1);
         __syncwarp();
-        uint8_t* st = stage_base + s * STAGE_BYTES;
-        produce_tile<BM>(A, g.lda, g.a_kmajor != 0, m0, kb * BK, st, st + A_BYTES, p.split != 0, ptid);
-        produce_tile<BN>(B, g.ldb, g.b_kmajor != 0, 0, kb * BK, st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, p.split != 0, ptid);
+        const uint32_t st = stage0 + s * STAGE_BYTES;
+#pragma unroll
+        for (int j = 0; j < TileMap<BM>::PER_THREAD; ++j) store_split(st + ma.soff[j], st + A_BYTES + ma.soff[j], va[j], split);
+#pragma unroll
+        for (int j = 0; j < TileMap<BN>::PER_THREAD; ++j) store_split(st + 2 * A_BYTES + mb.soff[j], st + 2 * A_BYTES + B_BYTES + mb.soff[j], vb[j], split);
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar(s));
@@ -202,8 +205,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
   } else if (warp == N_EPI_WARPS) {
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
-      // InstrDescriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), K-major A/B, N>>3 at bit 17, M>>4 at bit 24
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // InstrDescriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), a_major bit 15, b_major bit 16 (1 = MN-major),
+      // N>>3 at bit 17, M>>4 at bit 24
+      const bool a_km = g.a_kmajor != 0, b_km = g.b_kmajor != 0;
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((a_km ? 0u : 1u) << 15) | ((b_km ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // per-MMA (K = 8 tf32) advance: 32 bytes inside the swizzled 128-byte row (K-major) or two 4-k groups (MN-major)
+      const uint32_t a_lbo = a_km ? 16u : 512u, a_sbo = a_km ? 1024u : (uint32_t)(BM / 32) * 512u, a_kadv = a_km ? 32u : 2u * a_sbo, a_lt = a_km ? 2u : 1u;
+      const uint32_t b_lbo = b_km ? 16u : 512u, b_sbo = b_km ? 1024u : (uint32_t)(BN / 32) * 512u, b_kadv = b_km ? 32u : 2u * b_sbo, b_lt = b_km ? 2u : 1u;
       uint32_t kb_global = 0, it = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
@@ -217,14 +225,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
           const uint32_t a_hi = smem_u32(stage_base + s * STAGE_BYTES), a_lo = a_hi + A_BYTES, b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {
-            const uint32_t ko = kk * 32;  // 8 tf32 = 32 bytes along K inside the 128 B swizzled row
+            const uint32_t ao = kk * a_kadv, bo = kk * b_kadv;
             const uint32_t first = (kb == 0 && kk == 0) ? 0u : 1u;
             if (p.split) {
-              tc_mma_tf32(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, first);
-              tc_mma_tf32(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1u);
-              tc_mma_tf32(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, 1u);
+              tc_mma_tf32(d_tmem, make_desc(a_lo + ao, a_lbo, a_sbo, a_lt), make_desc(b_hi + bo, b_lbo, b_sbo, b_lt), idesc, first);
+              tc_mma_tf32(d_tmem, make_desc(a_hi + ao, a_lbo, a_sbo, a_lt), make_desc(b_lo + bo, b_lbo, b_sbo, b_lt), idesc, 1u);
+              tc_mma_tf32(d_tmem, make_desc(a_hi + ao, a_lbo, a_sbo, a_lt), make_desc(b_hi + bo, b_lbo, b_sbo, b_lt), idesc, 1u);
             } else {
-              tc_mma_tf32(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, first);
+              tc_mma_tf32(d_tmem, make_desc(a_hi + ao, a_lbo, a_sbo, a_lt), make_desc(b_hi + bo, b_lbo, b_sbo, b_lt), idesc, first);
             }
           }
           tc_commit(empty_bar(s));  // frees the stage once these MMAs have read it (implicit before_thread_sync fence)
@@ -235,16 +243,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
     __syncwarp();
   } else {
     // ================= epilogue (warps 0..3 <-> TMEM lanes 32w .. 32w+31) =================
-    float* stg = epi + warp * 32 * EPI_LD;
+    const uint32_t stg = smem_u32(epi) + (uint32_t)(warp * 32 * EPI_LD * 4);
+    const int cq = (lane & 7) * 4, rsub = lane >> 3;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const int grp = tile / p.tiles_m, m0 = (tile % p.tiles_m) * BM;
       mbar_wait(tfull_bar(acc), (it >> 1) & 1);
       tc_fence_after();
-      float* C = g.C + (int64_t)grp * g.c_gs;
-      const float* bias = g.bias ? g.bias + (int64_t)grp * g.bias_gs : nullptr;
-      const float* mask = g.mask ? g.mask + (int64_t)grp * g.mask_gs : nullptr;
+      float* C = g.C + (int64_t)grp * g.c_gs + (int64_t)(m0 + warp * 32 + rsub) * g.ldc + cq;
+      const float* bias = (EPI == 1 || (EPI == 3 && g.bias)) ? g.bias + (int64_t)grp * g.bias_gs + cq : nullptr;
+      const float* mask = (EPI == 2 || (EPI == 3 && g.mask)) ? g.mask + (int64_t)grp * g.mask_gs + (int64_t)(m0 + warp * 32 + rsub) * g.ldmask + cq : nullptr;
 #pragma unroll 1
       for (int cb = 0; cb < BN / 32; ++cb) {
         uint32_t r[32];
@@ -257,28 +266,38 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
               "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        // lane = row (32 rows of this warp), registers = 32 consecutive columns -> staging tile [row][col]
+        // lane = row (32 rows of this warp), registers = 32 consecutive columns -> staging tile [row][col] (padded: no bank conflicts)
+        const uint32_t wrow = stg + (uint32_t)(lane * EPI_LD * 4);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) stg[lane * EPI_LD + c] = __uint_as_float(r[c]);
+        for (int c = 0; c < 32; ++c) asm volatile("st.shared.b32 [%0], %1;" ::"r"(wrow + c * 4), "r"(r[c]) : "memory");
         __syncwarp();
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + cb * 32));
         // coalesced write-out: 8 lanes cover one 128-byte row segment, 4 rows per pass
-        const int cq = (lane & 7) * 4, rsub = lane >> 3;
 #pragma unroll
         for (int pass = 0; pass < 8; ++pass) {
-          const int rl = pass * 4 + rsub;
-          const int m = m0 + warp * 32 + rl, n = cb * 32 + cq;
-          float4 v = make_float4(stg[rl * EPI_LD + cq], stg[rl * EPI_LD + cq + 1], stg[rl * EPI_LD + cq + 2], stg[rl * EPI_LD + cq + 3]);
-          if (bias) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n));
-            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          const uint32_t rrow = stg + (uint32_t)(((pass * 4 + rsub) * EPI_LD + cq) * 4);
+          float4 v;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v.x) : "r"(rrow));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v.y) : "r"(rrow + 4));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v.z) : "r"(rrow + 8));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v.w) : "r"(rrow + 12));
+          const int64_t ro = (int64_t)(pass * 4) * g.ldc + cb * 32;
+          if (EPI == 1) {
+            v.x = fmaxf(v.x + bv.x, 0.f); v.y = fmaxf(v.y + bv.y, 0.f); v.z = fmaxf(v.z + bv.z, 0.f); v.w = fmaxf(v.w + bv.w, 0.f);
+          } else if (EPI == 2) {
+            const float4 mv = __ldg(reinterpret_cast<const float4*>(mask + (int64_t)(pass * 4) * g.ldmask + cb * 32));
+            v.x = mv.x > 0.f ? v.x : 0.f; v.y = mv.y > 0.f ? v.y : 0.f; v.z = mv.z > 0.f ? v.z : 0.f; v.w = mv.w > 0.f ? v.w : 0.f;
+          } else if (EPI == 3) {
+            if (bias) { v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w; }
+            if (g.act >= 0) { v.x = act_apply(v.x, g.act); v.y = act_apply(v.y, g.act); v.z = act_apply(v.z, g.act); v.w = act_apply(v.w, g.act); }
+            if (mask) {
+              const float4 mv = __ldg(reinterpret_cast<const float4*>(mask + (int64_t)(pass * 4) * g.ldmask + cb * 32));
+              v.x *= act_grad_from_output(mv.x, g.mask_act); v.y *= act_grad_from_output(mv.y, g.mask_act);
+              v.z *= act_grad_from_output(mv.z, g.mask_act); v.w *= act_grad_from_output(mv.w, g.mask_act);
+            }
           }
-          if (g.act >= 0) { v.x = act_apply(v.x, g.act); v.y = act_apply(v.y, g.act); v.z = act_apply(v.z, g.act); v.w = act_apply(v.w, g.act); }
-          if (mask) {
-            const float4 mv = __ldg(reinterpret_cast<const float4*>(mask + (int64_t)m * g.ldmask + n));
-            v.x *= act_grad_from_output(mv.x, g.mask_act); v.y *= act_grad_from_output(mv.y, g.mask_act);
-            v.z *= act_grad_from_output(mv.z, g.mask_act); v.w *= act_grad_from_output(mv.w, g.mask_act);
-          }
-          *reinterpret_cast<float4*>(C + (int64_t)m * g.ldc + n) = v;
+          *reinterpret_cast<float4*>(C + ro) = v;
         }
         __syncwarp();
       }
@@ -319,7 +338,10 @@ bool tc_gemm_eligible(const GemmArgs& a) {
 }
 
 int tc_gemm_init() {
-  IL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  IL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  IL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  IL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  IL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   return 0;
 }
 
@@ -331,7 +353,13 @@ int launch_tc_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   p.n_tiles = a.G * p.tiles_m;
   p.split = h->gemm_mode == IL_GEMM_TF32X3 ? 1 : 0;
   const int grid = p.n_tiles < h->sm_count ? p.n_tiles : h->sm_count;
-  IL_LAUNCH(h, tc_gemm_kernel, grid, THREADS, SMEM_BYTES, stream, p);
+  const bool plain = !a.bias && a.act < 0 && !a.mask;
+  const bool bias_relu = a.bias && a.act == IL_ACT_RELU && !a.mask;
+  const bool mask_relu = !a.bias && a.act < 0 && a.mask && a.mask_act == IL_ACT_RELU;
+  if (plain) IL_LAUNCH(h, tc_gemm_kernel<0>, grid, THREADS, SMEM_BYTES, stream, p);
+  else if (bias_relu) IL_LAUNCH(h, tc_gemm_kernel<1>, grid, THREADS, SMEM_BYTES, stream, p);
+  else if (mask_relu) IL_LAUNCH(h, tc_gemm_kernel<2>, grid, THREADS, SMEM_BYTES, stream, p);
+  else IL_LAUNCH(h, tc_gemm_kernel<3>, grid, THREADS, SMEM_BYTES, stream, p);
   if (a.colsum) {
     dim3 cg((a.M + 127) / 128, a.G);
     IL_LAUNCH(h, colsum_kernel, cg, 128, 0, stream, a.A, a.a_gs, a.a_gdiv, a.lda, a.K, a.M, a.colsum, a.colsum_gs);
