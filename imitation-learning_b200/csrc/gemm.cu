@@ -242,6 +242,77 @@ __global__ void __launch_bounds__(256, 2) gemm_grouped_kernel(const GemmArgs p) 
   }
 }
 
+// Thin-contraction kernel (K <= 32, wide output): the first layer of every MLP (K = state size) and the backward of
+// the last layer (K = head width). These products are pure output bandwidth, so the tile loop of the general kernel is
+// replaced by: B (K x 256) and 32 rows of A in shared memory, 8 x 4 outputs per thread, 128-bit coalesced stores.
+constexpr int TK_MAXK = 32, TK_ROWS = 32, TK_COLS = 256;
+template <bool B_KMAJOR>
+__global__ void __launch_bounds__(256) gemm_thin_k_kernel(const GemmArgs p) {
+  __shared__ __align__(16) float Bs[TK_MAXK][TK_COLS];
+  __shared__ float As[TK_ROWS][TK_MAXK + 1];
+  const int tid = threadIdx.x, g = blockIdx.z, m0 = blockIdx.y * TK_ROWS, n0 = blockIdx.x * TK_COLS;
+  const int M = p.M, N = p.N, K = p.K;
+  const float* __restrict__ A = p.A + (int64_t)(g / p.a_gdiv) * p.a_gs;
+  const float* __restrict__ B = p.B + (int64_t)(g / p.b_gdiv) * p.b_gs;
+  const int ncols = min(TK_COLS, N - n0);
+  if (B_KMAJOR) {  // B stored [N, K]: rows n0.. are contiguous when ldb == K
+    for (int idx = tid; idx < ncols * K; idx += 256) {
+      const int n = idx / K, k = idx % K;
+      Bs[k][n] = __ldg(B + (int64_t)(n0 + n) * p.ldb + k);
+    }
+  } else {  // B stored [K, N]
+    for (int idx = tid; idx < K * ncols; idx += 256) {
+      const int k = idx / ncols, n = idx % ncols;
+      Bs[k][n] = __ldg(B + (int64_t)k * p.ldb + n0 + n);
+    }
+  }
+  for (int idx = tid; idx < TK_ROWS * K; idx += 256) {
+    const int r = idx / K, k = idx % K;
+    As[r][k] = (m0 + r < M) ? __ldg(A + (int64_t)(m0 + r) * p.lda + k) : 0.f;
+  }
+  __syncthreads();
+  const int n = (tid & 63) * 4, tr = tid >> 6;
+  if (n >= ncols) return;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float4 b = *reinterpret_cast<const float4*>(&Bs[k][n]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a = As[tr + 4 * i][k];
+      acc[i][0] = fmaf(a, b.x, acc[i][0]); acc[i][1] = fmaf(a, b.y, acc[i][1]);
+      acc[i][2] = fmaf(a, b.z, acc[i][2]); acc[i][3] = fmaf(a, b.w, acc[i][3]);
+    }
+  }
+  float* __restrict__ C = p.C + (int64_t)g * p.c_gs;
+  const float* __restrict__ mask = p.mask ? p.mask + (int64_t)g * p.mask_gs : nullptr;
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + (int64_t)g * p.bias_gs + n0 + n));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + tr + 4 * i;
+    if (m >= M) continue;
+    float4 v = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
+    if (p.act >= 0) { v.x = act_apply(v.x, p.act); v.y = act_apply(v.y, p.act); v.z = act_apply(v.z, p.act); v.w = act_apply(v.w, p.act); }
+    if (mask) {
+      const float4 mv = __ldg(reinterpret_cast<const float4*>(mask + (int64_t)m * p.ldmask + n0 + n));
+      v.x *= act_grad_from_output(mv.x, p.mask_act); v.y *= act_grad_from_output(mv.y, p.mask_act);
+      v.z *= act_grad_from_output(mv.z, p.mask_act); v.w *= act_grad_from_output(mv.w, p.mask_act);
+    }
+    *reinterpret_cast<float4*>(C + (int64_t)m * p.ldc + n0 + n) = v;
+  }
+}
+
+bool thin_k_eligible(const GemmArgs& a) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (a.K > TK_MAXK || !a.a_kmajor || a.N < 64 || a.N % 4 || a.colsum || a.accumulate) return false;
+  if (!al16(a.C) || a.ldc % 4 || a.c_gs % 4) return false;
+  if (a.bias && (!al16(a.bias) || a.bias_gs % 4)) return false;
+  if (a.mask && (!al16(a.mask) || a.ldmask % 4 || a.mask_gs % 4)) return false;
+  return true;
+}
+
 template <int BM, int BN, int TM, int TN>
 int launch_cfg(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   constexpr int BK = 16;
@@ -265,6 +336,12 @@ int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   IL_CHECK(a.G <= 65535, "gemm: too many groups (%d)", a.G);
   IL_CHECK(!(a.colsum && a.a_kmajor), "gemm: colsum needs the [K, M] operand layout");
   IL_CHECK(!(a.accumulate && a.act >= 0), "gemm: accumulate with activation is not supported");
+  if (a.M > 16 && thin_k_eligible(a)) {
+    dim3 grid((a.N + TK_COLS - 1) / TK_COLS, (a.M + TK_ROWS - 1) / TK_ROWS, a.G);
+    if (a.b_kmajor) IL_LAUNCH(h, gemm_thin_k_kernel<true>, grid, 256, 0, stream, a);
+    else IL_LAUNCH(h, gemm_thin_k_kernel<false>, grid, 256, 0, stream, a);
+    return 0;
+  }
   if (a.M <= 16) return launch_cfg<16, 128, 1, 8>(h, a, stream);
   if (a.N <= 16) return launch_cfg<128, 16, 8, 1>(h, a, stream);
   if (a.M <= 32) return launch_cfg<32, 128, 2, 8>(h, a, stream);
