@@ -134,14 +134,25 @@ def run_b200(a):
 
   def timed(n, e2e=False):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # e2e: every step's results (losses, returns) are copied device -> pinned host memory and consumed one step later,
+    # so the read-back of step i overlaps the kernels of step i+1 (the host never skips a step's results)
+    outs = (tr.sac_out['losses'], tr.gail_losses, tr.last_return)
+    pinned = [[torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs] for _ in range(2)]
+    done = [None, None]
+    consumed = 0.0
     distributed.barrier(); torch.cuda.synchronize()
     launches0 = tr.total_launches()
     ev0.record()
-    host = None
-    for _ in range(n):
+    for i in range(n):
       tr.train_step()
-      if e2e:  # device -> host read of the step's results (losses, returns)
-        host = (tr.sac_out['losses'].cpu(), tr.gail_losses.cpu(), tr.last_return.cpu())
+      if e2e:
+        slot = i & 1
+        for dst, src in zip(pinned[slot], outs): dst.copy_(src, non_blocking=True)
+        done[slot] = torch.cuda.Event(); done[slot].record()
+        prev = done[slot ^ 1]
+        if prev is not None:
+          prev.synchronize()
+          consumed += float(pinned[slot ^ 1][0][0, 0])  # host touches the previous step's results
     ev1.record()
     torch.cuda.synchronize(); distributed.barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], device='cuda')

@@ -217,11 +217,19 @@ class Trainer:
     """One iteration of the loop at train.py:149: rollout, then (after `training.start`) one update."""
     self.step += 1
     if self._will_update(self.step):
-      if not self.device_rng:  # host-drawn index uniforms, like the reference's np.random draws (memory.py:54)
-        if getattr(self, '_pin', None) is None: self._pin = torch.empty(2, self.R, self.B, pin_memory=True)
-        self._pin.copy_(torch.from_numpy(np.random.random_sample((2, self.R, self.B)).astype(np.float32)))
-        self.u_pol.copy_(self._pin[0], non_blocking=True)
-        self.u_exp.copy_(self._pin[1], non_blocking=True)
+      if not self.device_rng:  # host-drawn index uniforms (the reference draws its indices on the host: memory.py:54)
+        if getattr(self, '_pin', None) is None:
+          self._pin = [torch.empty(2, self.R, self.B, pin_memory=True) for _ in range(2)]  # double-buffered pinned staging
+          self._pin_ev = [None, None]
+          self._host_rng = np.random.default_rng(self.cfg.seed)
+        slot = self.step & 1
+        if self._pin_ev[slot] is not None: self._pin_ev[slot].synchronize()  # the H2D copy that last used this buffer is done
+        self._host_rng.random(out=self._pin[slot].numpy(), dtype=np.float32)
+        self.u_pol.copy_(self._pin[slot][0], non_blocking=True)
+        self.u_exp.copy_(self._pin[slot][1], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pin_ev[slot] = ev
       self._run('step+update', lambda: (self.rollout(), self.update()))
       self.updates += 1
     else:
