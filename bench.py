@@ -31,7 +31,8 @@ def parse():
   p.add_argument('--replicas', type=int, default=1024, help='replica-envs per GPU')
   p.add_argument('--batch-size', type=int, default=256)
   p.add_argument('--start', type=int, default=300, help='update-free prefill steps before the timed region (training.start)')
-  p.add_argument('--gemm-mode', default=os.environ.get('IL_GEMM_MODE', 'fp32'))
+  p.add_argument('--gemm-mode', default=os.environ.get('IL_GEMM_MODE', 'tf32x3'), choices=['fp32', 'tf32x3', 'tf32'],
+                 help='arithmetic of the 256x256 layers: tf32x3 = 3xTF32 split on tcgen05 (fp32-level accuracy, parity-tested), fp32 = FFMA engine')
   p.add_argument('--no-e2e', action='store_true')
   p.add_argument('--no-cpu-baseline', action='store_true')
   p.add_argument('--ref-steps-per-step', type=int, default=10, help='reference arm: oracle loop iterations per bench step and worker')
