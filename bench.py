@@ -49,9 +49,20 @@ def workload(a):
 # ------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port loop on the host cores
 # ------------------------------------------------------------------------------------------------------------------
+def usable_cores():
+  """Host cores this process may actually use: affinity mask, capped by the cgroup CPU quota when one is set."""
+  n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+  try:
+    quota, period = open('/sys/fs/cgroup/cpu.max').read().split()
+    if quota != 'max': n = max(1, min(n, int(float(quota) / float(period))))
+  except Exception:
+    pass
+  return n
+
+
 def cpu_reference(a, steps, warmup, procs=None):
   from oracle import loop
-  procs = procs or (os.cpu_count() or 1)
+  procs = procs or usable_cores()
   per_worker = max(steps * a.ref_steps_per_step, 1)
   r = loop.measure_multiprocess(procs, a.algorithm, a.env, steps=per_worker, warmup=max(warmup, 1), batch_size=a.batch_size, prefill=a.start)
   return r, procs, per_worker
