@@ -181,3 +181,7 @@ int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream);
 bool tc_gemm_eligible(const GemmArgs& a);
 int launch_tc_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream);
 int tc_gemm_init();
+// dense hidden layer + bias + ReLU with the following (final, <= 8 units) linear layer fused into the epilogue
+bool tc_head_fusable(const il_handle* h, const GemmArgs& a, int head_n);
+int launch_tc_gemm_head(il_handle* h, const GemmArgs& a, const float* head_w, const float* head_b, int64_t head_gs, int head_n, float* head_out, int64_t head_out_gs, int store_c,
+                        cudaStream_t stream);

@@ -35,10 +35,25 @@ char* mlp_acts_carve(const il_mlp* m, int G, int n, char* ws, MlpActs* acts) {
   return ws;
 }
 
-int mlp_forward(il_handle* h, const il_mlp* m, int G, int n, MatView X, const MlpActs& acts, float* out, int64_t out_gs, int ld_out, cudaStream_t stream) {
+int mlp_forward(il_handle* h, const il_mlp* m, int G, int n, MatView X, const MlpActs& acts, float* out, int64_t out_gs, int ld_out, cudaStream_t stream, bool keep_hidden) {
   const MlpOffsets o = mlp_offsets(m->dims, m->n_layers);
   const int L = m->n_layers;
   for (int l = 0; l < L; ++l) {
+    if (l == L - 2 && L >= 2 && m->activation == IL_ACT_RELU && ld_out == m->dims[L] && out_gs == (int64_t)n * m->dims[L]) {
+      // last hidden layer on the tensor-core engine: fuse the final linear layer (N <= 8) into its epilogue
+      GemmArgs a{};
+      if (l == 0) { a.A = X.ptr; a.a_gs = X.gs; a.a_gdiv = X.gdiv; a.lda = X.ld; }
+      else { a.A = acts.hid[l - 1]; a.a_gs = (int64_t)n * m->dims[l]; a.a_gdiv = 1; a.lda = m->dims[l]; }
+      a.a_kmajor = 1;
+      a.B = m->params + o.w[l]; a.b_gs = m->stride; a.b_gdiv = 1; a.ldb = m->dims[l]; a.b_kmajor = 1;
+      a.bias = m->params + o.b[l]; a.bias_gs = m->stride;
+      a.C = acts.hid[l]; a.c_gs = (int64_t)n * m->dims[l + 1]; a.ldc = m->dims[l + 1]; a.act = m->activation;
+      a.M = n; a.N = m->dims[l + 1]; a.K = m->dims[l]; a.G = G;
+      if (tc_head_fusable(h, a, m->dims[L])) {
+        IL_TRY(launch_tc_gemm_head(h, a, m->params + o.w[L - 1], m->params + o.b[L - 1], m->stride, m->dims[L], out, out_gs, keep_hidden ? 1 : 0, stream));
+        return 0;
+      }
+    }
     GemmArgs a{};
     if (l == 0) {
       a.A = X.ptr; a.a_gs = X.gs; a.a_gdiv = X.gdiv; a.lda = X.ld;

@@ -20,8 +20,10 @@ int64_t mlp_acts_bytes(const il_mlp* m, int G, int n);
 char* mlp_acts_carve(const il_mlp* m, int G, int n, char* ws, MlpActs* acts);
 
 // Forward of G nets: out[g] ([n, dims[L]], row stride ld_out, group stride out_gs) = net_g(X[g]).
+// keep_hidden == false: the hidden activations are not needed afterwards (no backward pass follows), which lets the
+// fused head epilogue skip writing the last hidden layer.
 int mlp_forward(il_handle* h, const il_mlp* m, int G, int n, MatView X, const MlpActs& acts, float* out, int64_t out_gs, int ld_out,
-                cudaStream_t stream);
+                cudaStream_t stream, bool keep_hidden = true);
 
 // Backward of G nets from dOut (gradient at the linear head), using the saved hidden outputs.
 //  grads != nullptr : parameter gradients written in the flat parameter layout (net stride grad_stride).

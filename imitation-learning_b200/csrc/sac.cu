@@ -199,7 +199,7 @@ extern "C" int il_sac_update(il_handle* h, const il_sac_args* a, void* stream) {
   IL_TRY(launch_tick(h, a->actor_opt.step, a->critic_opt.step, a->alpha_opt.step, st));
 
   // (1) a' ~ pi(.|s'), log pi(a'|s')  [training.py:20-23]
-  IL_TRY(mlp_forward(h, &a->actor, R, B, MatView{rows + L.next_state, rs, 1, row}, w.actor_acts, w.head, (int64_t)B * 2 * A, 2 * A, st));
+  IL_TRY(mlp_forward(h, &a->actor, R, B, MatView{rows + L.next_state, rs, 1, row}, w.actor_acts, w.head, (int64_t)B * 2 * A, 2 * A, st, /*keep_hidden=*/false));
   {
     HeadFwdArgs ha{};
     ha.head = w.head; ha.eps = a->eps_next;
@@ -211,7 +211,7 @@ extern "C" int il_sac_update(il_handle* h, const il_sac_args* a, void* stream) {
     IL_TRY(launch_actor_head(h, ha, st));
   }
   // (2) target critics on (s', a') and the Bellman target  [training.py:24-25]
-  IL_TRY(mlp_forward(h, &a->target, 2 * R, B, MatView{w.xn, (int64_t)B * d, 2, d}, w.critic_acts, w.q, (int64_t)B, 1, st));
+  IL_TRY(mlp_forward(h, &a->target, 2 * R, B, MatView{w.xn, (int64_t)B * d, 2, d}, w.critic_acts, w.q, (int64_t)B, 1, st, /*keep_hidden=*/false));
   IL_LAUNCH(h, sac_target_kernel, ew, 128, 0, st, w.q, w.lp_next, a->log_alpha, rows, rs, row, L.reward, L.terminal, av, a->discount, w.y, R, B);
   // (3) critic loss, backward, AdamW  [training.py:26-31]
   IL_TRY(mlp_forward(h, &a->critic, 2 * R, B, MatView{rows + L.state, rs, 2, row}, w.critic_acts, w.q, (int64_t)B, 1, st));

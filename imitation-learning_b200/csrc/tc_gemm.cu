@@ -28,7 +28,9 @@ constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;          // 16 KB, 3
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;               // 96 KB
 constexpr int EPI_LD = 33;                                           // padded row of the epilogue staging tile
 constexpr int EPI_BYTES = N_EPI_WARPS * 32 * EPI_LD * 4;
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + 256;
+constexpr int HEAD_MAX = 8;                                          // fused head: up to 8 output units (N = 1 critic, 2A <= 8 actor)
+constexpr int HEAD_BYTES = (BN + HEAD_MAX * BN) * 4;                 // bias [256] + head weights [8][256]
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + 256 + HEAD_BYTES;
 constexpr uint32_t TMEM_COLS = 512;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
@@ -87,6 +89,12 @@ struct TcParams {
   int tiles_m;      // M / BM
   int n_tiles;      // G * tiles_m
   int split;        // 1: 3xTF32, 0: single TF32
+  // EPI 4 (bias + ReLU + fused linear head): head_out[g, m, j] = sum_n head_w[g, j, n] * relu(C[g, m, n] + bias[n]) + head_b[g, j]
+  const float* head_w;
+  const float* head_b;
+  float* head_out;
+  int64_t head_gs, head_out_gs;  // group strides of head_w / head_b (same buffer family) and of head_out
+  int head_n, store_c;           // head units (<= HEAD_MAX); store_c == 0: the hidden output itself is not needed (no backward)
 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
@@ -134,7 +142,8 @@ struct TileMap {
   }
 };
 
-// EPI: 0 plain store, 1 bias + relu, 2 relu-derivative mask, 3 generic (runtime bias / activation / mask)
+// EPI: 0 plain store, 1 bias + relu, 2 relu-derivative mask, 3 generic (runtime bias / activation / mask),
+//      4 bias + relu + fused linear head (the next, final layer of the MLP computed from the accumulator row in registers)
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -144,6 +153,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
   // bars: full[2], empty[2], tmem_full[2], tmem_empty[2], then the TMEM base address
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* head_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + EPI_BYTES + 256);  // [BN] bias then [HEAD_MAX][BN] head weights
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (2 + s); };
@@ -252,6 +262,18 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
       mbar_wait(tfull_bar(acc), (it >> 1) & 1);
       tc_fence_after();
       float* C = g.C + (int64_t)grp * g.c_gs + (int64_t)(m0 + warp * 32 + rsub) * g.ldc + cq;
+      float hacc[HEAD_MAX];
+      if (EPI == 4) {  // stage this group's bias and head weights once per tile for the 4 epilogue warps
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done
+        const int et = threadIdx.x;  // 0..127
+        const float* bsrc = g.bias + (int64_t)grp * g.bias_gs;
+        const float* wsrc = p.head_w + (int64_t)grp * p.head_gs;
+        for (int i = et; i < BN; i += 128) head_s[i] = __ldg(bsrc + i);
+        for (int i = et; i < p.head_n * BN; i += 128) head_s[BN + i] = __ldg(wsrc + i);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < HEAD_MAX; ++j) hacc[j] = 0.f;
+      }
       const float* bias = (EPI == 1 || (EPI == 3 && g.bias)) ? g.bias + (int64_t)grp * g.bias_gs + cq : nullptr;
       const float* mask = (EPI == 2 || (EPI == 3 && g.mask)) ? g.mask + (int64_t)grp * g.mask_gs + (int64_t)(m0 + warp * 32 + rsub) * g.ldmask + cq : nullptr;
 #pragma unroll 1
@@ -266,6 +288,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
               "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (EPI == 4) {  // bias + ReLU in registers (lane = row), then the head dot products with smem-broadcast weights
+          const float* bs = head_s + cb * 32;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(fmaxf(__uint_as_float(r[c]) + bs[c], 0.f));
+#pragma unroll
+          for (int j = 0; j < HEAD_MAX; ++j) {
+            if (j < p.head_n) {
+              const float* ws = head_s + BN + j * BN + cb * 32;
+              float a = hacc[j];
+#pragma unroll
+              for (int c = 0; c < 32; ++c) a = fmaf(__uint_as_float(r[c]), ws[c], a);
+              hacc[j] = a;
+            }
+          }
+          if (!p.store_c) continue;
+        }
         // lane = row (32 rows of this warp), registers = 32 consecutive columns -> staging tile [row][col] (padded: no bank conflicts)
         const uint32_t wrow = stg + (uint32_t)(lane * EPI_LD * 4);
 #pragma unroll
@@ -300,6 +338,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
           *reinterpret_cast<float4*>(C + ro) = v;
         }
         __syncwarp();
+      }
+      if (EPI == 4) {
+        float* ho = p.head_out + (int64_t)grp * p.head_out_gs + (int64_t)(m0 + warp * 32 + lane) * p.head_n;
+        const float* hb = p.head_b + (int64_t)grp * p.head_gs;
+#pragma unroll
+        for (int j = 0; j < HEAD_MAX; ++j)
+          if (j < p.head_n) ho[j] = hacc[j] + __ldg(hb + j);
       }
       tc_fence_before();
       __syncwarp();
@@ -342,12 +387,31 @@ int tc_gemm_init() {
   IL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   IL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   IL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  IL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  return 0;
+}
+
+bool tc_head_fusable(const il_handle* h, const GemmArgs& a, int head_n) {
+  return h->gemm_mode != IL_GEMM_FP32 && tc_gemm_eligible(a) && a.bias && a.act == IL_ACT_RELU && !a.mask && !a.colsum && head_n >= 1 && head_n <= HEAD_MAX;
+}
+
+int launch_tc_gemm_head(il_handle* h, const GemmArgs& a, const float* head_w, const float* head_b, int64_t head_gs, int head_n, float* head_out, int64_t head_out_gs, int store_c,
+                        cudaStream_t stream) {
+  IL_CHECK(tc_head_fusable(h, a, head_n), "tc_gemm_head: not fusable");
+  TcParams p{};
+  p.g = a;
+  p.tiles_m = a.M / BM;
+  p.n_tiles = a.G * p.tiles_m;
+  p.split = h->gemm_mode == IL_GEMM_TF32X3 ? 1 : 0;
+  p.head_w = head_w; p.head_b = head_b; p.head_out = head_out; p.head_gs = head_gs; p.head_out_gs = head_out_gs; p.head_n = head_n; p.store_c = store_c;
+  const int grid = p.n_tiles < h->sm_count ? p.n_tiles : h->sm_count;
+  IL_LAUNCH(h, tc_gemm_kernel<4>, grid, THREADS, SMEM_BYTES, stream, p);
   return 0;
 }
 
 int launch_tc_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   IL_CHECK(tc_gemm_eligible(a), "tc_gemm: shape/layout not eligible (M=%d N=%d K=%d)", a.M, a.N, a.K);
-  TcParams p;
+  TcParams p{};
   p.g = a;
   p.tiles_m = a.M / BM;
   p.n_tiles = a.G * p.tiles_m;
