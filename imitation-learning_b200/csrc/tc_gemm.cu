@@ -180,6 +180,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
 
   if (warp > N_EPI_WARPS) {
     // ================= producers =================
+    // cp.async (16 B, L2-only) copies the raw fp32 chunks straight into the swizzled "hi" tile of the NEXT stage while
+    // this thread derives the "lo" tile of the CURRENT stage from the chunks it copied itself (thread-local: no
+    // cross-thread hazard). The tensor core reads only the top 19 bits of each 32-bit tf32 container, so the raw tile
+    // is the hi operand (truncated) and lo = x - trunc_tf32(x) is exact in fp32.
     const int ptid = threadIdx.x - (N_EPI_WARPS + 1) * 32;
     const bool a_km = g.a_kmajor != 0, b_km = g.b_kmajor != 0, split = p.split != 0;
     TileMap<BM> ma;
@@ -188,29 +192,44 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
     mb.init(g.ldb, b_km, ptid);
     const int64_t a_kstep = a_km ? BK : (int64_t)BK * g.lda, b_kstep = b_km ? BK : (int64_t)BK * g.ldb;  // floats per k-block
     const uint32_t stage0 = smem_u32(stage_base);
-    uint32_t kb_global = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_kb = my_tiles * nkb;
+    auto issue = [&](int idx) {  // async copies of this CTA's idx-th k-block into stage idx % STAGES
+      const int tile = blockIdx.x + (idx / nkb) * gridDim.x, kb = idx % nkb;
       const int grp = tile / p.tiles_m, m0 = (tile % p.tiles_m) * BM;
-      const float* A = g.A + (int64_t)(grp / g.a_gdiv) * g.a_gs + (a_km ? (int64_t)m0 * g.lda : (int64_t)m0);
-      const float* B = g.B + (int64_t)(grp / g.b_gdiv) * g.b_gs;
-      for (int kb = 0; kb < nkb; ++kb, ++kb_global, A += a_kstep, B += b_kstep) {
-        float4 va[TileMap<BM>::PER_THREAD], vb[TileMap<BN>::PER_THREAD];
+      const float* A = g.A + (int64_t)(grp / g.a_gdiv) * g.a_gs + (a_km ? (int64_t)m0 * g.lda : (int64_t)m0) + kb * a_kstep;
+      const float* B = g.B + (int64_t)(grp / g.b_gdiv) * g.b_gs + kb * b_kstep;
+      const int s = idx % STAGES;
+      if (lane == 0) mbar_wait(empty_bar(s), ((idx / STAGES) & 1) ^ 1);
+      __syncwarp();
+      const uint32_t st = stage0 + s * STAGE_BYTES;
 #pragma unroll
-        for (int j = 0; j < TileMap<BM>::PER_THREAD; ++j) va[j] = __ldg(reinterpret_cast<const float4*>(A + ma.goff[j]));
+      for (int j = 0; j < TileMap<BM>::PER_THREAD; ++j) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + ma.soff[j]), "l"(A + ma.goff[j]) : "memory");
 #pragma unroll
-        for (int j = 0; j < TileMap<BN>::PER_THREAD; ++j) vb[j] = __ldg(reinterpret_cast<const float4*>(B + mb.goff[j]));
-        const int s = kb_global % STAGES;
-        if (lane == 0) mbar_wait(empty_bar(s), ((kb_global / STAGES) & 1) ^ 1);
-        __syncwarp();
-        const uint32_t st = stage0 + s * STAGE_BYTES;
+      for (int j = 0; j < TileMap<BN>::PER_THREAD; ++j) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + 2 * A_BYTES + mb.soff[j]), "l"(B + mb.goff[j]) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto lo_chunk = [&](uint32_t hi_addr, uint32_t lo_addr) {
+      uint32_t x, y, z, w;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(hi_addr));
+      sts128(lo_addr, __float_as_uint(__uint_as_float(x) - __uint_as_float(x & 0xFFFFE000u)), __float_as_uint(__uint_as_float(y) - __uint_as_float(y & 0xFFFFE000u)),
+             __float_as_uint(__uint_as_float(z) - __uint_as_float(z & 0xFFFFE000u)), __float_as_uint(__uint_as_float(w) - __uint_as_float(w & 0xFFFFE000u)));
+    };
+    if (total_kb > 0) issue(0);
+    for (int idx = 0; idx < total_kb; ++idx) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's copies of k-block idx have landed
+      const int s = idx % STAGES;
+      const uint32_t st = stage0 + s * STAGE_BYTES;
+      if (split) {
 #pragma unroll
-        for (int j = 0; j < TileMap<BM>::PER_THREAD; ++j) store_split(st + ma.soff[j], st + A_BYTES + ma.soff[j], va[j], split);
+        for (int j = 0; j < TileMap<BM>::PER_THREAD; ++j) lo_chunk(st + ma.soff[j], st + A_BYTES + ma.soff[j]);
 #pragma unroll
-        for (int j = 0; j < TileMap<BN>::PER_THREAD; ++j) store_split(st + 2 * A_BYTES + mb.soff[j], st + 2 * A_BYTES + B_BYTES + mb.soff[j], vb[j], split);
-        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar(s));
+        for (int j = 0; j < TileMap<BN>::PER_THREAD; ++j) lo_chunk(st + 2 * A_BYTES + mb.soff[j], st + 2 * A_BYTES + B_BYTES + mb.soff[j]);
       }
+      fence_proxy_async();  // generic-proxy / cp.async writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(s));
+      if (idx + 1 < total_kb) issue(idx + 1);  // waits for the MMAs that last read that stage, then refills it asynchronously
     }
   } else if (warp == N_EPI_WARPS) {
     // ================= MMA issuer (one thread) =================
