@@ -239,7 +239,10 @@ def measure_dense_gemm(tr, a):
     pass
   return dict(bound='tensor', kernel='grouped dense-layer GEMM (256x256x256 per net, fwd / dX / dW) of the SAC update', achieved=achieved, peak=peak, unit='TFLOP/s',
               frac=(achieved / peak) if achieved else None, traffic=traffic, launches=int(n.value), avg_launch_ms=ms.value / max(n.value, 1),
-              algorithmic_flops_per_launch=flops.value / max(n.value, 1), peak_source=src, arithmetic=a.gemm_mode)
+              algorithmic_flops_per_launch=flops.value / max(n.value, 1), peak_source=src, arithmetic=a.gemm_mode,
+              mma_tflops=(achieved * (3 if a.gemm_mode == 'tf32x3' else 1)) if achieved else None,
+              note='tf32x3 issues 3 tf32 MMAs per algorithmic product (fp32-level accuracy); dense tf32 peak is half the bf16 denominator, so the ceiling of this '
+                   'arithmetic is peak/6 algorithmic TFLOP/s' if a.gemm_mode == 'tf32x3' else None)
 
 
 def main():

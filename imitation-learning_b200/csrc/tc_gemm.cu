@@ -20,8 +20,14 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 32;         // tile: 128 x 256 outputs, 32-float (128 B) k-blocks
-constexpr int STAGES = 2;
+#ifndef IL_TC_BK
+#define IL_TC_BK 16
+#endif
+constexpr int BM = 128, BN = 256, BK = IL_TC_BK;   // tile: 128 x 256 outputs; k-blocks of 16 floats (64 B rows, SWIZZLE_64B) or 32 (128 B)
+constexpr int STAGES = BK == 16 ? 4 : 2;           // 4 x 48 KB or 2 x 96 KB of operand stages
+constexpr int KM_CHUNKS = BK / 4;                  // 16-byte chunks per K-major row
+constexpr int KM_ROW_BYTES = BK * 4;
+constexpr uint32_t KM_LAYOUT = BK == 16 ? 4u : 2u; // UMMA LayoutType: SWIZZLE_64B = 4, SWIZZLE_128B = 2
 constexpr int N_PRODUCER_WARPS = 8, N_EPI_WARPS = 4;
 constexpr int THREADS = (N_EPI_WARPS + 1 + N_PRODUCER_WARPS) * 32;  // 416
 constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;          // 16 KB, 32 KB (per hi or lo copy)
@@ -81,8 +87,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   d |= (uint64_t)layout_type << 61;
   return d;
 }
-// byte offset of 16-byte chunk `c` (0..7) of row `r` inside a K-major SWIZZLE_128B tile
-__device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
+// byte offset of 16-byte chunk `c` of row `r` inside a K-major swizzled tile (8-row atoms; Swizzle<3,4,3> on 128 B rows:
+// chunk ^= r % 8; Swizzle<2,4,3> on 64 B rows: chunk ^= (r / 2) % 4 — address bits [7,9) are (r >> 1) & 3 there)
+__device__ __forceinline__ uint32_t sw128(int r, int c) {
+  const int x = BK == 32 ? (r & 7) : ((r >> 1) & 3);
+  return (uint32_t)((r >> 3) * (8 * KM_ROW_BYTES) + (r & 7) * KM_ROW_BYTES + ((c ^ x) << 4));
+}
 
 struct TcParams {
   GemmArgs g;
@@ -120,7 +130,7 @@ __device__ __forceinline__ void store_split(uint32_t hi_addr, uint32_t lo_addr, 
 //                   atoms along r 512 B apart (LBO), groups of 4 k (ROWS / 32) * 512 B apart (SBO).
 template <int ROWS>
 struct TileMap {
-  static constexpr int PER_THREAD = ROWS * 8 / (N_PRODUCER_WARPS * 32);  // float4 per thread per k-block: 4 (A) or 8 (B)
+  static constexpr int PER_THREAD = ROWS * KM_CHUNKS / (N_PRODUCER_WARPS * 32);  // 16-byte chunks per thread per k-block
   uint32_t goff[PER_THREAD];   // global offset (floats) relative to the tile origin at k-block 0
   uint32_t soff[PER_THREAD];   // byte offset inside the stage tile
   __device__ __forceinline__ void init(int ld, bool kmajor, int ptid) {
@@ -128,7 +138,7 @@ struct TileMap {
     for (int j = 0; j < PER_THREAD; ++j) {
       const int i = ptid + j * (N_PRODUCER_WARPS * 32);
       if (kmajor) {
-        const int r = i >> 3, c = i & 7;
+        const int r = i / KM_CHUNKS, c = i % KM_CHUNKS;
         goff[j] = (uint32_t)(r * ld + c * 4);
         soff[j] = sw128(r, c);
       } else {
@@ -151,14 +161,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
   uint8_t* stage_base = smem;
   float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
-  // bars: full[2], empty[2], tmem_full[2], tmem_empty[2], then the TMEM base address
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float* head_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + EPI_BYTES + 256);  // [BN] bias then [HEAD_MAX][BN] head weights
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (2 + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (4 + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (6 + a); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GemmArgs& g = p.g;
@@ -215,9 +225,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
       sts128(lo_addr, __float_as_uint(__uint_as_float(x) - __uint_as_float(x & 0xFFFFE000u)), __float_as_uint(__uint_as_float(y) - __uint_as_float(y & 0xFFFFE000u)),
              __float_as_uint(__uint_as_float(z) - __uint_as_float(z & 0xFFFFE000u)), __float_as_uint(__uint_as_float(w) - __uint_as_float(w & 0xFFFFE000u)));
     };
-    if (total_kb > 0) issue(0);
+    // STAGES - 1 k-blocks of copies are kept in flight; one commit group per loop iteration (empty at the tail) keeps
+    // the wait_group bookkeeping uniform
+    for (int i = 0; i < STAGES - 1; ++i) {
+      if (i < total_kb) issue(i);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     for (int idx = 0; idx < total_kb; ++idx) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's copies of k-block idx have landed
+      if (STAGES == 4) asm volatile("cp.async.wait_group 2;" ::: "memory");  // this thread's copies of k-block idx have landed
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
       const int s = idx % STAGES;
       const uint32_t st = stage0 + s * STAGE_BYTES;
       if (split) {
@@ -229,7 +245,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
       fence_proxy_async();  // generic-proxy / cp.async writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(s));
-      if (idx + 1 < total_kb) issue(idx + 1);  // waits for the MMAs that last read that stage, then refills it asynchronously
+      if (idx + STAGES - 1 < total_kb) issue(idx + STAGES - 1);  // waits for the MMAs that last read that stage, then refills it
+      else asm volatile("cp.async.commit_group;" ::: "memory");
     }
   } else if (warp == N_EPI_WARPS) {
     // ================= MMA issuer (one thread) =================
@@ -239,8 +256,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
       const bool a_km = g.a_kmajor != 0, b_km = g.b_kmajor != 0;
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((a_km ? 0u : 1u) << 15) | ((b_km ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       // per-MMA (K = 8 tf32) advance: 32 bytes inside the swizzled 128-byte row (K-major) or two 4-k groups (MN-major)
-      const uint32_t a_lbo = a_km ? 16u : 512u, a_sbo = a_km ? 1024u : (uint32_t)(BM / 32) * 512u, a_kadv = a_km ? 32u : 2u * a_sbo, a_lt = a_km ? 2u : 1u;
-      const uint32_t b_lbo = b_km ? 16u : 512u, b_sbo = b_km ? 1024u : (uint32_t)(BN / 32) * 512u, b_kadv = b_km ? 32u : 2u * b_sbo, b_lt = b_km ? 2u : 1u;
+      const uint32_t a_lbo = a_km ? 16u : 512u, a_sbo = a_km ? 8u * KM_ROW_BYTES : (uint32_t)(BM / 32) * 512u, a_kadv = a_km ? 32u : 2u * a_sbo, a_lt = a_km ? KM_LAYOUT : 1u;
+      const uint32_t b_lbo = b_km ? 16u : 512u, b_sbo = b_km ? 8u * KM_ROW_BYTES : (uint32_t)(BN / 32) * 512u, b_kadv = b_km ? 32u : 2u * b_sbo, b_lt = b_km ? KM_LAYOUT : 1u;
       uint32_t kb_global = 0, it = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
