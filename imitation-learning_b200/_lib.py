@@ -47,6 +47,10 @@ class SacArgs(C.Structure):
               ('workspace', vp), ('workspace_bytes', C.c_int64)]
 
 
+class BcArgs(C.Structure):
+  _fields_ = [('actor', Mlp), ('opt', Adam), ('batch', Batch), ('R', C.c_int32), ('_pad', C.c_int32), ('out_loss', vp), ('workspace', vp), ('workspace_bytes', C.c_int64)]
+
+
 class Gail(C.Structure):
   _fields_ = [('g', Mlp), ('u', vp), ('v', vp), ('u_stride', C.c_int32), ('v_stride', C.c_int32), ('state_only', C.c_int32), ('reward_function', C.c_int32)]
 
@@ -95,6 +99,8 @@ SIGNATURES = {
   'il_polyak': (C.c_int, [vp, vp, vp, i64, f32, vp]),
   'il_sac_workspace_bytes': (i64, [P(SacArgs)]),
   'il_sac_update': (C.c_int, [vp, P(SacArgs), vp]),
+  'il_bc_workspace_bytes': (i64, [P(BcArgs)]),
+  'il_bc_update': (C.c_int, [vp, P(BcArgs), vp]),
   'il_adam_step': (C.c_int, [vp, vp, vp, P(Adam), i64, vp]),
   'il_replay_append': (C.c_int, [vp, P(Replay), C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]),
   'il_replay_wrap_absorbing': (C.c_int, [vp, P(Replay), C.c_int, vp, vp]),

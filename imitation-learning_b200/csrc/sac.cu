@@ -127,6 +127,39 @@ __global__ void sac_alpha_kernel(float* __restrict__ log_alpha, const float* __r
   }
 }
 
+// behavioural cloning (training.py:57-64): d(-w log pi(a|s) / B) / d(mean, log-std) for a given (clamped) expert action.
+__global__ void bc_head_backward_kernel(const float* __restrict__ head, const float* __restrict__ rows, int64_t rs, int row, int off_action, int off_weight,
+                                        float* __restrict__ dhead, float* __restrict__ row_loss, int R, int B, int A) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)R * B) return;
+  const int r = (int)(i / B), b = (int)(i % B);
+  const float* tr = rows + (int64_t)r * rs + (int64_t)b * row;
+  const float w = tr[off_weight], c = -w / (float)B;
+  const float A_LO = (float)(-1.0 + 1e-6), A_HI = (float)(1.0 - 1e-6), LOG_SQRT_2PI = 0.91893853320467274178f, LOG2 = 0.69314718055994530942f;
+  const float* hd = head + i * 2 * A;
+  float lp = 0.f, ladj = 0.f;
+  for (int j = 0; j < A; ++j) {
+    const float raw = hd[A + j];
+    const bool in_range = raw >= -20.f && raw <= 2.f;
+    const float ls = fminf(fmaxf(raw, -20.f), 2.f), sd = expf(ls), var = sd * sd;
+    const float x = atanhf(fminf(fmaxf(tr[off_action + j], A_LO), A_HI));  // training.py:59, models.py:98
+    const float diff = x - hd[j];
+    lp += -(diff * diff) / (2.f * var) - logf(sd) - LOG_SQRT_2PI;
+    ladj += 2.f * (LOG2 - x - softplusf(-2.f * x));
+    dhead[i * 2 * A + j] = c * diff / var;
+    dhead[i * 2 * A + A + j] = in_range ? c * (diff * diff / var - 1.f) : 0.f;
+  }
+  if (row_loss) row_loss[i] = -w * ((0.f - ladj) + lp);
+}
+
+__global__ void row_mean_kernel(const float* __restrict__ x, float* __restrict__ out, int B) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) s += x[(int64_t)blockIdx.x * B + b];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[blockIdx.x] = s / (float)B;
+}
+
 struct SacWs {
   MlpActs actor_acts, critic_acts;
   float *head, *q, *xn, *y, *lp_next, *dq, *dxa, *dhead, *tmpA, *tmpB, *g_actor, *g_critic;
@@ -244,4 +277,49 @@ extern "C" int il_sac_update(il_handle* h, const il_sac_args* a, void* stream) {
             a->alpha_opt.lr, a->alpha_opt.beta1, a->alpha_opt.beta2, a->alpha_opt.eps, a->alpha_opt.weight_decay, a->out_losses, B);
   // (6) polyak  [training.py:52]
   return il_polyak(h, a->target.params, a->critic.params, (int64_t)2 * R * a->critic.stride, a->polyak_factor, stream);
+}
+
+// ---- behavioural_cloning_update (training.py:57-64) --------------------------------------------------------------------
+namespace {
+struct BcWs {
+  MlpActs acts;
+  float *head, *dhead, *row_loss, *tmpA, *tmpB, *grads;
+  int64_t bytes;
+};
+BcWs bc_layout(const il_bc_args* a, char* base) {
+  BcWs w{};
+  const int R = a->R, B = a->batch.B, A = a->batch.A;
+  char* p = mlp_acts_carve(&a->actor, R, B, base, &w.acts);
+  auto take = [&](int64_t floats) { float* r = reinterpret_cast<float*>(p); carve(p, floats); return r; };
+  w.head = take((int64_t)R * B * 2 * A);
+  w.dhead = take((int64_t)R * B * 2 * A);
+  w.row_loss = take((int64_t)R * B);
+  const int hmax = mlp_max_hidden(&a->actor);
+  w.tmpA = take((int64_t)R * B * hmax);
+  w.tmpB = take((int64_t)R * B * hmax);
+  w.grads = take((int64_t)R * a->actor.stride);
+  w.bytes = p - base;
+  return w;
+}
+}  // namespace
+
+extern "C" int64_t il_bc_workspace_bytes(const il_bc_args* a) { return a ? bc_layout(a, nullptr).bytes : -1; }
+
+extern "C" int il_bc_update(il_handle* h, const il_bc_args* a, void* stream) {
+  IL_CHECK(h && a, "il_bc_update: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R = a->R, B = a->batch.B, S = a->batch.S, A = a->batch.A;
+  IL_TRY(mlp_validate(&a->actor, "il_bc_update(actor)"));
+  IL_CHECK(R > 0 && B > 0 && a->actor.dims[0] == S && a->actor.dims[a->actor.n_layers] == 2 * A, "il_bc_update: actor dims do not match the batch");
+  const RowLayout L = row_layout(S, A);
+  IL_CHECK(a->batch.rows && a->batch.row == L.len && a->workspace && a->workspace_bytes >= il_bc_workspace_bytes(a), "il_bc_update: bad batch / workspace");
+  BcWs w = bc_layout(a, static_cast<char*>(a->workspace));
+  const MatView X{a->batch.rows + L.state, a->batch.replica_stride, 1, L.len};
+  IL_TRY(launch_tick(h, a->opt.step, nullptr, nullptr, st));
+  IL_TRY(mlp_forward(h, &a->actor, R, B, X, w.acts, w.head, (int64_t)B * 2 * A, 2 * A, st));
+  IL_LAUNCH(h, bc_head_backward_kernel, (unsigned)(((int64_t)R * B + 127) / 128), 128, 0, st, w.head, a->batch.rows, a->batch.replica_stride, L.len, L.action, L.weight, w.dhead,
+            a->out_loss ? w.row_loss : nullptr, R, B, A);
+  if (a->out_loss) IL_LAUNCH(h, row_mean_kernel, R, 256, 0, st, w.row_loss, a->out_loss, B);
+  IL_TRY(mlp_backward(h, &a->actor, R, B, X, w.acts, MatView{w.dhead, (int64_t)B * 2 * A, 1, 2 * A}, w.grads, a->actor.stride, nullptr, 0, 0, 0, 0, w.tmpA, w.tmpB, st));
+  return launch_adam(h, a->actor.params, w.grads, &a->opt, (int64_t)R * a->actor.stride, st);
 }

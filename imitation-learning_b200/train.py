@@ -26,7 +26,7 @@ from .models import GAILDiscriminator, GMMILDiscriminator, PWILDiscriminator, So
 from .net import ReplicaRNG
 from .optim import Adam, AdamW
 
-ACCELERATED = ['SAC', 'GAIL', 'GMMIL', 'PWIL']
+ACCELERATED = ['BC', 'SAC', 'GAIL', 'GMMIL', 'PWIL']
 
 
 def check_config(cfg: Config):
@@ -49,7 +49,6 @@ def check_config(cfg: Config):
   assert cfg.logging.interval >= 0
   if cfg.algorithm not in ACCELERATED:
     raise NotImplementedError(f'algorithm={cfg.algorithm} is outside the accelerated hot path (BASELINE.json north_star; SURVEY §8f); supported: {ACCELERATED}')
-  if cfg.bc_pretraining.iterations > 0 or cfg.imitation.bc_aux_loss: raise NotImplementedError('BC pretraining / bc_aux_loss are not on the accelerated path yet (SURVEY §8f item 3)')
 
 
 class Trainer:
@@ -70,7 +69,8 @@ class Trainer:
     self.env.seed(seed)
     self.eval_env.seed(seed)
     self.normalization_max, self.normalization_min = self.env.env.ref_max_score, self.env.env.ref_min_score
-    self.expert_memory = self.env.get_dataset(trajectories=cfg.imitation.trajectories, subsample=cfg.imitation.subsample) if self.algorithm != 'SAC' else None
+    need_expert = self.algorithm != 'SAC' or cfg.bc_pretraining.iterations > 0 or cfg.imitation.bc_aux_loss
+    self.expert_memory = self.env.get_dataset(trajectories=cfg.imitation.trajectories, subsample=cfg.imitation.subsample) if need_expert else None
     self.S, self.A = S, A = self.env.observation_space.shape[0], self.env.action_space.shape[0]
     # train.py:64-67 — replica r draws its initial weights from the stream of seed + r (fast_init: one stream, replicated)
     rng = None if (R == 1 or fast_init) else ReplicaRNG(seed, R)
@@ -182,11 +182,33 @@ class Trainer:
       if self.algorithm == 'GAIL': self.discriminator.predict_reward_batch(self.batch, write_rewards=True)  # train.py:194
       else: self.discriminator.predict_reward_batch(self.batch, self.expert_batch, reward_out=self.batch.rows[..., self.batch.off['rewards']])  # train.py:196
     from .training import sac_update
+    if cfg.imitation.bc_aux_loss:  # train.py:201
+      from .training import behavioural_cloning_update
+      behavioural_cloning_update(self.actor, self.expert_batch, self.actor_optimiser)
     if not self.inject:
       self.rng.normal(None, self.device, stream_id=6, out=self.eps_next)
       self.rng.normal(None, self.device, stream_id=7, out=self.eps_new)
     sac_update(self.actor, self.critic, self.log_alpha, self.target_critic, self.batch, self.actor_optimiser, self.critic_optimiser, self.temperature_optimiser,
                cfg.reinforcement.discount, self.entropy_target, cfg.reinforcement.polyak_factor, eps_next=self.eps_next, eps_new=self.eps_new, out=self.sac_out)  # train.py:203
+
+  def bc_pretrain(self, iterations: Optional[int] = None) -> Tensor:
+    """train.py:93-99: `iterations` behavioural-cloning steps on epoch-wise shuffled expert minibatches (drop_last), with a
+    separate AdamW (bc_pretraining.learning_rate / weight_decay). Every replica draws its own permutations (host RNG, like
+    the reference's DataLoader; the exact DataLoader stream is not reproduced). Returns the last per-replica loss."""
+    from .training import behavioural_cloning_update
+    cfg, B, n = self.cfg, self.B, self.expert_memory.size
+    iterations = cfg.bc_pretraining.iterations if iterations is None else iterations
+    opt = AdamW(self.actor.parameters(), lr=cfg.bc_pretraining.learning_rate, weight_decay=cfg.bc_pretraining.weight_decay)
+    loss = torch.zeros(self.R, device=self.device)
+    per_epoch = max(n // B, 1)
+    perm = None
+    for it in range(iterations):
+      if it % per_epoch == 0: perm = torch.stack([torch.randperm(n) for _ in range(self.R)]).to(self.device, torch.int32)
+      j = it % per_epoch
+      idx = perm[:, j * B:(j + 1) * B] if n >= B else perm[:, torch.arange(B) % n]
+      self.expert_memory.gather(idx.contiguous(), out=self.expert_batch)
+      behavioural_cloning_update(self.actor, self.expert_batch, opt, out_loss=loss)
+    return loss
 
   def _will_update(self, step: int) -> bool:
     return step >= self.cfg.training.start and step % self.cfg.training.interval == 0  # train.py:171
@@ -268,6 +290,18 @@ def train(cfg: Config, file_prefix: str = '') -> float:
   trainer = Trainer(cfg, replicas=hi - lo, seed_offset=lo)
   metrics, score = trainer.metrics, trainer.score
   start_time = time.time()
+  if cfg.bc_pretraining.iterations > 0:  # train.py:93-112
+    trainer.bc_pretrain()
+    if cfg.algorithm == 'BC':
+      returns = trainer.evaluate()
+      mean, std, n = distributed.return_statistics(returns)
+      normalized = (returns.cpu().numpy() - trainer.normalization_min) / (trainer.normalization_max - trainer.normalization_min)
+      metrics['test_steps'], metrics['test_returns'], metrics['test_returns_normalized'] = [0], [returns.cpu().numpy().tolist()], [normalized.tolist()]
+      if rank == 0:
+        print(f'BC: test return {mean:.3f} +- {std:.3f} over {n} episodes', flush=True)
+        torch.save(dict(actor=trainer.actor.state_dict()), f'{file_prefix}agent.pth')  # train.py:108
+        torch.save(metrics, f'{file_prefix}metrics.pth')
+      return float(np.mean(normalized))
   for step in range(1, cfg.steps + 1):
     trainer.train_step()
     if cfg.logging.interval > 0 and step % cfg.logging.interval == 0 and trainer.updates > 0: trainer.log_aux()

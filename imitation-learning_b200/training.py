@@ -88,8 +88,16 @@ def adversarial_imitation_update(actor: SoftActor, discriminator: GAILDiscrimina
   _lib.check(_lib.lib().il_gail_update(_lib.handle(), C.byref(a), _lib.stream()))
 
 
-def behavioural_cloning_update(actor, expert_transition, actor_optimiser):
-  raise NotImplementedError('behavioural_cloning_update (training.py:57-64) is not on the accelerated path yet (SURVEY §8f item 3)')
+def behavioural_cloning_update(actor: SoftActor, expert_transition, actor_optimiser: Adam, out_loss: Optional[Tensor] = None):
+  """training.py:57-64: one maximum-likelihood step of the actor on expert (state, action, weight) rows."""
+  R, device = actor.replicas, actor.device
+  batch, _ = _as_batch(expert_transition, device)
+  a = _lib.BcArgs()
+  a.actor, a.opt, a.batch, a.R, a.out_loss = actor.mlp.c_struct(), actor_optimiser.c_struct(), batch.c_struct(), R, _lib.ptr(out_loss)
+  need = _lib.lib().il_bc_workspace_bytes(C.byref(a))
+  ws = _workspace('bc', need, device)
+  a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+  _lib.check(_lib.lib().il_bc_update(_lib.handle(), C.byref(a), _lib.stream()))
 
 
 def target_estimation_update(discriminator, expert_transition, discriminator_optimiser):

@@ -149,6 +149,20 @@ typedef struct il_sac_args {
 int64_t il_sac_workspace_bytes(const il_sac_args* a);
 int il_sac_update(il_handle* h, const il_sac_args* a, void* stream);
 
+/* ---- behavioural_cloning_update (training.py:57-64): maximum-likelihood step of the actor on expert (state, action) rows */
+typedef struct il_bc_args {
+  il_mlp   actor;
+  il_adam  opt;                     /* train.py:95 pretraining optimiser or the actor optimiser (train.py:201) */
+  il_batch batch;                   /* expert transitions; uses states, actions, weights */
+  int32_t  R;
+  int32_t  _pad;
+  float*   out_loss;                /* [R] mean(weight * -log_prob) (may be NULL) */
+  void*    workspace;               /* il_bc_workspace_bytes */
+  int64_t  workspace_bytes;
+} il_bc_args;
+int64_t il_bc_workspace_bytes(const il_bc_args* a);
+int il_bc_update(il_handle* h, const il_bc_args* a, void* stream);
+
 /* AdamW step over a flat buffer (used by the fused updates; exposed for tests): torch _single_tensor_adam. */
 int il_adam_step(il_handle* h, float* params, const float* grads, const il_adam* opt, int64_t n, void* stream);
 

@@ -24,6 +24,8 @@ CASES: Dict[str, dict] = {
   'sac_small': dict(kind='sac', S=12, A=3, H=32, B=16, steps=2, seed=21, discount=0.97, entropy_target=-1.5, polyak=0.99, lr=3e-4, wd=0.0),
   'sac_small_wd': dict(kind='sac', S=18, A=6, H=48, B=24, steps=3, seed=22, discount=0.99, entropy_target=-6.0, polyak=0.995, lr=1e-3, wd=0.01),
   'sac_hopper': dict(kind='sac', S=12, A=3, H=256, B=256, steps=2, seed=23, discount=0.97, entropy_target=-1.5, polyak=0.99, lr=3e-4, wd=0.0),
+  'bc_small': dict(kind='bc', S=12, A=3, H=32, B=24, steps=3, seed=25, lr=2.5e-4, wd=0.01),
+  'bc_hopper': dict(kind='bc', S=12, A=3, H=256, B=256, steps=2, seed=26, lr=2.5e-4, wd=0.0),
   'gail_default': dict(kind='gail', S=12, A=3, H=64, B=256, steps=2, seed=31, spectral_norm=True, grad_penalty=1.0, entropy_bonus=0.0, loss='BCE', lr=3e-5, wd=10.0, reward='AIRL'),
   'gail_entropy_nosn': dict(kind='gail', S=18, A=6, H=32, B=64, steps=2, seed=32, spectral_norm=False, grad_penalty=0.5, entropy_bonus=0.1, loss='BCE', lr=1e-3, wd=0.1, reward='GAIL'),
   'gail_pugail': dict(kind='gail', S=12, A=3, H=64, B=64, steps=2, seed=33, spectral_norm=True, grad_penalty=1.0, entropy_bonus=0.0, loss='PUGAIL', lr=1e-3, wd=0.0, reward='FAIRL'),
@@ -83,6 +85,11 @@ def make_inputs(name: str, seed_offset: int = 0) -> Dict[str, np.ndarray]:
       for key, v in _batch(rs, c['B'], S, A).items(): inp[f'b{s}_{key}'] = v
       inp[f'b{s}_eps_next'] = rs.standard_normal((c['B'], A)).astype(np.float32)
       inp[f'b{s}_eps_new'] = rs.standard_normal((c['B'], A)).astype(np.float32)
+  elif k == 'bc':
+    for i, w in enumerate(_mlp_weights(rs, [c['S'], c['H'], c['H'], 2 * c['A']])): inp[f'actor_{i}'] = w
+    for s in range(c['steps']):
+      for key, v in _batch(rs, c['B'], c['S'], c['A']).items(): inp[f'b{s}_{key}'] = v
+      inp[f'b{s}_actions'][0, 0] = 1.0  # exercises the clamp at training.py:59
   elif k == 'gail':
     S, A, H = c['S'], c['A'], c['H']
     for i, w in enumerate(_mlp_weights(rs, [S + A, H, 1], scale=1.5)): inp[f'g_{i}'] = w
@@ -156,6 +163,13 @@ def run_port(name: str, inp: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
     for which in ('actor', 'critic', 'alpha'):
       m, v = agent.adam_state(which)
       for i, (mi, vi) in enumerate(zip(m, v)): out[f'adam_{which}_m_{i}'], out[f'adam_{which}_v_{i}'] = _np(mi), _np(vi)
+  elif k == 'bc':
+    actor = [torch.nn.Parameter(_t(inp[f'actor_{i}']).clone()) for i in range(6)]
+    opt = torch.optim.AdamW(actor, lr=c['lr'], weight_decay=c['wd'])
+    for s in range(c['steps']): out[f's{s}_loss'] = _np(port.behavioural_cloning_update(actor, opt, _batch_from(inp, f'b{s}_')))
+    for i, p in enumerate(actor):
+      out[f'actor_{i}'] = _np(p)
+      out[f'adam_m_{i}'], out[f'adam_v_{i}'] = _np(opt.state[p]['exp_avg']), _np(opt.state[p]['exp_avg_sq'])
   elif k == 'gail':
     g = [_t(inp[f'g_{i}']) for i in range(4)]
     sn = [(port._l2_normalise(_t(inp[f'u_{l}'])), port._l2_normalise(_t(inp[f'v_{l}']))) for l in range(2)] if c['spectral_norm'] else None
@@ -278,6 +292,14 @@ def run_reference(name: str, inp: Dict[str, np.ndarray]) -> Dict[str, np.ndarray
     out['log_alpha'] = _np(log_alpha)
     for which, opt, params in (('actor', oa, list(actor.parameters())), ('critic', oc, list(critic.parameters())), ('alpha', ot, [log_alpha])):
       for i, p in enumerate(params): out[f'adam_{which}_m_{i}'], out[f'adam_{which}_v_{i}'] = _np(opt.state[p]['exp_avg']), _np(opt.state[p]['exp_avg_sq'])
+  elif k == 'bc':
+    actor = ref.models.SoftActor(c['S'], c['A'], model_cfg(c['H']))
+    _load_mlp(actor.actor, [inp[f'actor_{i}'] for i in range(6)])
+    opt = torch.optim.AdamW(actor.parameters(), lr=c['lr'], weight_decay=c['wd'])
+    for s in range(c['steps']): ref.training.behavioural_cloning_update(actor, _batch_from(inp, f'b{s}_'), opt)
+    for i, p in enumerate(actor.parameters()):
+      out[f'actor_{i}'] = _np(p)
+      out[f'adam_m_{i}'], out[f'adam_v_{i}'] = _np(opt.state[p]['exp_avg']), _np(opt.state[p]['exp_avg_sq'])
   elif k == 'gail':
     S, A, H = c['S'], c['A'], c['H']
     icfg = DC(state_only=False, spectral_norm=c['spectral_norm'], loss_function=c['loss'], grad_penalty=c['grad_penalty'], mixup_alpha=1, entropy_bonus=c['entropy_bonus'],

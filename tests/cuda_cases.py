@@ -95,6 +95,19 @@ def run_cuda(name, inps):
       _export(actor.mlp, r, 0, 'adam_actor_v', outs[r], oa.exp_avg_sq)
       outs[r]['log_alpha'] = _np(log_alpha[r:r + 1])
       outs[r]['adam_alpha_m_0'], outs[r]['adam_alpha_v_0'] = _np(ot.exp_avg[r:r + 1]), _np(ot.exp_avg_sq[r:r + 1])
+  elif k == 'bc':
+    S, A = c['S'], c['A']
+    actor = il_b200.SoftActor(S, A, mcfg, replicas=R)
+    _load_mlp(actor.mlp, inps, 'actor')
+    opt = il_b200.AdamW(actor.parameters(), lr=c['lr'], weight_decay=c['wd'])
+    for s in range(c['steps']):
+      loss = torch.empty(R, device=DEV)
+      il_b200.behavioural_cloning_update(actor, _batch(inps, f'b{s}_', S, A), opt, out_loss=loss)
+      for r in range(R): outs[r][f's{s}_loss'] = _np(loss[r])
+    for r in range(R):
+      _export(actor.mlp, r, 0, 'actor', outs[r])
+      _export(actor.mlp, r, 0, 'adam_m', outs[r], opt.exp_avg)
+      _export(actor.mlp, r, 0, 'adam_v', outs[r], opt.exp_avg_sq)
   elif k == 'gail':
     S, A, H = c['S'], c['A'], c['H']
     icfg = Cfg(state_only=False, spectral_norm=c['spectral_norm'], loss_function=c['loss'], grad_penalty=c['grad_penalty'], mixup_alpha=1, entropy_bonus=c['entropy_bonus'],

@@ -183,3 +183,18 @@ def test_device_index_sampling_respects_memory_py_rules():
   u = torch.rand(2, 64, device='cuda')
   idx_u = mem.sample_indices_device(64, uniform=u)
   assert int(idx_u.max()) <= 9 and not bool((idx_u == 4).any())
+
+
+def test_bc_pretraining_reduces_the_cloning_loss():
+  """BASELINE.json configs[0] (BC hopper, 5 expert trajectories) on the accelerated path: the maximum-likelihood loss of
+  training.py:62 must go down over pretraining, for every replica."""
+  import il_b200
+  from il_b200.config import load_config
+  from il_b200.train import Trainer
+  cfg = load_config(['algorithm=BC', 'env=hopper', 'steps=10', 'bc_pretraining.iterations=150', 'training.batch_size=64', 'imitation.trajectories=5', 'reinforcement.actor.hidden_size=64',
+                     'reinforcement.critic.hidden_size=64', 'replicas=3', 'seed=2', 'bc_pretraining.learning_rate=0.001'])
+  tr = Trainer(cfg)
+  first = tr.bc_pretrain(1).clone()
+  last = tr.bc_pretrain(150)
+  assert bool((last < first).all()), (first, last)
+  assert bool(torch.isfinite(last).all())
