@@ -245,13 +245,13 @@ __global__ void __launch_bounds__(256, 2) gemm_grouped_kernel(const GemmArgs p) 
 // Thin-contraction kernel (K <= 32, wide output): the first layer of every MLP (K = state size) and the backward of
 // the last layer (K = head width). These products are pure output bandwidth, so the tile loop of the general kernel is
 // replaced by: B (K x 256) and 32 rows of A in shared memory, 8 x 4 outputs per thread, 128-bit coalesced stores.
-constexpr int TK_MAXK = 32, TK_ROWS = 32, TK_COLS = 256;
+constexpr int TK_MAXK = 32, TK_ROWS = 32, TK_COLS = 256, TK_LDA = TK_MAXK + 4;
 template <bool B_KMAJOR>
 __global__ void __launch_bounds__(256) gemm_thin_k_kernel(const GemmArgs p) {
   __shared__ __align__(16) float Bs[TK_MAXK][TK_COLS];
-  __shared__ float As[TK_ROWS][TK_MAXK + 1];
+  __shared__ __align__(16) float As[TK_ROWS][TK_LDA];  // K zero-padded to a multiple of 4 so rows are read as float4
   const int tid = threadIdx.x, g = blockIdx.z, m0 = blockIdx.y * TK_ROWS, n0 = blockIdx.x * TK_COLS;
-  const int M = p.M, N = p.N, K = p.K;
+  const int M = p.M, N = p.N, K = p.K, K4 = (K + 3) & ~3;
   const float* __restrict__ A = p.A + (int64_t)(g / p.a_gdiv) * p.a_gs;
   const float* __restrict__ B = p.B + (int64_t)(g / p.b_gdiv) * p.b_gs;
   const int ncols = min(TK_COLS, N - n0);
@@ -266,9 +266,10 @@ __global__ void __launch_bounds__(256) gemm_thin_k_kernel(const GemmArgs p) {
       Bs[k][n] = __ldg(B + (int64_t)k * p.ldb + n0 + n);
     }
   }
-  for (int idx = tid; idx < TK_ROWS * K; idx += 256) {
-    const int r = idx / K, k = idx % K;
-    As[r][k] = (m0 + r < M) ? __ldg(A + (int64_t)(m0 + r) * p.lda + k) : 0.f;
+  for (int idx = tid; idx < (K4 - K) * TK_COLS; idx += 256) Bs[K + idx / TK_COLS][idx % TK_COLS] = 0.f;
+  for (int idx = tid; idx < TK_ROWS * K4; idx += 256) {
+    const int r = idx / K4, k = idx % K4;
+    As[r][k] = (m0 + r < M && k < K) ? __ldg(A + (int64_t)(m0 + r) * p.lda + k) : 0.f;
   }
   __syncthreads();
   const int n = (tid & 63) * 4, tr = tid >> 6;
@@ -276,13 +277,16 @@ __global__ void __launch_bounds__(256) gemm_thin_k_kernel(const GemmArgs p) {
   float acc[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-  for (int k = 0; k < K; ++k) {
-    const float4 b = *reinterpret_cast<const float4*>(&Bs[k][n]);
+  for (int k = 0; k < K4; k += 4) {
+    const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][n]), b1 = *reinterpret_cast<const float4*>(&Bs[k + 1][n]);
+    const float4 b2 = *reinterpret_cast<const float4*>(&Bs[k + 2][n]), b3 = *reinterpret_cast<const float4*>(&Bs[k + 3][n]);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float a = As[tr + 4 * i][k];
-      acc[i][0] = fmaf(a, b.x, acc[i][0]); acc[i][1] = fmaf(a, b.y, acc[i][1]);
-      acc[i][2] = fmaf(a, b.z, acc[i][2]); acc[i][3] = fmaf(a, b.w, acc[i][3]);
+      const float4 a = *reinterpret_cast<const float4*>(&As[tr + 4 * i][k]);  // warp-uniform address: one broadcast load for 4 k
+      acc[i][0] = fmaf(a.x, b0.x, acc[i][0]); acc[i][1] = fmaf(a.x, b0.y, acc[i][1]); acc[i][2] = fmaf(a.x, b0.z, acc[i][2]); acc[i][3] = fmaf(a.x, b0.w, acc[i][3]);
+      acc[i][0] = fmaf(a.y, b1.x, acc[i][0]); acc[i][1] = fmaf(a.y, b1.y, acc[i][1]); acc[i][2] = fmaf(a.y, b1.z, acc[i][2]); acc[i][3] = fmaf(a.y, b1.w, acc[i][3]);
+      acc[i][0] = fmaf(a.z, b2.x, acc[i][0]); acc[i][1] = fmaf(a.z, b2.y, acc[i][1]); acc[i][2] = fmaf(a.z, b2.z, acc[i][2]); acc[i][3] = fmaf(a.z, b2.w, acc[i][3]);
+      acc[i][0] = fmaf(a.w, b3.x, acc[i][0]); acc[i][1] = fmaf(a.w, b3.y, acc[i][1]); acc[i][2] = fmaf(a.w, b3.z, acc[i][2]); acc[i][3] = fmaf(a.w, b3.w, acc[i][3]);
     }
   }
   float* __restrict__ C = p.C + (int64_t)g * p.c_gs;
@@ -331,6 +335,10 @@ int launch_cfg(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
+static bool gemm_uses_tc(const il_handle* h, const GemmArgs& a) {
+  return a.M >= 128 && a.N >= 128 && a.K >= 128 && h->gemm_mode != IL_GEMM_FP32 && tc_gemm_eligible(a);
+}
+
 int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   IL_CHECK(a.M > 0 && a.N > 0 && a.K > 0 && a.G > 0, "gemm: empty problem M=%d N=%d K=%d G=%d", a.M, a.N, a.K, a.G);
   IL_CHECK(a.G <= 65535, "gemm: too many groups (%d)", a.G);
@@ -346,7 +354,7 @@ int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   if (a.N <= 16) return launch_cfg<128, 16, 8, 1>(h, a, stream);
   if (a.M <= 32) return launch_cfg<32, 128, 2, 8>(h, a, stream);
   const bool dense = a.M >= 128 && a.N >= 128 && a.K >= 128;  // the H x H hidden-layer contractions
-  const bool tc = dense && h->gemm_mode != IL_GEMM_FP32 && tc_gemm_eligible(a);
+  const bool tc = gemm_uses_tc(h, a);
   auto run = [&]() { return tc ? launch_tc_gemm(h, a, stream) : launch_cfg<128, 128, 8, 8>(h, a, stream); };
   if (h->profiling && dense) {
     ProfiledLaunch pl;
