@@ -163,6 +163,80 @@ __global__ void actor_head_kernel(const HeadFwdArgs p) {
   if (want_lp) p.log_prob[row] = __fadd_rn(__fsub_rn(0.f, sum_ladj), sum_nlp);
 }
 
+// Whole-MLP forward for a few rows per net (rollout: n = 1 per replica, train.py:152; batched evaluation: n = episodes):
+// one CTA per (net, block of NR rows); activations ping-pong in shared memory, every weight row is streamed once per CTA
+// with coalesced 128-bit loads (one warp per output unit) — a GEMV that is bound by reading the parameters.
+struct SmallFwdArgs {
+  il_mlp m;
+  MlpOffsets o;
+  const float* X;
+  int64_t x_gs;
+  int x_gdiv, ldx, n, maxd;
+  float* out;  // [G, n, dims[L]]
+};
+template <int NR>
+__global__ void __launch_bounds__(256) mlp_small_forward_kernel(const SmallFwdArgs p) {
+  extern __shared__ __align__(16) float sm[];
+  const int g = blockIdx.x, r0 = blockIdx.y * NR, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nr = min(NR, p.n - r0), L = p.m.n_layers, maxd = p.maxd;
+  float* bufs[2] = {sm, sm + NR * maxd};
+  const float* X = p.X + (int64_t)(g / p.x_gdiv) * p.x_gs;
+  for (int idx = tid; idx < NR * p.m.dims[0]; idx += 256) {
+    const int r = idx / p.m.dims[0], k = idx % p.m.dims[0];
+    bufs[0][r * maxd + k] = r < nr ? __ldg(X + (int64_t)(r0 + r) * p.ldx + k) : 0.f;
+  }
+  __syncthreads();
+  const float* prm = p.m.params + (int64_t)g * p.m.stride;
+  for (int l = 0; l < L; ++l) {
+    const int in = p.m.dims[l], od = p.m.dims[l + 1];
+    const float* W = prm + p.o.w[l];
+    const float* bias = prm + p.o.b[l];
+    const float* xin = bufs[l & 1];
+    float* xout = bufs[(l + 1) & 1];
+    const bool vec = (in % 4 == 0) && (p.m.stride % 4 == 0);
+    for (int o = warp; o < od; o += 8) {
+      float acc[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc[r] = 0.f;
+      const float* wr = W + (int64_t)o * in;
+      if (vec) {
+        for (int k = lane * 4; k < in; k += 128) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + k));
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            const float4 x4 = *reinterpret_cast<const float4*>(xin + r * maxd + k);
+            acc[r] = fmaf(w4.x, x4.x, fmaf(w4.y, x4.y, fmaf(w4.z, x4.z, fmaf(w4.w, x4.w, acc[r]))));
+          }
+        }
+      } else {
+        for (int k = lane; k < in; k += 32) {
+          const float w = __ldg(wr + k);
+#pragma unroll
+          for (int r = 0; r < NR; ++r) acc[r] = fmaf(w, xin[r * maxd + k], acc[r]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc[r] = warp_sum(acc[r]);
+      if (lane == 0) {
+        const float b = __ldg(bias + o);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          float v = acc[r] + b;
+          if (l < L - 1) v = act_apply(v, p.m.activation);
+          xout[r * maxd + o] = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int od = p.m.dims[L];
+  const float* fin = bufs[L & 1];
+  for (int idx = tid; idx < nr * od; idx += 256) {
+    const int r = idx / od, o = idx % od;
+    p.out[((int64_t)g * p.n + r0 + r) * od + o] = fin[r * maxd + o];
+  }
+}
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, const int64_t* __restrict__ step,
                             double lr, double beta1_d, double beta2_d, double eps_d, double wd, int64_t n) {
   __shared__ float s_step_size, s_bc2_sqrt;
@@ -247,6 +321,23 @@ int launch_tick(il_handle* h, int64_t* s0, int64_t* s1, int64_t* s2, cudaStream_
   return 0;
 }
 
+// n <= 32 rows per net: the fused whole-MLP kernel (parameter-bandwidth bound) instead of per-layer GEMMs.
+int mlp_small_forward(il_handle* h, const il_mlp* m, int G, int n, MatView X, float* out, cudaStream_t stream) {
+  SmallFwdArgs a;
+  a.m = *m; a.o = mlp_offsets(m->dims, m->n_layers);
+  a.X = X.ptr; a.x_gs = X.gs; a.x_gdiv = X.gdiv; a.ldx = X.ld; a.n = n; a.out = out;
+  int maxd = 4;
+  for (int l = 0; l <= m->n_layers; ++l) maxd = m->dims[l] > maxd ? m->dims[l] : maxd;
+  a.maxd = (maxd + 3) / 4 * 4;
+  if (n == 1) {
+    IL_LAUNCH(h, mlp_small_forward_kernel<1>, dim3(G, 1), 256, (size_t)2 * 1 * a.maxd * 4, stream, a);
+  } else {
+    IL_CHECK((size_t)2 * 8 * a.maxd * 4 <= 48 * 1024, "mlp_small_forward: layer width %d too large", maxd);
+    IL_LAUNCH(h, mlp_small_forward_kernel<8>, dim3(G, (n + 7) / 8), 256, (size_t)2 * 8 * a.maxd * 4, stream, a);
+  }
+  return 0;
+}
+
 extern "C" int il_adam_step(il_handle* h, float* params, const float* grads, const il_adam* opt, int64_t n, void* stream) {
   IL_CHECK(h && params && grads && opt, "il_adam_step: null argument");
   IL_TRY(launch_tick(h, opt->step, nullptr, nullptr, (cudaStream_t)stream));
@@ -277,7 +368,8 @@ extern "C" int il_actor_forward(il_handle* h, const il_mlp* actor, int R, int n,
   MlpActs acts;
   char* ws = mlp_acts_carve(actor, R, n, static_cast<char*>(workspace), &acts);
   float* head = reinterpret_cast<float*>(ws);
-  IL_TRY(mlp_forward(h, actor, R, n, MatView{states, states_rs, 1, ld_states}, acts, head, (int64_t)n * out, out, (cudaStream_t)stream));
+  if (n <= 32) IL_TRY(mlp_small_forward(h, actor, R, n, MatView{states, states_rs, 1, ld_states}, head, (cudaStream_t)stream));
+  else IL_TRY(mlp_forward(h, actor, R, n, MatView{states, states_rs, 1, ld_states}, acts, head, (int64_t)n * out, out, (cudaStream_t)stream));
   HeadFwdArgs a{};
   a.head = head; a.eps = eps; a.given = given_action;
   a.action = action; a.action_rs = (int64_t)n * (out / 2); a.ld_action = out / 2;

@@ -24,12 +24,15 @@ CASES: Dict[str, dict] = {
   'sac_small': dict(kind='sac', S=12, A=3, H=32, B=16, steps=2, seed=21, discount=0.97, entropy_target=-1.5, polyak=0.99, lr=3e-4, wd=0.0),
   'sac_small_wd': dict(kind='sac', S=18, A=6, H=48, B=24, steps=3, seed=22, discount=0.99, entropy_target=-6.0, polyak=0.995, lr=1e-3, wd=0.01),
   'sac_hopper': dict(kind='sac', S=12, A=3, H=256, B=256, steps=2, seed=23, discount=0.97, entropy_target=-1.5, polyak=0.99, lr=3e-4, wd=0.0),
+  'sac_ant_small': dict(kind='sac', S=112, A=8, H=64, B=32, steps=2, seed=24, discount=0.99, entropy_target=-8.0, polyak=0.995, lr=3e-4, wd=0.0),
   'bc_small': dict(kind='bc', S=12, A=3, H=32, B=24, steps=3, seed=25, lr=2.5e-4, wd=0.01),
   'bc_hopper': dict(kind='bc', S=12, A=3, H=256, B=256, steps=2, seed=26, lr=2.5e-4, wd=0.0),
   'gail_default': dict(kind='gail', S=12, A=3, H=64, B=256, steps=2, seed=31, spectral_norm=True, grad_penalty=1.0, entropy_bonus=0.0, loss='BCE', lr=3e-5, wd=10.0, reward='AIRL'),
   'gail_entropy_nosn': dict(kind='gail', S=18, A=6, H=32, B=64, steps=2, seed=32, spectral_norm=False, grad_penalty=0.5, entropy_bonus=0.1, loss='BCE', lr=1e-3, wd=0.1, reward='GAIL'),
   'gail_pugail': dict(kind='gail', S=12, A=3, H=64, B=64, steps=2, seed=33, spectral_norm=True, grad_penalty=1.0, entropy_bonus=0.0, loss='PUGAIL', lr=1e-3, wd=0.0, reward='FAIRL'),
   'gail_mixup': dict(kind='gail', S=12, A=3, H=64, B=64, steps=2, seed=34, spectral_norm=True, grad_penalty=0.0, entropy_bonus=0.0, loss='Mixup', lr=1e-3, wd=0.0, reward='AIRL'),
+  'gail_ant': dict(kind='gail', S=112, A=8, H=64, B=96, steps=2, seed=35, spectral_norm=True, grad_penalty=1.0, entropy_bonus=0.05, loss='BCE', lr=3e-5, wd=10.0, reward='AIRL'),
+  'gmmil_ant': dict(kind='gmmil', S=112, A=8, B=300, seed=43),
   'gmmil_hopper': dict(kind='gmmil', S=12, A=3, B=64, seed=41),
   'gmmil_halfcheetah': dict(kind='gmmil', S=18, A=6, B=256, seed=42),
   'pwil_small': dict(kind='pwil', S=12, A=3, N=150, T=40, steps=100, seed=51),
