@@ -245,66 +245,67 @@ __global__ void __launch_bounds__(256, 2) gemm_grouped_kernel(const GemmArgs p) 
 // Thin-contraction kernel (K <= 32, wide output): the first layer of every MLP (K = state size) and the backward of
 // the last layer (K = head width). These products are pure output bandwidth, so the tile loop of the general kernel is
 // replaced by: B (K x 256) and 32 rows of A in shared memory, 8 x 4 outputs per thread, 128-bit coalesced stores.
-constexpr int TK_MAXK = 32, TK_ROWS = 32, TK_COLS = 256, TK_LDA = TK_MAXK + 4;
+constexpr int TK_MAXK = 32, TK_ROWS = 32, TK_ITERS = 4, TK_COLS = 256, TK_LDA = TK_MAXK + 4;  // a CTA covers 4 x 32 rows
 template <bool B_KMAJOR>
 __global__ void __launch_bounds__(256) gemm_thin_k_kernel(const GemmArgs p) {
   __shared__ __align__(16) float Bs[TK_MAXK][TK_COLS];
   __shared__ __align__(16) float As[TK_ROWS][TK_LDA];  // K zero-padded to a multiple of 4 so rows are read as float4
-  const int tid = threadIdx.x, g = blockIdx.z, m0 = blockIdx.y * TK_ROWS, n0 = blockIdx.x * TK_COLS;
+  const int tid = threadIdx.x, g = blockIdx.z, n0 = blockIdx.x * TK_COLS;
   const int M = p.M, N = p.N, K = p.K, K4 = (K + 3) & ~3;
   const float* __restrict__ A = p.A + (int64_t)(g / p.a_gdiv) * p.a_gs;
   const float* __restrict__ B = p.B + (int64_t)(g / p.b_gdiv) * p.b_gs;
   const int ncols = min(TK_COLS, N - n0);
-  if (B_KMAJOR) {  // B stored [N, K]: rows n0.. are contiguous when ldb == K
-    for (int idx = tid; idx < ncols * K; idx += 256) {
-      const int n = idx / K, k = idx % K;
-      Bs[k][n] = __ldg(B + (int64_t)(n0 + n) * p.ldb + k);
-    }
-  } else {  // B stored [K, N]
-    for (int idx = tid; idx < K * ncols; idx += 256) {
-      const int k = idx / ncols, n = idx % ncols;
-      Bs[k][n] = __ldg(B + (int64_t)k * p.ldb + n0 + n);
-    }
+  // B (K x ncols) staged once per CTA; consecutive threads -> consecutive n (conflict-free shared stores; the strided
+  // global reads of the [N, K] weight layout stay in L1/L2: the whole matrix is K * N * 4 <= 32 KB)
+  for (int idx = tid; idx < K4 * TK_COLS; idx += 256) {
+    const int k = idx / TK_COLS, n = idx % TK_COLS;
+    float v = 0.f;
+    if (k < K && n < ncols) v = B_KMAJOR ? __ldg(B + (int64_t)(n0 + n) * p.ldb + k) : __ldg(B + (int64_t)k * p.ldb + n0 + n);
+    Bs[k][n] = v;
   }
-  for (int idx = tid; idx < (K4 - K) * TK_COLS; idx += 256) Bs[K + idx / TK_COLS][idx % TK_COLS] = 0.f;
-  for (int idx = tid; idx < TK_ROWS * K4; idx += 256) {
-    const int r = idx / K4, k = idx % K4;
-    As[r][k] = (m0 + r < M && k < K) ? __ldg(A + (int64_t)(m0 + r) * p.lda + k) : 0.f;
-  }
-  __syncthreads();
   const int n = (tid & 63) * 4, tr = tid >> 6;
-  if (n >= ncols) return;
-  float acc[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-  for (int k = 0; k < K4; k += 4) {
-    const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][n]), b1 = *reinterpret_cast<const float4*>(&Bs[k + 1][n]);
-    const float4 b2 = *reinterpret_cast<const float4*>(&Bs[k + 2][n]), b3 = *reinterpret_cast<const float4*>(&Bs[k + 3][n]);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[tr + 4 * i][k]);  // warp-uniform address: one broadcast load for 4 k
-      acc[i][0] = fmaf(a.x, b0.x, acc[i][0]); acc[i][1] = fmaf(a.x, b0.y, acc[i][1]); acc[i][2] = fmaf(a.x, b0.z, acc[i][2]); acc[i][3] = fmaf(a.x, b0.w, acc[i][3]);
-      acc[i][0] = fmaf(a.y, b1.x, acc[i][0]); acc[i][1] = fmaf(a.y, b1.y, acc[i][1]); acc[i][2] = fmaf(a.y, b1.z, acc[i][2]); acc[i][3] = fmaf(a.y, b1.w, acc[i][3]);
-      acc[i][0] = fmaf(a.z, b2.x, acc[i][0]); acc[i][1] = fmaf(a.z, b2.y, acc[i][1]); acc[i][2] = fmaf(a.z, b2.z, acc[i][2]); acc[i][3] = fmaf(a.z, b2.w, acc[i][3]);
-      acc[i][0] = fmaf(a.w, b3.x, acc[i][0]); acc[i][1] = fmaf(a.w, b3.y, acc[i][1]); acc[i][2] = fmaf(a.w, b3.z, acc[i][2]); acc[i][3] = fmaf(a.w, b3.w, acc[i][3]);
-    }
-  }
   float* __restrict__ C = p.C + (int64_t)g * p.c_gs;
   const float* __restrict__ mask = p.mask ? p.mask + (int64_t)g * p.mask_gs : nullptr;
   float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + (int64_t)g * p.bias_gs + n0 + n));
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int m = m0 + tr + 4 * i;
-    if (m >= M) continue;
-    float4 v = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
-    if (p.act >= 0) { v.x = act_apply(v.x, p.act); v.y = act_apply(v.y, p.act); v.z = act_apply(v.z, p.act); v.w = act_apply(v.w, p.act); }
-    if (mask) {
-      const float4 mv = __ldg(reinterpret_cast<const float4*>(mask + (int64_t)m * p.ldmask + n0 + n));
-      v.x *= act_grad_from_output(mv.x, p.mask_act); v.y *= act_grad_from_output(mv.y, p.mask_act);
-      v.z *= act_grad_from_output(mv.z, p.mask_act); v.w *= act_grad_from_output(mv.w, p.mask_act);
+  if (p.bias && n < ncols) bv = __ldg(reinterpret_cast<const float4*>(p.bias + (int64_t)g * p.bias_gs + n0 + n));
+  for (int it = 0; it < TK_ITERS; ++it) {
+    const int m0 = (blockIdx.y * TK_ITERS + it) * TK_ROWS;
+    if (m0 >= M) break;
+    __syncthreads();  // previous iteration's readers of As are done (and Bs is complete on the first pass)
+    for (int idx = tid; idx < TK_ROWS * K4; idx += 256) {
+      const int r = idx / K4, k = idx % K4;
+      As[r][k] = (m0 + r < M && k < K) ? __ldg(A + (int64_t)(m0 + r) * p.lda + k) : 0.f;
     }
-    *reinterpret_cast<float4*>(C + (int64_t)m * p.ldc + n0 + n) = v;
+    __syncthreads();
+    if (n >= ncols) continue;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    for (int k = 0; k < K4; k += 4) {
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][n]), b1 = *reinterpret_cast<const float4*>(&Bs[k + 1][n]);
+      const float4 b2 = *reinterpret_cast<const float4*>(&Bs[k + 2][n]), b3 = *reinterpret_cast<const float4*>(&Bs[k + 3][n]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[tr + 4 * i][k]);  // warp-uniform address: one broadcast load for 4 k
+        acc[i][0] = fmaf(a.x, b0.x, acc[i][0]); acc[i][1] = fmaf(a.x, b0.y, acc[i][1]); acc[i][2] = fmaf(a.x, b0.z, acc[i][2]); acc[i][3] = fmaf(a.x, b0.w, acc[i][3]);
+        acc[i][0] = fmaf(a.y, b1.x, acc[i][0]); acc[i][1] = fmaf(a.y, b1.y, acc[i][1]); acc[i][2] = fmaf(a.y, b1.z, acc[i][2]); acc[i][3] = fmaf(a.y, b1.w, acc[i][3]);
+        acc[i][0] = fmaf(a.z, b2.x, acc[i][0]); acc[i][1] = fmaf(a.z, b2.y, acc[i][1]); acc[i][2] = fmaf(a.z, b2.z, acc[i][2]); acc[i][3] = fmaf(a.z, b2.w, acc[i][3]);
+        acc[i][0] = fmaf(a.w, b3.x, acc[i][0]); acc[i][1] = fmaf(a.w, b3.y, acc[i][1]); acc[i][2] = fmaf(a.w, b3.z, acc[i][2]); acc[i][3] = fmaf(a.w, b3.w, acc[i][3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + tr + 4 * i;
+      if (m >= M) continue;
+      float4 v = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
+      if (p.act >= 0) { v.x = act_apply(v.x, p.act); v.y = act_apply(v.y, p.act); v.z = act_apply(v.z, p.act); v.w = act_apply(v.w, p.act); }
+      if (mask) {
+        const float4 mv = __ldg(reinterpret_cast<const float4*>(mask + (int64_t)m * p.ldmask + n0 + n));
+        v.x *= act_grad_from_output(mv.x, p.mask_act); v.y *= act_grad_from_output(mv.y, p.mask_act);
+        v.z *= act_grad_from_output(mv.z, p.mask_act); v.w *= act_grad_from_output(mv.w, p.mask_act);
+      }
+      *reinterpret_cast<float4*>(C + (int64_t)m * p.ldc + n0 + n) = v;
+    }
   }
 }
 
@@ -345,7 +346,7 @@ int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   IL_CHECK(!(a.colsum && a.a_kmajor), "gemm: colsum needs the [K, M] operand layout");
   IL_CHECK(!(a.accumulate && a.act >= 0), "gemm: accumulate with activation is not supported");
   if (a.M > 16 && thin_k_eligible(a)) {
-    dim3 grid((a.N + TK_COLS - 1) / TK_COLS, (a.M + TK_ROWS - 1) / TK_ROWS, a.G);
+    dim3 grid((a.N + TK_COLS - 1) / TK_COLS, (a.M + TK_ROWS * TK_ITERS - 1) / (TK_ROWS * TK_ITERS), a.G);
     if (a.b_kmajor) IL_LAUNCH(h, gemm_thin_k_kernel<true>, grid, 256, 0, stream, a);
     else IL_LAUNCH(h, gemm_thin_k_kernel<false>, grid, 256, 0, stream, a);
     return 0;
