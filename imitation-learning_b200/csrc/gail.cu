@@ -16,7 +16,7 @@ struct GailDims {
 };
 
 struct GailSmem {
-  float *W1, *W1e, *G1, *b1, *w2, *w2e, *G2, *gb1, *G2k, *gb1k, *u1, *v1, *v2, *tvec, *slots, *X, *Z, *GX, *DF, *CO, *red, *scal;
+  float *W1, *W1e, *G1, *b1, *w2, *w2e, *G2, *gb1, *G2k, *gb1k, *u1, *v1, *v2, *tvec, *slots, *X, *Z, *GX, *DF, *CO, *red, *scal, *part;
 };
 
 __host__ __device__ inline int gail_slot_floats(int H, int d) { return 2 * H + d + 4; }  // u1[H] v1[d] v2[H] + sigma1 sigma2 u2 pad
@@ -30,7 +30,7 @@ __host__ __device__ inline int64_t gail_carve(const GailDims& g, float* base, Ga
   t.u1 = take(g.H); t.v1 = take(g.d); t.v2 = take(g.H); t.tvec = take(g.H > g.d ? g.H : g.d);
   t.slots = take(3 * gail_slot_floats(g.H, g.d));
   t.X = take(g.RB * g.ldx); t.Z = take(g.RB * g.ldz); t.GX = take(g.RB * g.ldx); t.DF = take(g.RB); t.CO = take(g.RB);
-  t.red = take(32); t.scal = take(32);
+  t.red = take(32); t.scal = take(32); t.part = take(2 * THREADS);  // per-thread partial sums of the row-split reductions
   if (s) *s = t;
   return o * 4;
 }
@@ -285,18 +285,30 @@ __global__ void __launch_bounds__(THREADS) gail_update_kernel(const GailUpdParam
         }
         __syncthreads();
         // dL/dw2e[h] += sum_b df_b hidden[b,h];  dz[b,h] = df_b w2e[h] 1[hidden>0] (in place);  dL/db1[h] += sum_b dz[b,h]
-        for (int h = tid; h < H; h += THREADS) {
+        // all 256 threads: hidden unit h = tid % H, row slice = tid / H of the chunk; partials combined in a fixed order
+        {
+          const int parts = H <= THREADS ? THREADS / H : 1, hh = tid % H, part = tid / H;
           float acc2 = 0.f, accb = 0.f;
-          const float w2h = s.w2e[h];
-          for (int b = 0; b < nb; ++b) {
-            const float hv = s.Z[b * g.ldz + h], df = s.DF[b];
-            acc2 = fmaf(df, hv, acc2);
-            const float dz = hv > 0.f ? df * w2h : 0.f;
-            s.Z[b * g.ldz + h] = dz;
-            accb += dz;
+          if (part < parts) {
+            const float w2h = s.w2e[hh];
+            const int per = (nb + parts - 1) / parts, b_lo = part * per, b_hi = min(nb, b_lo + per);
+            for (int b = b_lo; b < b_hi; ++b) {
+              const float hv = s.Z[b * g.ldz + hh], df = s.DF[b];
+              acc2 = fmaf(df, hv, acc2);
+              const float dz = hv > 0.f ? df * w2h : 0.f;
+              s.Z[b * g.ldz + hh] = dz;
+              accb += dz;
+            }
           }
-          s.G2k[h] += acc2;
-          s.gb1k[h] += accb;
+          s.part[tid] = acc2;
+          s.part[THREADS + tid] = accb;
+          __syncthreads();
+          for (int h = tid; h < H; h += THREADS) {
+            float a2 = 0.f, ab = 0.f;
+            for (int q = 0; q < parts; ++q) { a2 += s.part[q * H + h]; ab += s.part[THREADS + q * H + h]; }
+            s.G2k[h] += a2;
+            s.gb1k[h] += ab;
+          }
         }
         __syncthreads();
         // dL/dW1e[h, j] += sum_b dz[b,h] x[b,j]
@@ -330,17 +342,27 @@ __global__ void __launch_bounds__(THREADS) gail_update_kernel(const GailUpdParam
         }
         __syncthreads();
         // dL/dw2e[h] += sum_b coef_b m[b,h] (W1e g_b)[h]
-        for (int h = tid; h < H; h += THREADS) {
+        {
+          const int parts = H <= THREADS ? THREADS / H : 1, hh = tid % H, part = tid / H;
           float acc2 = 0.f;
-          const float* wr = s.W1e + h * d;
-          for (int b = 0; b < nb; ++b) {
-            if (s.Z[b * g.ldz + h] > 0.f) {
-              float t = 0.f;
-              for (int j = 0; j < d; ++j) t = fmaf(wr[j], s.GX[b * g.ldx + j], t);
-              acc2 = fmaf(s.DF[b], t, acc2);
+          if (part < parts) {
+            const float* wr = s.W1e + hh * d;
+            const int per = (nb + parts - 1) / parts, b_lo = part * per, b_hi = min(nb, b_lo + per);
+            for (int b = b_lo; b < b_hi; ++b) {
+              if (s.Z[b * g.ldz + hh] > 0.f) {
+                float t = 0.f;
+                for (int j = 0; j < d; ++j) t = fmaf(wr[j], s.GX[b * g.ldx + j], t);
+                acc2 = fmaf(s.DF[b], t, acc2);
+              }
             }
           }
-          s.G2k[h] += acc2;
+          s.part[tid] = acc2;
+          __syncthreads();
+          for (int h = tid; h < H; h += THREADS) {
+            float a2 = 0.f;
+            for (int q = 0; q < parts; ++q) a2 += s.part[q * H + h];
+            s.G2k[h] += a2;
+          }
         }
         // dL/dW1e[h, j] += sum_b coef_b (m[b,h] w2e[h]) g_b[j]
 #pragma unroll
@@ -477,6 +499,7 @@ int gail_setup(const il_gail* disc, const il_batch* batch, GailDims* g, int64_t*
   IL_CHECK(disc->g.dims[0] == d, "%s: discriminator input %d != %d", what, disc->g.dims[0], d);
   const int H = disc->g.dims[1];
   IL_CHECK(H * d <= 64 * THREADS, "%s: hidden*input = %d exceeds the kernel limit %d", what, H * d, 64 * THREADS);
+  IL_CHECK(H <= THREADS, "%s: hidden size %d exceeds the kernel limit %d", what, H, THREADS);
   IL_CHECK((disc->u == nullptr) == (disc->v == nullptr), "%s: spectral-norm buffers must both be set or both be null", what);
   if (disc->u) IL_CHECK(disc->u_stride >= H + 1 && disc->v_stride >= d + H, "%s: spectral-norm buffer strides too small", what);
   int RB = 64;

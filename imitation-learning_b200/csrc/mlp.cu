@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256) mlp_small_forward_kernel(const SmallFwdAr
 }
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, const int64_t* __restrict__ step,
-                            double lr, double beta1_d, double beta2_d, double eps_d, double wd, int64_t n) {
+                            double lr, double beta1_d, double beta2_d, double eps_d, double wd, int64_t n, float* __restrict__ target, float tau, float one_minus_tau) {
   __shared__ float s_step_size, s_bc2_sqrt;
   if (threadIdx.x == 0) {  // torch _single_tensor_adam: Python-double scalars, then cast to the tensor dtype
     const double t = (double)*step;
@@ -260,6 +260,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);        // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
     pi = __fadd_rn(pi, __fmul_rn(-step_size, __fdiv_rn(mi, denom)));           // param.addcdiv_(exp_avg, denom, value=-step_size)
     p[i] = pi; m[i] = mi; v[i] = vi;
+    if (target) target[i] = __fadd_rn(__fmul_rn(target[i], tau), __fmul_rn(one_minus_tau, pi));  // fused update_target_network (models.py:81)
   }
 }
 
@@ -309,10 +310,10 @@ int launch_actor_head(il_handle* h, const HeadFwdArgs& a, cudaStream_t stream) {
   return 0;
 }
 
-int launch_adam(il_handle* h, float* params, const float* grads, const il_adam* opt, int64_t n, cudaStream_t stream) {
+int launch_adam(il_handle* h, float* params, const float* grads, const il_adam* opt, int64_t n, cudaStream_t stream, float* polyak_target, float polyak_factor) {
   IL_CHECK(opt->m && opt->v && opt->step, "adam: null state");
   IL_LAUNCH(h, adam_kernel, ew_blocks(n, 256, h->sm_count), 256, 0, stream, params, grads, opt->m, opt->v, opt->step, opt->lr, opt->beta1, opt->beta2, opt->eps,
-            opt->weight_decay, n);
+            opt->weight_decay, n, polyak_target, polyak_factor, (float)(1.0 - (double)polyak_factor));
   return 0;
 }
 

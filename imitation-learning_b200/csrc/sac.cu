@@ -251,7 +251,9 @@ extern "C" int il_sac_update(il_handle* h, const il_sac_args* a, void* stream) {
   IL_LAUNCH(h, sac_critic_lossgrad_kernel, R, 256, 0, st, w.q, w.y, rows, rs, row, L.weight, w.dq, a->out_q_values, a->out_losses, B);
   IL_TRY(mlp_backward(h, &a->critic, 2 * R, B, MatView{rows + L.state, rs, 2, row}, w.critic_acts, MatView{w.dq, (int64_t)B, 1, 1}, w.g_critic, a->critic.stride, nullptr, 0,
                       0, 0, 0, w.tmpA, w.tmpB, st));
-  IL_TRY(launch_adam(h, a->critic.params, w.g_critic, &a->critic_opt, (int64_t)2 * R * a->critic.stride, st));
+  // polyak (training.py:52) is fused into the critic AdamW pass: the critic parameters do not change again inside this
+  // update and the target is not read again, so the result equals the reference's end-of-update target step
+  IL_TRY(launch_adam(h, a->critic.params, w.g_critic, &a->critic_opt, (int64_t)2 * R * a->critic.stride, st, a->target.params, a->polyak_factor));
   // (4) actor loss through the UPDATED critic  [training.py:34-42]
   IL_TRY(mlp_forward(h, &a->actor, R, B, MatView{rows + L.state, rs, 1, row}, w.actor_acts, w.head, (int64_t)B * 2 * A, 2 * A, st));
   {
@@ -275,8 +277,7 @@ extern "C" int il_sac_update(il_handle* h, const il_sac_args* a, void* stream) {
   // (5) temperature  [training.py:45-49]
   IL_LAUNCH(h, sac_alpha_kernel, R, 256, 0, st, a->log_alpha, lp_new, rows, rs, row, L.weight, av, a->entropy_target, a->alpha_opt.m, a->alpha_opt.v, a->alpha_opt.step,
             a->alpha_opt.lr, a->alpha_opt.beta1, a->alpha_opt.beta2, a->alpha_opt.eps, a->alpha_opt.weight_decay, a->out_losses, B);
-  // (6) polyak  [training.py:52]
-  return il_polyak(h, a->target.params, a->critic.params, (int64_t)2 * R * a->critic.stride, a->polyak_factor, stream);
+  return 0;  // (6) polyak [training.py:52]: done inside the critic AdamW kernel above
 }
 
 // ---- behavioural_cloning_update (training.py:57-64) --------------------------------------------------------------------
