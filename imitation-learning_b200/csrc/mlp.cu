@@ -250,17 +250,33 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
   const float decay = (float)(1.0 - lr * wd), w1 = (float)(1.0 - beta1_d), w2 = (float)(1.0 - beta2_d);
   const float beta2 = (float)beta2_d, eps = (float)eps_d;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float pi = p[i];
-    const float gi = g[i];
-    float mi = m[i], vi = v[i];
-    if (wd != 0.0) pi = __fmul_rn(pi, decay);                                  // param.mul_(1 - lr * weight_decay)
+  const bool has_wd = wd != 0.0;
+  auto upd = [&](float& pi, float& mi, float& vi, float gi) {
+    if (has_wd) pi = __fmul_rn(pi, decay);                                     // param.mul_(1 - lr * weight_decay)
     mi = __fadd_rn(mi, __fmul_rn(w1, __fsub_rn(gi, mi)));                      // exp_avg.lerp_(grad, 1 - beta1)
     vi = __fadd_rn(__fmul_rn(vi, beta2), __fmul_rn(__fmul_rn(w2, gi), gi));    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
     const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);        // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
     pi = __fadd_rn(pi, __fmul_rn(-step_size, __fdiv_rn(mi, denom)));           // param.addcdiv_(exp_avg, denom, value=-step_size)
+  };
+  // n is a multiple of 4 and all buffers are 16-byte aligned (flat parameter layout): 128-bit streams
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i], mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    upd(pv.x, mv.x, vv.x, gv.x); upd(pv.y, mv.y, vv.y, gv.y); upd(pv.z, mv.z, vv.z, gv.z); upd(pv.w, mv.w, vv.w, gv.w);
+    reinterpret_cast<float4*>(p)[i] = pv; reinterpret_cast<float4*>(m)[i] = mv; reinterpret_cast<float4*>(v)[i] = vv;
+    if (target) {  // fused update_target_network (models.py:81)
+      float4 tv = reinterpret_cast<float4*>(target)[i];
+      tv.x = __fadd_rn(__fmul_rn(tv.x, tau), __fmul_rn(one_minus_tau, pv.x)); tv.y = __fadd_rn(__fmul_rn(tv.y, tau), __fmul_rn(one_minus_tau, pv.y));
+      tv.z = __fadd_rn(__fmul_rn(tv.z, tau), __fmul_rn(one_minus_tau, pv.z)); tv.w = __fadd_rn(__fmul_rn(tv.w, tau), __fmul_rn(one_minus_tau, pv.w));
+      reinterpret_cast<float4*>(target)[i] = tv;
+    }
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {  // tail (< 4 elements)
+    float pi = p[i], mi = m[i], vi = v[i];
+    upd(pi, mi, vi, g[i]);
     p[i] = pi; m[i] = mi; v[i] = vi;
-    if (target) target[i] = __fadd_rn(__fmul_rn(target[i], tau), __fmul_rn(one_minus_tau, pi));  // fused update_target_network (models.py:81)
+    if (target) target[i] = __fadd_rn(__fmul_rn(target[i], tau), __fmul_rn(one_minus_tau, pi));
   }
 }
 
@@ -312,7 +328,9 @@ int launch_actor_head(il_handle* h, const HeadFwdArgs& a, cudaStream_t stream) {
 
 int launch_adam(il_handle* h, float* params, const float* grads, const il_adam* opt, int64_t n, cudaStream_t stream, float* polyak_target, float polyak_factor) {
   IL_CHECK(opt->m && opt->v && opt->step, "adam: null state");
-  IL_LAUNCH(h, adam_kernel, ew_blocks(n, 256, h->sm_count), 256, 0, stream, params, grads, opt->m, opt->v, opt->step, opt->lr, opt->beta1, opt->beta2, opt->eps,
+  IL_CHECK(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(opt->m) | reinterpret_cast<uintptr_t>(opt->v) |
+             reinterpret_cast<uintptr_t>(polyak_target)) & 15) == 0, "adam: buffers must be 16-byte aligned");
+  IL_LAUNCH(h, adam_kernel, ew_blocks(n / 4 + 1, 256, h->sm_count), 256, 0, stream, params, grads, opt->m, opt->v, opt->step, opt->lr, opt->beta1, opt->beta2, opt->eps,
             opt->weight_decay, n, polyak_target, polyak_factor, (float)(1.0 - (double)polyak_factor));
   return 0;
 }
