@@ -4,6 +4,7 @@
 thread_local char g_il_error[512] = "";
 int gail_init();
 int gmmil_pwil_init();
+int gemm_init();
 
 extern "C" const char* il_last_error(void) { return g_il_error; }
 extern "C" int il_version(void) { return 100; }
@@ -21,6 +22,7 @@ extern "C" int il_create(int device, il_handle** out) {
   IL_TRY(gail_init());
   IL_TRY(gmmil_pwil_init());
   IL_TRY(tc_gemm_init());
+  IL_TRY(gemm_init());
   il_handle* h = new il_handle();
   h->device = device;
   h->sm_count = prop.multiProcessorCount;

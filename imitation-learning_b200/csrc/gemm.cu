@@ -318,6 +318,119 @@ bool thin_k_eligible(const GemmArgs& a) {
   return true;
 }
 
+// Streaming kernels for head-shaped products whose cost is one pass over a [K, wide] or [M, wide] activation matrix
+// (wide = hidden width) while the other operand and the output are tiny (<= 16 columns). HBM-bound by construction.
+constexpr int ST_MAXS = 16;
+// TN: C[m][n] = sum_k A[k][m] * B[k][n] (A stored [K, M], B stored [K, N]) with min(M, N) <= 16. WIDE_A: M is the wide side
+// (first-layer weight gradient: A = dZ [B, H], B = X [B, S]); else N is wide (last-layer weight gradient: A = dOut [B, NH],
+// B = H2 [B, H]). One CTA per (group, 256 wide columns); each thread owns one wide column and streams it over K.
+template <bool WIDE_A>
+__global__ void __launch_bounds__(256) gemm_stream_tn_kernel(const GemmArgs p) {
+  extern __shared__ __align__(16) float U[];  // [K][ST_MAXS] small operand, zero padded
+  const int g = blockIdx.y, w0 = blockIdx.x * 256, tid = threadIdx.x;
+  const int K = p.K, S = WIDE_A ? p.N : p.M, W = WIDE_A ? p.M : p.N;
+  const float* __restrict__ A = p.A + (int64_t)(g / p.a_gdiv) * p.a_gs;
+  const float* __restrict__ B = p.B + (int64_t)(g / p.b_gdiv) * p.b_gs;
+  const float* __restrict__ T = WIDE_A ? A : B;
+  const float* __restrict__ Us = WIDE_A ? B : A;
+  const int ldt = WIDE_A ? p.lda : p.ldb, ldu = WIDE_A ? p.ldb : p.lda;
+  for (int idx = tid; idx < K * ST_MAXS; idx += 256) {
+    const int k = idx / ST_MAXS, j = idx % ST_MAXS;
+    U[idx] = j < S ? __ldg(Us + (int64_t)k * ldu + j) : 0.f;
+  }
+  __syncthreads();
+  const int w = w0 + tid;
+  float acc[ST_MAXS], tsum = 0.f;
+#pragma unroll
+  for (int j = 0; j < ST_MAXS; ++j) acc[j] = 0.f;
+  if (w < W) {
+    const float* tp = T + w;
+    int k = 0;
+    for (; k + 8 <= K; k += 8) {
+      float t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = __ldg(tp + (int64_t)(k + u) * ldt);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        tsum += t[u];
+        const float4* ur = reinterpret_cast<const float4*>(U + (k + u) * ST_MAXS);
+#pragma unroll
+        for (int q = 0; q < ST_MAXS / 4; ++q) {
+          if (q * 4 < S) {
+            const float4 uv = ur[q];
+            acc[q * 4 + 0] = fmaf(t[u], uv.x, acc[q * 4 + 0]); acc[q * 4 + 1] = fmaf(t[u], uv.y, acc[q * 4 + 1]);
+            acc[q * 4 + 2] = fmaf(t[u], uv.z, acc[q * 4 + 2]); acc[q * 4 + 3] = fmaf(t[u], uv.w, acc[q * 4 + 3]);
+          }
+        }
+      }
+    }
+    for (; k < K; ++k) {
+      const float t = __ldg(tp + (int64_t)k * ldt);
+      tsum += t;
+#pragma unroll
+      for (int j = 0; j < ST_MAXS; ++j) acc[j] = fmaf(t, U[k * ST_MAXS + j], acc[j]);
+    }
+    float* __restrict__ C = p.C + (int64_t)g * p.c_gs;
+    if (WIDE_A) {  // C[m = w][n = j]
+#pragma unroll
+      for (int j = 0; j < ST_MAXS; ++j)
+        if (j < S) C[(int64_t)w * p.ldc + j] = acc[j];
+      if (p.colsum) p.colsum[(int64_t)g * p.colsum_gs + w] = tsum;  // sum_k A[k][m]
+    } else {       // C[m = j][n = w]
+#pragma unroll
+      for (int j = 0; j < ST_MAXS; ++j)
+        if (j < S) C[(int64_t)j * p.ldc + w] = acc[j];
+    }
+  }
+  if (!WIDE_A && p.colsum && blockIdx.x == 0 && tid < S) {  // sum_k A[k][m] of the small operand
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s += U[k * ST_MAXS + tid];
+    p.colsum[(int64_t)g * p.colsum_gs + tid] = s;
+  }
+}
+
+// NN thin output: C[m][n] = sum_k A[m][k] * B[k][n] with N <= 16 (input gradient w.r.t. a few columns: A = dZ [B, H] rows
+// streamed once, B = W[:, cols] staged in shared memory). One warp per row.
+__global__ void __launch_bounds__(256) gemm_stream_nn_kernel(const GemmArgs p) {
+  extern __shared__ __align__(16) float Bs[];  // [K][ST_MAXS]
+  const int g = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = p.K, N = p.N, M = p.M;
+  const float* __restrict__ A = p.A + (int64_t)(g / p.a_gdiv) * p.a_gs;
+  const float* __restrict__ B = p.B + (int64_t)(g / p.b_gdiv) * p.b_gs;
+  for (int idx = tid; idx < K * ST_MAXS; idx += 256) {
+    const int k = idx / ST_MAXS, j = idx % ST_MAXS;
+    Bs[idx] = j < N ? __ldg(B + (int64_t)k * p.ldb + j) : 0.f;
+  }
+  __syncthreads();
+  float* __restrict__ C = p.C + (int64_t)g * p.c_gs;
+  for (int m = blockIdx.x * 8 + warp; m < M; m += gridDim.x * 8) {
+    float acc[ST_MAXS];
+#pragma unroll
+    for (int j = 0; j < ST_MAXS; ++j) acc[j] = 0.f;
+    const float* ar = A + (int64_t)m * p.lda;
+    for (int k = lane; k < K; k += 32) {
+      const float a = __ldg(ar + k);
+      const float4* br = reinterpret_cast<const float4*>(Bs + k * ST_MAXS);
+#pragma unroll
+      for (int q = 0; q < ST_MAXS / 4; ++q) {
+        if (q * 4 < N) {
+          const float4 bv = br[q];
+          acc[q * 4 + 0] = fmaf(a, bv.x, acc[q * 4 + 0]); acc[q * 4 + 1] = fmaf(a, bv.y, acc[q * 4 + 1]);
+          acc[q * 4 + 2] = fmaf(a, bv.z, acc[q * 4 + 2]); acc[q * 4 + 3] = fmaf(a, bv.w, acc[q * 4 + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < ST_MAXS; ++j)
+      if (j < N) acc[j] = warp_sum(acc[j]);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < ST_MAXS; ++j)
+        if (j < N) C[(int64_t)m * p.ldc + j] = acc[j];
+    }
+  }
+}
+
 template <int BM, int BN, int TM, int TN>
 int launch_cfg(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   constexpr int BK = 16;
@@ -340,11 +453,33 @@ static bool gemm_uses_tc(const il_handle* h, const GemmArgs& a) {
   return a.M >= 128 && a.N >= 128 && a.K >= 128 && h->gemm_mode != IL_GEMM_FP32 && tc_gemm_eligible(a);
 }
 
+int gemm_init() {
+  IL_CUDA(cudaFuncSetAttribute(gemm_stream_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  IL_CUDA(cudaFuncSetAttribute(gemm_stream_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  IL_CUDA(cudaFuncSetAttribute(gemm_stream_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  return 0;
+}
+
 int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   IL_CHECK(a.M > 0 && a.N > 0 && a.K > 0 && a.G > 0, "gemm: empty problem M=%d N=%d K=%d G=%d", a.M, a.N, a.K, a.G);
   IL_CHECK(a.G <= 65535, "gemm: too many groups (%d)", a.G);
   IL_CHECK(!(a.colsum && a.a_kmajor), "gemm: colsum needs the [K, M] operand layout");
   IL_CHECK(!(a.accumulate && a.act >= 0), "gemm: accumulate with activation is not supported");
+  const bool plain = !a.bias && a.act < 0 && !a.mask && !a.accumulate;
+  if (plain && !a.a_kmajor && !a.b_kmajor && a.K >= 64 && a.K * ST_MAXS * 4 <= 64 * 1024 && ((a.M <= ST_MAXS && a.N >= 64) || (a.N <= ST_MAXS && a.M >= 64))) {
+    const bool wide_a = a.N <= ST_MAXS && a.M >= 64;
+    const int W = wide_a ? a.M : a.N;
+    dim3 grid((W + 255) / 256, a.G);
+    const size_t smem = (size_t)a.K * ST_MAXS * 4;
+    if (wide_a) IL_LAUNCH(h, gemm_stream_tn_kernel<true>, grid, 256, smem, stream, a);
+    else IL_LAUNCH(h, gemm_stream_tn_kernel<false>, grid, 256, smem, stream, a);
+    return 0;
+  }
+  if (plain && a.a_kmajor && !a.b_kmajor && !a.colsum && a.N <= ST_MAXS && a.M >= 64 && a.K >= 64 && a.K * ST_MAXS * 4 <= 64 * 1024) {
+    dim3 grid((a.M + 63) / 64, a.G);
+    IL_LAUNCH(h, gemm_stream_nn_kernel, grid, 256, (size_t)a.K * ST_MAXS * 4, stream, a);
+    return 0;
+  }
   if (a.M > 16 && thin_k_eligible(a)) {
     dim3 grid((a.N + TK_COLS - 1) / TK_COLS, (a.M + TK_ROWS * TK_ITERS - 1) / (TK_ROWS * TK_ITERS), a.G);
     if (a.b_kmajor) IL_LAUNCH(h, gemm_thin_k_kernel<true>, grid, 256, 0, stream, a);
