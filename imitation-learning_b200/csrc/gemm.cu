@@ -389,48 +389,6 @@ __global__ void __launch_bounds__(256) gemm_stream_tn_kernel(const GemmArgs p) {
   }
 }
 
-// NN thin output: C[m][n] = sum_k A[m][k] * B[k][n] with N <= 16 (input gradient w.r.t. a few columns: A = dZ [B, H] rows
-// streamed once, B = W[:, cols] staged in shared memory). One warp per row.
-__global__ void __launch_bounds__(256) gemm_stream_nn_kernel(const GemmArgs p) {
-  extern __shared__ __align__(16) float Bs[];  // [K][ST_MAXS]
-  const int g = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int K = p.K, N = p.N, M = p.M;
-  const float* __restrict__ A = p.A + (int64_t)(g / p.a_gdiv) * p.a_gs;
-  const float* __restrict__ B = p.B + (int64_t)(g / p.b_gdiv) * p.b_gs;
-  for (int idx = tid; idx < K * ST_MAXS; idx += 256) {
-    const int k = idx / ST_MAXS, j = idx % ST_MAXS;
-    Bs[idx] = j < N ? __ldg(B + (int64_t)k * p.ldb + j) : 0.f;
-  }
-  __syncthreads();
-  float* __restrict__ C = p.C + (int64_t)g * p.c_gs;
-  for (int m = blockIdx.x * 8 + warp; m < M; m += gridDim.x * 8) {
-    float acc[ST_MAXS];
-#pragma unroll
-    for (int j = 0; j < ST_MAXS; ++j) acc[j] = 0.f;
-    const float* ar = A + (int64_t)m * p.lda;
-    for (int k = lane; k < K; k += 32) {
-      const float a = __ldg(ar + k);
-      const float4* br = reinterpret_cast<const float4*>(Bs + k * ST_MAXS);
-#pragma unroll
-      for (int q = 0; q < ST_MAXS / 4; ++q) {
-        if (q * 4 < N) {
-          const float4 bv = br[q];
-          acc[q * 4 + 0] = fmaf(a, bv.x, acc[q * 4 + 0]); acc[q * 4 + 1] = fmaf(a, bv.y, acc[q * 4 + 1]);
-          acc[q * 4 + 2] = fmaf(a, bv.z, acc[q * 4 + 2]); acc[q * 4 + 3] = fmaf(a, bv.w, acc[q * 4 + 3]);
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < ST_MAXS; ++j)
-      if (j < N) acc[j] = warp_sum(acc[j]);
-    if (lane == 0) {
-#pragma unroll
-      for (int j = 0; j < ST_MAXS; ++j)
-        if (j < N) C[(int64_t)m * p.ldc + j] = acc[j];
-    }
-  }
-}
-
 template <int BM, int BN, int TM, int TN>
 int launch_cfg(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   constexpr int BK = 16;
@@ -456,7 +414,6 @@ static bool gemm_uses_tc(const il_handle* h, const GemmArgs& a) {
 int gemm_init() {
   IL_CUDA(cudaFuncSetAttribute(gemm_stream_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   IL_CUDA(cudaFuncSetAttribute(gemm_stream_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  IL_CUDA(cudaFuncSetAttribute(gemm_stream_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   return 0;
 }
 
@@ -473,11 +430,6 @@ int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
     const size_t smem = (size_t)a.K * ST_MAXS * 4;
     if (wide_a) IL_LAUNCH(h, gemm_stream_tn_kernel<true>, grid, 256, smem, stream, a);
     else IL_LAUNCH(h, gemm_stream_tn_kernel<false>, grid, 256, smem, stream, a);
-    return 0;
-  }
-  if (plain && a.a_kmajor && !a.b_kmajor && !a.colsum && a.N <= ST_MAXS && a.M >= 64 && a.K >= 64 && a.K * ST_MAXS * 4 <= 64 * 1024) {
-    dim3 grid((a.M + 63) / 64, a.G);
-    IL_LAUNCH(h, gemm_stream_nn_kernel, grid, 256, (size_t)a.K * ST_MAXS * 4, stream, a);
     return 0;
   }
   if (a.M > 16 && thin_k_eligible(a)) {
