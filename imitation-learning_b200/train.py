@@ -112,7 +112,7 @@ class Trainer:
     row = self.memory.row
     self.batch = TransitionBatch(f(R, B, row), S, A, absorbing)
     self.expert_batch = TransitionBatch(f(R, B, row), S, A, absorbing)
-    self.eps_gp, self.eps_next, self.eps_new = f(R, B), f(R, B, A), f(R, B, A)
+    self.eps_gp, self.eps_mix, self.eps_next, self.eps_new = f(R, B), f(R, B), f(R, B, A), f(R, B, A)
     self.sac_out = dict(log_probs=f(R, B), q_values=f(R, B), losses=f(R, 3))
     self.gail_losses = f(R, 2)
     self.rng = _RNG(seed, dev)
@@ -171,9 +171,14 @@ class Trainer:
     if self.algorithm == 'GAIL':
       from .training import adversarial_imitation_update
       if cfg.imitation.grad_penalty > 0 and not self.inject: self.rng.uniform(None, self.device, stream_id=5, out=self.eps_gp)
+      eps_mix = None
+      if cfg.imitation.loss_function == 'Mixup':  # training.py:106: Beta(a, a) draws; a == 1 (all published configs) is U(0, 1)
+        if float(cfg.imitation.mixup_alpha) != 1.0: raise NotImplementedError('mixup_alpha != 1 needs Beta draws; only mixup_alpha = 1 (the reference default) is on the graph-captured path')
+        if not self.inject: self.rng.uniform(None, self.device, stream_id=8, out=self.eps_mix)
+        eps_mix = self.eps_mix
       self.discriminator.train()  # train.py:178-180
       adversarial_imitation_update(self.actor, self.discriminator, self.batch, self.expert_batch, self.discriminator_optimiser, cfg.imitation, eps_gp=self.eps_gp,
-                                   out_losses=self.gail_losses)
+                                   eps_mix=eps_mix, out_losses=self.gail_losses)
       self.discriminator.eval()
     if self.algorithm in ('GAIL', 'GMMIL'):
       if cfg.imitation.mix_expert_data == 'mixed_batch':

@@ -75,8 +75,9 @@ def adversarial_imitation_update(actor: SoftActor, discriminator: GAILDiscrimina
   loss_function, grad_penalty = imitation_cfg.loss_function, float(imitation_cfg.grad_penalty)
   if grad_penalty > 0 and eps_gp is None: eps_gp = default_rng.uniform((R, B), device, stream_id=21)
   if loss_function == 'Mixup' and eps_mix is None:
-    alpha = float(imitation_cfg.mixup_alpha)  # training.py:106; Beta draws come from torch (setup-free, device-side)
-    eps_mix = torch.distributions.Beta(torch.full((R, B), alpha, device=device), torch.full((R, B), alpha, device=device)).sample()
+    alpha = float(imitation_cfg.mixup_alpha)  # training.py:106
+    if alpha == 1.0: eps_mix = default_rng.uniform((R, B), device, stream_id=22)  # Beta(1, 1) = U(0, 1): every published config uses mixup_alpha 1
+    else: eps_mix = torch.distributions.Beta(torch.full((R, B), alpha, device=device), torch.full((R, B), alpha, device=device)).sample()
   as_dev = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.float32).to(device).reshape(R, B).contiguous()
   eps_gp, eps_mix = as_dev(eps_gp), as_dev(eps_mix)
   a = _lib.GailUpdateArgs()
