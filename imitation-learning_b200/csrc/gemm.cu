@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256, 2) gemm_grouped_kernel(const GemmArgs p) 
 // replaced by: B (K x 256) and 32 rows of A in shared memory, 8 x 4 outputs per thread, 128-bit coalesced stores.
 constexpr int TK_MAXK = 32, TK_ROWS = 32, TK_ITERS = 4, TK_COLS = 256, TK_LDA = TK_MAXK + 4;  // a CTA covers 4 x 32 rows
 template <bool B_KMAJOR>
-__global__ void __launch_bounds__(256) gemm_thin_k_kernel(const GemmArgs p) {
+__global__ void __launch_bounds__(256, 3) gemm_thin_k_kernel(const GemmArgs p) {
   __shared__ __align__(16) float Bs[TK_MAXK][TK_COLS];
   __shared__ __align__(16) float As[TK_ROWS][TK_LDA];  // K zero-padded to a multiple of 4 so rows are read as float4
   const int tid = threadIdx.x, g = blockIdx.z, n0 = blockIdx.x * TK_COLS;
@@ -268,15 +268,28 @@ __global__ void __launch_bounds__(256) gemm_thin_k_kernel(const GemmArgs p) {
   const float* __restrict__ mask = p.mask ? p.mask + (int64_t)g * p.mask_gs : nullptr;
   float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
   if (p.bias && n < ncols) bv = __ldg(reinterpret_cast<const float4*>(p.bias + (int64_t)g * p.bias_gs + n0 + n));
+  // A rows of the next 32-row block are fetched into registers while the current block is computed
+  constexpr int A_PER = TK_ROWS * TK_MAXK / 256;  // 4 elements per thread cover the zero-padded [32][K4 <= 32] tile
+  float a_next[A_PER];
+  auto fetch_a = [&](int m0) {
+#pragma unroll
+    for (int q = 0; q < A_PER; ++q) {
+      const int idx = tid + q * 256, r = idx / K4, k = idx % K4;
+      a_next[q] = (idx < TK_ROWS * K4 && m0 + r < M && k < K) ? __ldg(A + (int64_t)(m0 + r) * p.lda + k) : 0.f;
+    }
+  };
+  fetch_a(blockIdx.y * TK_ITERS * TK_ROWS);
   for (int it = 0; it < TK_ITERS; ++it) {
     const int m0 = (blockIdx.y * TK_ITERS + it) * TK_ROWS;
     if (m0 >= M) break;
     __syncthreads();  // previous iteration's readers of As are done (and Bs is complete on the first pass)
-    for (int idx = tid; idx < TK_ROWS * K4; idx += 256) {
-      const int r = idx / K4, k = idx % K4;
-      As[r][k] = (m0 + r < M && k < K) ? __ldg(A + (int64_t)(m0 + r) * p.lda + k) : 0.f;
+#pragma unroll
+    for (int q = 0; q < A_PER; ++q) {
+      const int idx = tid + q * 256;
+      if (idx < TK_ROWS * K4) As[idx / K4][idx % K4] = a_next[q];
     }
     __syncthreads();
+    if (it + 1 < TK_ITERS && m0 + TK_ROWS < M) fetch_a(m0 + TK_ROWS);
     if (n >= ncols) continue;
     float acc[8][4];
 #pragma unroll
