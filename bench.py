@@ -23,7 +23,7 @@ METRIC, UNIT = 'env_steps_per_s', 'env-steps/s'
 def parse():
   p = argparse.ArgumentParser()
   p.add_argument('--gpus', type=int, default=1)
-  p.add_argument('--steps', type=int, default=20)
+  p.add_argument('--steps', type=int, default=100)
   p.add_argument('--warmup', type=int, default=3)
   p.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   p.add_argument('--algorithm', default='GAIL')
@@ -90,11 +90,11 @@ class Clocks:
   FIELDS = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
   def __init__(self, gpu_index):
-    self.rows, self.proc, self.gpu = [], None, gpu_index
+    self.rows, self.proc, self.gpu, self.mark_idx = [], None, gpu_index, 0
 
   def start(self):
     try:
-      self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits', '-lms', '100', '-i', str(self.gpu)], stdout=subprocess.PIPE,
+      self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits', '-lms', '25', '-i', str(self.gpu)], stdout=subprocess.PIPE,
                                    stderr=subprocess.DEVNULL, text=True)
       threading.Thread(target=self._read, daemon=True).start()
     except Exception:
@@ -103,12 +103,25 @@ class Clocks:
   def _read(self):
     for line in self.proc.stdout: self.rows.append(line.strip())
 
+  def mark(self):
+    """Call at the start of the timed region: only samples taken after this point are reported."""
+    self.mark_idx = len(self.rows)
+
   def stop(self):
     if self.proc is None: return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
-    time.sleep(0.15)
+    end_idx = len(self.rows)
+    time.sleep(0.05)
     self.proc.terminate()
+    rows, note = self.rows[self.mark_idx:max(end_idx, self.mark_idx + 1)], None
+    if not rows:  # timed region shorter than the sampling period: fall back to the samples taken under the same load just before it
+      rows, note = self.rows[-8:], 'no sample landed inside the timed region; these are the last samples of the warm-up under the same load'
+    out = self._summarise(rows)
+    if note: out['note'] = note
+    return out
+
+  def _summarise(self, rows):
     sm, mx, reasons = [], [], set()
-    for r in self.rows:
+    for r in rows:
       f = [x.strip() for x in r.split(',')]
       if len(f) < 9: continue
       try:
@@ -140,6 +153,8 @@ def run_b200(a):
                      f'replicas={R}', f'gemm_mode={a.gemm_mode}', f'memory.size={max(total_steps * 2, 4096)}', 'seed=0'])
   lo, hi = distributed.shard(R * world, rank, world)
   tr = Trainer(cfg, replicas=R, seed_offset=lo, fast_init=True)
+  clocks = Clocks(dev)
+  clocks.start()  # sampler runs from the prefill on; only samples after clocks.mark() (timed region) are reported
   for _ in range(a.start - 1): tr.train_step()  # update-free prefill (train.py:171), untimed setup
   for _ in range(W): tr.train_step()            # warm-up incl. CUDA-graph capture
   torch.cuda.synchronize()
@@ -171,8 +186,7 @@ def run_b200(a):
     if world > 1: dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return float(ms.item()), tr.total_launches() - launches0
 
-  clocks = Clocks(dev)
-  clocks.start()
+  clocks.mark()
   ms, launches = timed(K)
   clk = clocks.stop()
   value = R * world * K / (ms / 1e3)
