@@ -198,3 +198,45 @@ def test_bc_pretraining_reduces_the_cloning_loss():
   last = tr.bc_pretrain(150)
   assert bool((last < first).all()), (first, last)
   assert bool(torch.isfinite(last).all())
+
+
+def test_twin_critic_forward_and_target_update_match_oracle():
+  """models.py:123-141 and models.py:72-81 through il_critic_forward / il_polyak, 3 replicas."""
+  import il_b200
+  from oracle import port
+  R, n, S, A = 3, 40, 12, 3
+  torch.manual_seed(4)
+  critic = il_b200.TwinCritic(S, A, MODEL, replicas=R, rng=il_b200.ReplicaRNG(4, R))
+  s, a = torch.randn(R, n, S, device='cuda'), torch.tanh(torch.randn(R, n, A, device='cuda'))
+  q1, q2 = critic(s, a)
+  for r in range(R):
+    ref1, ref2 = port.twin_critic_forward([critic.mlp.export_params(r, 0), critic.mlp.export_params(r, 1)], s[r].cpu(), a[r].cpu())
+    np.testing.assert_allclose(q1[r].cpu().numpy(), ref1.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(q2[r].cpu().numpy(), ref2.numpy(), rtol=1e-4, atol=1e-5)
+  target = il_b200.create_target_network(critic)
+  assert target.mlp.flat.data_ptr() != critic.mlp.flat.data_ptr() and torch.equal(target.mlp.flat, critic.mlp.flat)
+  critic.mlp.flat.add_(0.5)
+  before = target.mlp.flat.clone()
+  il_b200.update_target_network(critic, target, 0.99)
+  np.testing.assert_allclose(target.mlp.flat.cpu().numpy(), (before * 0.99 + (1 - 0.99) * critic.mlp.flat).cpu().numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_separate_wrap_call_equals_fused_wrap_and_transfer():
+  """memory.py:65-68 as its own call (the reference's call pattern, train.py:157,162) == the fused append+wrap the
+  trainer uses; transfer_transitions (memory.py:46-48) copies every row with weight 1."""
+  import il_b200
+  rs = np.random.RandomState(0)
+  S, A, n = 12, 3, 20
+  a, b = il_b200.ReplayMemory(50, S, A, True), il_b200.ReplayMemory(50, S, A, True)
+  f = lambda *s: torch.from_numpy(rs.standard_normal(s).astype(np.float32)).cuda()
+  for i in range(n):
+    st, ac, ns, rw, term = f(1, S), f(1, A), f(1, S), float(rs.standard_normal()), bool(i % 6 == 5)
+    a.append(i + 1, st, ac, rw, ns, term, False)
+    if term: a.wrap_for_absorbing_states()
+    b.append(float(i + 1), st, ac, rw, ns, float(term), 0.0, wrap=True)
+  assert torch.equal(a.rows, b.rows) and a.idx == b.idx == n + 3 and a.num_trajectories == b.num_trajectories == 3
+  c = il_b200.ReplayMemory(50, S, A, True)
+  src = il_b200.ReplayMemory(a.idx, S, A, True, transitions=dict(states=a.states[:a.idx], actions=a.actions[:a.idx], rewards=a.rewards[:a.idx], next_states=a.next_states[:a.idx],
+                                                                terminals=a.terminals[:a.idx], timeouts=a.timeouts[:a.idx], weights=a.weights[:a.idx] * 0.5, num_trajectories=3))
+  c.transfer_transitions(src)
+  assert c.idx == a.idx and torch.equal(c.states[:a.idx], a.states[:a.idx]) and bool((c.weights[:a.idx] == 1).all())
