@@ -204,11 +204,20 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
     const uint32_t stage0 = smem_u32(stage_base);
     const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_kb = my_tiles * nkb;
+    // running position of the next k-block to copy (no divisions in the steady state)
+    int iss_tile = blockIdx.x, iss_kb = 0;
+    const float *iss_a = nullptr, *iss_b = nullptr;
     auto issue = [&](int idx) {  // async copies of this CTA's idx-th k-block into stage idx % STAGES
-      const int tile = blockIdx.x + (idx / nkb) * gridDim.x, kb = idx % nkb;
-      const int grp = tile / p.tiles_m, m0 = (tile % p.tiles_m) * BM;
-      const float* A = g.A + (int64_t)(grp / g.a_gdiv) * g.a_gs + (a_km ? (int64_t)m0 * g.lda : (int64_t)m0) + kb * a_kstep;
-      const float* B = g.B + (int64_t)(grp / g.b_gdiv) * g.b_gs + kb * b_kstep;
+      if (iss_kb == 0) {
+        const int grp = iss_tile / p.tiles_m, m0 = (iss_tile % p.tiles_m) * BM;
+        iss_a = g.A + (int64_t)(grp / g.a_gdiv) * g.a_gs + (a_km ? (int64_t)m0 * g.lda : (int64_t)m0);
+        iss_b = g.B + (int64_t)(grp / g.b_gdiv) * g.b_gs;
+      }
+      const float* A = iss_a;
+      const float* B = iss_b;
+      iss_a += a_kstep;
+      iss_b += b_kstep;
+      if (++iss_kb == nkb) { iss_kb = 0; iss_tile += gridDim.x; }
       const int s = idx % STAGES;
       if (lane == 0) mbar_wait(empty_bar(s), ((idx / STAGES) & 1) ^ 1);
       __syncwarp();
@@ -219,12 +228,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
       for (int j = 0; j < TileMap<BN>::PER_THREAD; ++j) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + 2 * A_BYTES + mb.soff[j]), "l"(B + mb.goff[j]) : "memory");
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto lo_chunk = [&](uint32_t hi_addr, uint32_t lo_addr) {
-      uint32_t x, y, z, w;
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(hi_addr));
-      sts128(lo_addr, __float_as_uint(__uint_as_float(x) - __uint_as_float(x & 0xFFFFE000u)), __float_as_uint(__uint_as_float(y) - __uint_as_float(y & 0xFFFFE000u)),
-             __float_as_uint(__uint_as_float(z) - __uint_as_float(z & 0xFFFFE000u)), __float_as_uint(__uint_as_float(w) - __uint_as_float(w & 0xFFFFE000u)));
+    auto lds128 = [&](uint32_t addr, uint32_t (&v)[4]) {
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
     };
+    auto lo_of = [](uint32_t x) { return __float_as_uint(__uint_as_float(x) - __uint_as_float(x & 0xFFFFE000u)); };
     // STAGES - 1 k-blocks of copies are kept in flight; one commit group per loop iteration (empty at the tail) keeps
     // the wait_group bookkeeping uniform
     for (int i = 0; i < STAGES - 1; ++i) {
@@ -236,11 +243,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
       else asm volatile("cp.async.wait_group 0;" ::: "memory");
       const int s = idx % STAGES;
       const uint32_t st = stage0 + s * STAGE_BYTES;
-      if (split) {
+      if (split) {  // all loads first (independent, in flight together), then the lo tiles
+        constexpr int NA = TileMap<BM>::PER_THREAD, NB = TileMap<BN>::PER_THREAD;
+        uint32_t v[NA + NB][4];
 #pragma unroll
-        for (int j = 0; j < TileMap<BM>::PER_THREAD; ++j) lo_chunk(st + ma.soff[j], st + A_BYTES + ma.soff[j]);
+        for (int j = 0; j < NA; ++j) lds128(st + ma.soff[j], v[j]);
 #pragma unroll
-        for (int j = 0; j < TileMap<BN>::PER_THREAD; ++j) lo_chunk(st + 2 * A_BYTES + mb.soff[j], st + 2 * A_BYTES + B_BYTES + mb.soff[j]);
+        for (int j = 0; j < NB; ++j) lds128(st + 2 * A_BYTES + mb.soff[j], v[NA + j]);
+#pragma unroll
+        for (int j = 0; j < NA; ++j) sts128(st + A_BYTES + ma.soff[j], lo_of(v[j][0]), lo_of(v[j][1]), lo_of(v[j][2]), lo_of(v[j][3]));
+#pragma unroll
+        for (int j = 0; j < NB; ++j) sts128(st + 2 * A_BYTES + B_BYTES + mb.soff[j], lo_of(v[NA + j][0]), lo_of(v[NA + j][1]), lo_of(v[NA + j][2]), lo_of(v[NA + j][3]));
       }
       fence_proxy_async();  // generic-proxy / cp.async writes -> visible to the tensor core (async proxy)
       __syncwarp();
