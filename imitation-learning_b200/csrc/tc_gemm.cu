@@ -24,19 +24,30 @@ namespace {
 #define IL_TC_BK 16
 #endif
 constexpr int BM = 128, BN = 256, BK = IL_TC_BK;   // tile: 128 x 256 outputs; k-blocks of 16 floats (64 B rows, SWIZZLE_64B) or 32 (128 B)
-constexpr int STAGES = BK == 16 ? 4 : 2;           // 4 x 48 KB or 2 x 96 KB of operand stages
+#ifndef IL_TC_NH
+#define IL_TC_NH 6
+#endif
+#ifndef IL_TC_NL
+#define IL_TC_NL 2
+#endif
+// The raw (hi) tiles and the derived lo tiles live in separate rings: NH raw slots keep NH - 1 k-blocks of global loads
+// in flight (the kernel is bound by loaded HBM latency, not by the tensor pipe), the lo tiles only exist between the
+// split pass and the MMAs that read them, so NL = 2 slots suffice.
+constexpr int NH = IL_TC_NH, NL = IL_TC_NL;
+static_assert(BK == 16, "the hi/lo rings are laid out for 64-byte k-blocks");
 constexpr int KM_CHUNKS = BK / 4;                  // 16-byte chunks per K-major row
 constexpr int KM_ROW_BYTES = BK * 4;
 constexpr uint32_t KM_LAYOUT = BK == 16 ? 4u : 2u; // UMMA LayoutType: SWIZZLE_64B = 4, SWIZZLE_128B = 2
 constexpr int N_PRODUCER_WARPS = 8, N_EPI_WARPS = 4;
 constexpr int THREADS = (N_EPI_WARPS + 1 + N_PRODUCER_WARPS) * 32;  // 416
 constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;          // 16 KB, 32 KB (per hi or lo copy)
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;               // 96 KB
+constexpr int SLOT_BYTES = A_BYTES + B_BYTES;                        // 24 KB: one k-block of A (8 KB) then B (16 KB)
+constexpr int RING_BYTES = (NH + NL) * SLOT_BYTES;                   // 192 KB
 constexpr int EPI_LD = 33;                                           // padded row of the epilogue staging tile
 constexpr int EPI_BYTES = N_EPI_WARPS * 32 * EPI_LD * 4;
 constexpr int HEAD_MAX = 8;                                          // fused head: up to 8 output units (N = 1 critic, 2A <= 8 actor)
 constexpr int HEAD_BYTES = (BN + HEAD_MAX * BN) * 4;                 // bias [256] + head weights [8][256]
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + 256 + HEAD_BYTES;
+constexpr int SMEM_BYTES = 1024 + RING_BYTES + EPI_BYTES + 256 + HEAD_BYTES;
 constexpr uint32_t TMEM_COLS = 512;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
@@ -58,15 +69,22 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// `leader` != 0 on the one elected lane that issues (the rest of the warp executes the same uniform code predicated off)
+__device__ __forceinline__ void tc_commit(uint32_t bar, uint32_t leader) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar),
+      "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }
 __device__ __forceinline__ uint32_t to_tf32(float x) {
@@ -159,23 +177,25 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
-  float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
-  // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* head_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + EPI_BYTES + 256);  // [BN] bias then [HEAD_MAX][BN] head weights
+  float* epi = reinterpret_cast<float*>(smem + RING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING_BYTES + EPI_BYTES);
+  // bars: full[NH], empty[NH] (raw slots), lo_empty[NL], tmem_full[2], tmem_empty[2], then the TMEM base address
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NH + NL + 4);
+  float* head_s = reinterpret_cast<float*>(smem + RING_BYTES + EPI_BYTES + 256);  // [BN] bias then [HEAD_MAX][BN] head weights
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (NH + s); };
+  auto lo_empty_bar = [&](int l) { return bar0 + 8u * (2 * NH + l); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * NH + NL + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * NH + NL + 2 + a); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GemmArgs& g = p.g;
   const int nkb = g.K / BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), N_PRODUCER_WARPS); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < NH; ++s) { mbar_init(full_bar(s), N_PRODUCER_WARPS); mbar_init(empty_bar(s), 1); }
+    for (int l = 0; l < NL; ++l) mbar_init(lo_empty_bar(l), 1);
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), N_EPI_WARPS); }
     fence_barrier_init();
   }
@@ -205,9 +225,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
     const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_kb = my_tiles * nkb;
     // running position of the next k-block to copy (no divisions in the steady state)
-    int iss_tile = blockIdx.x, iss_kb = 0;
+    int iss_tile = blockIdx.x, iss_kb = 0, iss_slot = 0;
+    uint32_t iss_par = 1;  // parity to wait for on the slot's empty barrier (a fresh barrier passes parity 1)
     const float *iss_a = nullptr, *iss_b = nullptr;
-    auto issue = [&](int idx) {  // async copies of this CTA's idx-th k-block into stage idx % STAGES
+    auto issue = [&]() {  // async copies of this CTA's next k-block into the next raw slot
       if (iss_kb == 0) {
         const int grp = iss_tile / p.tiles_m, m0 = (iss_tile % p.tiles_m) * BM;
         iss_a = g.A + (int64_t)(grp / g.a_gdiv) * g.a_gs + (a_km ? (int64_t)m0 * g.lda : (int64_t)m0);
@@ -218,86 +239,100 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
       iss_a += a_kstep;
       iss_b += b_kstep;
       if (++iss_kb == nkb) { iss_kb = 0; iss_tile += gridDim.x; }
-      const int s = idx % STAGES;
-      if (lane == 0) mbar_wait(empty_bar(s), ((idx / STAGES) & 1) ^ 1);
+      if (lane == 0) mbar_wait(empty_bar(iss_slot), iss_par);
       __syncwarp();
-      const uint32_t st = stage0 + s * STAGE_BYTES;
+      const uint32_t st = stage0 + iss_slot * SLOT_BYTES;
+      if (++iss_slot == NH) { iss_slot = 0; iss_par ^= 1u; }
 #pragma unroll
       for (int j = 0; j < TileMap<BM>::PER_THREAD; ++j) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + ma.soff[j]), "l"(A + ma.goff[j]) : "memory");
 #pragma unroll
-      for (int j = 0; j < TileMap<BN>::PER_THREAD; ++j) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + 2 * A_BYTES + mb.soff[j]), "l"(B + mb.goff[j]) : "memory");
+      for (int j = 0; j < TileMap<BN>::PER_THREAD; ++j) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + A_BYTES + mb.soff[j]), "l"(B + mb.goff[j]) : "memory");
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     auto lds128 = [&](uint32_t addr, uint32_t (&v)[4]) {
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
     };
     auto lo_of = [](uint32_t x) { return __float_as_uint(__uint_as_float(x) - __uint_as_float(x & 0xFFFFE000u)); };
-    // STAGES - 1 k-blocks of copies are kept in flight; one commit group per loop iteration (empty at the tail) keeps
-    // the wait_group bookkeeping uniform
-    for (int i = 0; i < STAGES - 1; ++i) {
-      if (i < total_kb) issue(i);
+    // NH - 1 k-blocks of copies are kept in flight; one commit group per loop iteration (empty at the tail) keeps the
+    // wait_group bookkeeping uniform
+    for (int i = 0; i < NH - 1; ++i) {
+      if (i < total_kb) issue();
       else asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    int hs = 0, ls = 0;
+    uint32_t lo_par = 1;
     for (int idx = 0; idx < total_kb; ++idx) {
-      if (STAGES == 4) asm volatile("cp.async.wait_group 2;" ::: "memory");  // this thread's copies of k-block idx have landed
-      else asm volatile("cp.async.wait_group 0;" ::: "memory");
-      const int s = idx % STAGES;
-      const uint32_t st = stage0 + s * STAGE_BYTES;
-      if (split) {  // all loads first (independent, in flight together), then the lo tiles
+      asm volatile("cp.async.wait_group %0;" ::"n"(NH - 2) : "memory");  // this thread's copies of k-block idx have landed
+      const uint32_t st = stage0 + hs * SLOT_BYTES;
+      if (split) {  // all loads first (independent, in flight together), then the lo tiles into the next lo slot
         constexpr int NA = TileMap<BM>::PER_THREAD, NB = TileMap<BN>::PER_THREAD;
         uint32_t v[NA + NB][4];
 #pragma unroll
         for (int j = 0; j < NA; ++j) lds128(st + ma.soff[j], v[j]);
 #pragma unroll
-        for (int j = 0; j < NB; ++j) lds128(st + 2 * A_BYTES + mb.soff[j], v[NA + j]);
+        for (int j = 0; j < NB; ++j) lds128(st + A_BYTES + mb.soff[j], v[NA + j]);
+        if (lane == 0) mbar_wait(lo_empty_bar(ls), lo_par);  // the MMAs that read this lo slot NL k-blocks ago are done
+        __syncwarp();
+        const uint32_t lo = stage0 + (NH + ls) * SLOT_BYTES;
+        if (++ls == NL) { ls = 0; lo_par ^= 1u; }
 #pragma unroll
-        for (int j = 0; j < NA; ++j) sts128(st + A_BYTES + ma.soff[j], lo_of(v[j][0]), lo_of(v[j][1]), lo_of(v[j][2]), lo_of(v[j][3]));
+        for (int j = 0; j < NA; ++j) sts128(lo + ma.soff[j], lo_of(v[j][0]), lo_of(v[j][1]), lo_of(v[j][2]), lo_of(v[j][3]));
 #pragma unroll
-        for (int j = 0; j < NB; ++j) sts128(st + 2 * A_BYTES + B_BYTES + mb.soff[j], lo_of(v[NA + j][0]), lo_of(v[NA + j][1]), lo_of(v[NA + j][2]), lo_of(v[NA + j][3]));
+        for (int j = 0; j < NB; ++j) sts128(lo + A_BYTES + mb.soff[j], lo_of(v[NA + j][0]), lo_of(v[NA + j][1]), lo_of(v[NA + j][2]), lo_of(v[NA + j][3]));
       }
       fence_proxy_async();  // generic-proxy / cp.async writes -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) mbar_arrive(full_bar(s));
-      if (idx + STAGES - 1 < total_kb) issue(idx + STAGES - 1);  // waits for the MMAs that last read that stage, then refills it
+      if (lane == 0) mbar_arrive(full_bar(hs));
+      if (++hs == NH) hs = 0;
+      if (idx + NH - 1 < total_kb) issue();  // waits for the MMAs that last read that raw slot, then refills it
       else asm volatile("cp.async.commit_group;" ::: "memory");
     }
   } else if (warp == N_EPI_WARPS) {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
-      // InstrDescriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), a_major bit 15, b_major bit 16 (1 = MN-major),
-      // N>>3 at bit 17, M>>4 at bit 24
-      const bool a_km = g.a_kmajor != 0, b_km = g.b_kmajor != 0;
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((a_km ? 0u : 1u) << 15) | ((b_km ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      // per-MMA (K = 8 tf32) advance: 32 bytes inside the swizzled 128-byte row (K-major) or two 4-k groups (MN-major)
-      const uint32_t a_lbo = a_km ? 16u : 512u, a_sbo = a_km ? 8u * KM_ROW_BYTES : (uint32_t)(BM / 32) * 512u, a_kadv = a_km ? 32u : 2u * a_sbo, a_lt = a_km ? KM_LAYOUT : 1u;
-      const uint32_t b_lbo = b_km ? 16u : 512u, b_sbo = b_km ? 8u * KM_ROW_BYTES : (uint32_t)(BN / 32) * 512u, b_kadv = b_km ? 32u : 2u * b_sbo, b_lt = b_km ? KM_LAYOUT : 1u;
-      uint32_t kb_global = 0, it = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
+    // ================= MMA issuer =================
+    // The whole warp runs the (warp-uniform) control flow and address arithmetic so the descriptors stay in uniform
+    // registers; one elected lane issues the tcgen05 instructions. (Issuing from `if (lane == 0)` made the compiler wrap
+    // every MMA in a divergence loop and left the issuing thread, not the tensor pipe, as the bottleneck.)
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    // InstrDescriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), a_major bit 15, b_major bit 16 (1 = MN-major),
+    // N>>3 at bit 17, M>>4 at bit 24
+    const bool a_km = g.a_kmajor != 0, b_km = g.b_kmajor != 0, split = p.split != 0;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((a_km ? 0u : 1u) << 15) | ((b_km ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // per-MMA (K = 8 tf32) advance: 32 bytes inside the swizzled 64-byte row (K-major) or two 4-k groups (MN-major)
+    const uint32_t a_lbo = a_km ? 16u : 512u, a_sbo = a_km ? 8u * KM_ROW_BYTES : (uint32_t)(BM / 32) * 512u, a_kadv = a_km ? 32u : 2u * a_sbo, a_lt = a_km ? KM_LAYOUT : 1u;
+    const uint32_t b_lbo = b_km ? 16u : 512u, b_sbo = b_km ? 8u * KM_ROW_BYTES : (uint32_t)(BN / 32) * 512u, b_kadv = b_km ? 32u : 2u * b_sbo, b_lt = b_km ? KM_LAYOUT : 1u;
+    // descriptors = kernel-invariant part + (shared address >> 4) in the low 14 bits (shared addresses are < 256 KB)
+    const uint64_t a_desc0 = make_desc(0, a_lbo, a_sbo, a_lt), b_desc0 = make_desc(0, b_lbo, b_sbo, b_lt);
+    const uint32_t ring0 = smem_u32(stage_base);
+    uint32_t it = 0, hpar = 0;
+    int hs = 0, ls = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(full_bar(hs), hpar);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < nkb; ++kb, ++kb_global) {
-          const int s = kb_global % STAGES;
-          mbar_wait(full_bar(s), (kb_global / STAGES) & 1);
-          tc_fence_after();
-          const uint32_t a_hi = smem_u32(stage_base + s * STAGE_BYTES), a_lo = a_hi + A_BYTES, b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+        const uint32_t a_hi = ring0 + hs * SLOT_BYTES, b_hi = a_hi + A_BYTES, a_lo = ring0 + (NH + ls) * SLOT_BYTES, b_lo = a_lo + A_BYTES;
 #pragma unroll
-          for (int kk = 0; kk < BK / 8; ++kk) {
-            const uint32_t ao = kk * a_kadv, bo = kk * b_kadv;
-            const uint32_t first = (kb == 0 && kk == 0) ? 0u : 1u;
-            if (p.split) {
-              tc_mma_tf32(d_tmem, make_desc(a_lo + ao, a_lbo, a_sbo, a_lt), make_desc(b_hi + bo, b_lbo, b_sbo, b_lt), idesc, first);
-              tc_mma_tf32(d_tmem, make_desc(a_hi + ao, a_lbo, a_sbo, a_lt), make_desc(b_lo + bo, b_lbo, b_sbo, b_lt), idesc, 1u);
-              tc_mma_tf32(d_tmem, make_desc(a_hi + ao, a_lbo, a_sbo, a_lt), make_desc(b_hi + bo, b_lbo, b_sbo, b_lt), idesc, 1u);
-            } else {
-              tc_mma_tf32(d_tmem, make_desc(a_hi + ao, a_lbo, a_sbo, a_lt), make_desc(b_hi + bo, b_lbo, b_sbo, b_lt), idesc, first);
-            }
+        for (int kk = 0; kk < BK / 8; ++kk) {
+          const uint64_t ah = a_desc0 + ((a_hi + kk * a_kadv) >> 4), al = a_desc0 + ((a_lo + kk * a_kadv) >> 4);
+          const uint64_t bh = b_desc0 + ((b_hi + kk * b_kadv) >> 4), bl = b_desc0 + ((b_lo + kk * b_kadv) >> 4);
+          const uint32_t first = (kb == 0 && kk == 0) ? 0u : 1u;
+          if (split) {
+            tc_mma_tf32(d_tmem, al, bh, idesc, first, leader);
+            tc_mma_tf32(d_tmem, ah, bl, idesc, 1u, leader);
+            tc_mma_tf32(d_tmem, ah, bh, idesc, 1u, leader);
+          } else {
+            tc_mma_tf32(d_tmem, ah, bh, idesc, first, leader);
           }
-          tc_commit(empty_bar(s));  // frees the stage once these MMAs have read it (implicit before_thread_sync fence)
         }
-        tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        tc_commit(empty_bar(hs), leader);  // frees the raw slot once these MMAs have read it (implicit before_thread_sync fence)
+        if (split) { tc_commit(lo_empty_bar(ls), leader); if (++ls == NL) ls = 0; }
+        if (++hs == NH) { hs = 0; hpar ^= 1u; }
       }
+      tc_commit(tfull_bar(acc), leader);  // accumulator complete -> epilogue
     }
     __syncwarp();
   } else {
