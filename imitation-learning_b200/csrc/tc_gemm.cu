@@ -38,7 +38,10 @@ static_assert(BK == 16, "the hi/lo rings are laid out for 64-byte k-blocks");
 constexpr int KM_CHUNKS = BK / 4;                  // 16-byte chunks per K-major row
 constexpr int KM_ROW_BYTES = BK * 4;
 constexpr uint32_t KM_LAYOUT = BK == 16 ? 4u : 2u; // UMMA LayoutType: SWIZZLE_64B = 4, SWIZZLE_128B = 2
-constexpr int N_PRODUCER_WARPS = 8, N_EPI_WARPS = 4;
+#ifndef IL_TC_PW
+#define IL_TC_PW 8
+#endif
+constexpr int N_PRODUCER_WARPS = IL_TC_PW, N_EPI_WARPS = 4;
 constexpr int THREADS = (N_EPI_WARPS + 1 + N_PRODUCER_WARPS) * 32;  // 416
 constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;          // 16 KB, 32 KB (per hi or lo copy)
 constexpr int SLOT_BYTES = A_BYTES + B_BYTES;                        // 24 KB: one k-block of A (8 KB) then B (16 KB)
@@ -146,25 +149,36 @@ __device__ __forceinline__ void store_split(uint32_t hi_addr, uint32_t lo_addr, 
 //                   operands, SWIZZLE_128B_BASE32B (cute Layout_MN_SW128_32B_Atom, the only MN-major layout tf32 has):
 //                   atom = 4 k-rows x 128 B (32 consecutive r), 32-byte chunk q of a row stored at q ^ (k % 4);
 //                   atoms along r 512 B apart (LBO), groups of 4 k (ROWS / 32) * 512 B apart (SBO).
-template <int ROWS>
-struct TileMap {
-  static constexpr int PER_THREAD = ROWS * KM_CHUNKS / (N_PRODUCER_WARPS * 32);  // 16-byte chunks per thread per k-block
-  uint32_t goff[PER_THREAD];   // global offset (floats) relative to the tile origin at k-block 0
-  uint32_t soff[PER_THREAD];   // byte offset inside the stage tile
-  __device__ __forceinline__ void init(int ld, bool kmajor, int ptid) {
+constexpr int PT = N_PRODUCER_WARPS * 32;                       // producer threads
+constexpr int A_CHUNKS = BM * KM_CHUNKS, B_CHUNKS = BN * KM_CHUNKS;  // 16-byte chunks per k-block
+constexpr int CPT = (A_CHUNKS + B_CHUNKS) / PT;                 // chunks per producer thread per k-block
+static_assert(CPT * PT == A_CHUNKS + B_CHUNKS, "producer threads must divide the chunks of a k-block");
+constexpr bool A_SPLIT_STATIC = A_CHUNKS % PT == 0;             // chunk j of every thread belongs to the same operand
+struct ChunkMap {  // chunk j of a thread: global chunk id ptid + j * PT over [A chunks | B chunks]
+  uint32_t goff[CPT];   // global offset (floats) relative to the operand's tile origin at k-block 0
+  uint32_t soff[CPT];   // byte offset inside a ring slot (A tile at 0, B tile at A_BYTES)
+  uint32_t amask;       // bit j set: chunk j is an A chunk
+  __device__ __forceinline__ bool is_a(int j) const { return A_SPLIT_STATIC ? j < A_CHUNKS / PT : ((amask >> j) & 1u) != 0; }
+  __device__ __forceinline__ void init(int lda, bool a_km, int ldb, bool b_km, int ptid) {
+    amask = 0;
 #pragma unroll
-    for (int j = 0; j < PER_THREAD; ++j) {
-      const int i = ptid + j * (N_PRODUCER_WARPS * 32);
-      if (kmajor) {
+    for (int j = 0; j < CPT; ++j) {
+      int i = ptid + j * PT;
+      const bool isa = i < A_CHUNKS;
+      if (isa) amask |= 1u << j;
+      else i -= A_CHUNKS;
+      const int rows = isa ? BM : BN, ld = isa ? lda : ldb;
+      const uint32_t base = isa ? 0u : (uint32_t)A_BYTES;
+      if (isa ? a_km : b_km) {
         const int r = i / KM_CHUNKS, c = i % KM_CHUNKS;
         goff[j] = (uint32_t)(r * ld + c * 4);
-        soff[j] = sw128(r, c);
+        soff[j] = base + sw128(r, c);
       } else {
-        constexpr int CH = ROWS / 4;            // 16-byte chunks per k row
+        const int CH = rows / 4;                // 16-byte chunks per k row
         const int k = i / CH, c = i % CH;       // consecutive threads -> consecutive chunks of one k row (coalesced)
         const int atom = c >> 3, q = (c & 7) >> 1, half = c & 1;  // 32-row atom along r, 32-byte chunk, 16-byte half
         goff[j] = (uint32_t)(k * ld + c * 4);
-        soff[j] = (uint32_t)((k >> 2) * (ROWS / 32) * 512 + atom * 512 + (k & 3) * 128 + ((q ^ (k & 3)) << 5) + (half << 4));
+        soff[j] = base + (uint32_t)((k >> 2) * (rows / 32) * 512 + atom * 512 + (k & 3) * 128 + ((q ^ (k & 3)) << 5) + (half << 4));
       }
     }
   }
@@ -216,10 +230,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
     // is the hi operand (truncated) and lo = x - trunc_tf32(x) is exact in fp32.
     const int ptid = threadIdx.x - (N_EPI_WARPS + 1) * 32;
     const bool a_km = g.a_kmajor != 0, b_km = g.b_kmajor != 0, split = p.split != 0;
-    TileMap<BM> ma;
-    TileMap<BN> mb;
-    ma.init(g.lda, a_km, ptid);
-    mb.init(g.ldb, b_km, ptid);
+    ChunkMap cm;
+    cm.init(g.lda, a_km, g.ldb, b_km, ptid);
     const int64_t a_kstep = a_km ? BK : (int64_t)BK * g.lda, b_kstep = b_km ? BK : (int64_t)BK * g.ldb;  // floats per k-block
     const uint32_t stage0 = smem_u32(stage_base);
     const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -244,9 +256,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
       const uint32_t st = stage0 + iss_slot * SLOT_BYTES;
       if (++iss_slot == NH) { iss_slot = 0; iss_par ^= 1u; }
 #pragma unroll
-      for (int j = 0; j < TileMap<BM>::PER_THREAD; ++j) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + ma.soff[j]), "l"(A + ma.goff[j]) : "memory");
-#pragma unroll
-      for (int j = 0; j < TileMap<BN>::PER_THREAD; ++j) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + A_BYTES + mb.soff[j]), "l"(B + mb.goff[j]) : "memory");
+      for (int j = 0; j < CPT; ++j) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + cm.soff[j]), "l"((cm.is_a(j) ? A : B) + cm.goff[j]) : "memory");
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     auto lds128 = [&](uint32_t addr, uint32_t (&v)[4]) {
@@ -265,20 +275,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
       asm volatile("cp.async.wait_group %0;" ::"n"(NH - 2) : "memory");  // this thread's copies of k-block idx have landed
       const uint32_t st = stage0 + hs * SLOT_BYTES;
       if (split) {  // all loads first (independent, in flight together), then the lo tiles into the next lo slot
-        constexpr int NA = TileMap<BM>::PER_THREAD, NB = TileMap<BN>::PER_THREAD;
-        uint32_t v[NA + NB][4];
+        uint32_t v[CPT][4];
 #pragma unroll
-        for (int j = 0; j < NA; ++j) lds128(st + ma.soff[j], v[j]);
-#pragma unroll
-        for (int j = 0; j < NB; ++j) lds128(st + A_BYTES + mb.soff[j], v[NA + j]);
+        for (int j = 0; j < CPT; ++j) lds128(st + cm.soff[j], v[j]);
         if (lane == 0) mbar_wait(lo_empty_bar(ls), lo_par);  // the MMAs that read this lo slot NL k-blocks ago are done
         __syncwarp();
         const uint32_t lo = stage0 + (NH + ls) * SLOT_BYTES;
         if (++ls == NL) { ls = 0; lo_par ^= 1u; }
 #pragma unroll
-        for (int j = 0; j < NA; ++j) sts128(lo + ma.soff[j], lo_of(v[j][0]), lo_of(v[j][1]), lo_of(v[j][2]), lo_of(v[j][3]));
-#pragma unroll
-        for (int j = 0; j < NB; ++j) sts128(lo + A_BYTES + mb.soff[j], lo_of(v[NA + j][0]), lo_of(v[NA + j][1]), lo_of(v[NA + j][2]), lo_of(v[NA + j][3]));
+        for (int j = 0; j < CPT; ++j) sts128(lo + cm.soff[j], lo_of(v[j][0]), lo_of(v[j][1]), lo_of(v[j][2]), lo_of(v[j][3]));
       }
       fence_proxy_async();  // generic-proxy / cp.async writes -> visible to the tensor core (async proxy)
       __syncwarp();
