@@ -1,5 +1,6 @@
 // Library plumbing: handle, error reporting, layout queries, Philox fills.
 #include "common.cuh"
+#include <cstdlib>
 
 thread_local char g_il_error[512] = "";
 int gail_init();
@@ -27,6 +28,11 @@ extern "C" int il_create(int device, il_handle** out) {
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   h->gemm_mode = IL_GEMM_FP32;
+  {
+    const char* e = getenv("IL_TC_PAIRS");
+    h->tc_pairs = (e && e[0] == '0') ? 0 : 1;
+    h->tc_pair_groups = 0;
+  }
   h->launches = 0;
   h->profiling = 0;
   *out = h;

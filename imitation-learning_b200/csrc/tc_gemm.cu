@@ -17,6 +17,8 @@
 //   TMEM holds two 128 x 256 fp32 accumulators (512 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 // A TMA path is not used because every operand needs the hi/lo split (a CUDA-core pass over the tile) anyway.
 #include "common.cuh"
+#include <cstdio>
+#include <cstdlib>
 
 namespace {
 
@@ -33,7 +35,6 @@ constexpr int BM = 128, BN = 256, BK = IL_TC_BK;   // tile: 128 x 256 outputs; k
 // The raw (hi) tiles and the derived lo tiles live in separate rings: NH raw slots keep NH - 1 k-blocks of global loads
 // in flight (the kernel is bound by loaded HBM latency, not by the tensor pipe), the lo tiles only exist between the
 // split pass and the MMAs that read them, so NL = 2 slots suffice.
-constexpr int NH = IL_TC_NH, NL = IL_TC_NL;
 static_assert(BK == 16, "the hi/lo rings are laid out for 64-byte k-blocks");
 constexpr int KM_CHUNKS = BK / 4;                  // 16-byte chunks per K-major row
 constexpr int KM_ROW_BYTES = BK * 4;
@@ -43,9 +44,20 @@ constexpr uint32_t KM_LAYOUT = BK == 16 ? 4u : 2u; // UMMA LayoutType: SWIZZLE_6
 #endif
 constexpr int N_PRODUCER_WARPS = IL_TC_PW, N_EPI_WARPS = 4;
 constexpr int THREADS = (N_EPI_WARPS + 1 + N_PRODUCER_WARPS) * 32;  // 416
-constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;          // 16 KB, 32 KB (per hi or lo copy)
-constexpr int SLOT_BYTES = A_BYTES + B_BYTES;                        // 24 KB: one k-block of A (8 KB) then B (16 KB)
-constexpr int RING_BYTES = (NH + NL) * SLOT_BYTES;                   // 192 KB
+constexpr int A_BYTES = BM * BK * 4;                                 // 8 KB per k-block (hi or lo copy)
+// Per-CTA geometry for CG = 1 (one CTA computes a 128 x 256 tile) and CG = 2 (a CTA pair computes 256 x 256 with
+// tcgen05.mma.cta_group::2: each CTA stages its own 128 rows of A and HALF of B, i.e. 128 of the 256 output columns'
+// operand rows, so per-CTA shared-memory and L2 traffic per flop drop by a third and the rings get deeper).
+template <int CG>
+struct Geo {
+  static constexpr int BNL = BN / CG;                                // rows of the B operand tile staged by this CTA
+  static constexpr int B_BYTES = BNL * BK * 4;                       // 16 KB / 8 KB
+  static constexpr int SLOT_BYTES = A_BYTES + B_BYTES;               // one k-block of A then B: 24 KB / 16 KB
+  static constexpr int NH = CG == 1 ? IL_TC_NH : 9, NL = CG == 1 ? IL_TC_NL : 3;
+  static constexpr int RING_BYTES = (NH + NL) * SLOT_BYTES;          // 192 KB
+};
+constexpr int RING_BYTES = Geo<1>::RING_BYTES;
+static_assert(Geo<2>::RING_BYTES <= RING_BYTES, "the pair kernel uses the same shared-memory carve-up");
 constexpr int EPI_LD = 33;                                           // padded row of the epilogue staging tile
 constexpr int EPI_BYTES = N_EPI_WARPS * 32 * EPI_LD * 4;
 constexpr int HEAD_MAX = 8;                                          // fused head: up to 8 output units (N = 1 critic, 2A <= 8 actor)
@@ -68,27 +80,77 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// CTA pairs: arrive on the barrier at the same offset in CTA `cta` of the cluster. Default (.release.cta) semantics as in
+// cutlass::arch::ClusterBarrier::arrive(cta_id): a .release.cluster arrive waits for the thread's in-flight cp.async
+// groups as well, which collapses the load pipeline to one k-block (measured: 0.61 ms instead of 0.33 ms per launch).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // `leader` != 0 on the one elected lane that issues (the rest of the warp executes the same uniform code predicated off)
+template <int CG>
 __device__ __forceinline__ void tc_commit(uint32_t bar, uint32_t leader) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %1, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar),
-      "r"(leader)
-      : "memory");
+  if (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar),
+        "r"(leader)
+        : "memory");
+  else  // arrives on the barrier at this offset in BOTH CTAs of the pair
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .b16 m;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "mov.b16 m, 3;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}" ::"r"(bar),
+        "r"(leader)
+        : "memory");
 }
+template <int CG>
 __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate, uint32_t leader) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
-      : "memory");
+  if (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
 }
 __device__ __forceinline__ uint32_t to_tf32(float x) {
   uint32_t r;
@@ -150,11 +212,13 @@ __device__ __forceinline__ void store_split(uint32_t hi_addr, uint32_t lo_addr, 
 //                   atom = 4 k-rows x 128 B (32 consecutive r), 32-byte chunk q of a row stored at q ^ (k % 4);
 //                   atoms along r 512 B apart (LBO), groups of 4 k (ROWS / 32) * 512 B apart (SBO).
 constexpr int PT = N_PRODUCER_WARPS * 32;                       // producer threads
-constexpr int A_CHUNKS = BM * KM_CHUNKS, B_CHUNKS = BN * KM_CHUNKS;  // 16-byte chunks per k-block
-constexpr int CPT = (A_CHUNKS + B_CHUNKS) / PT;                 // chunks per producer thread per k-block
-static_assert(CPT * PT == A_CHUNKS + B_CHUNKS, "producer threads must divide the chunks of a k-block");
+constexpr int A_CHUNKS = BM * KM_CHUNKS;                        // 16-byte chunks of the A tile per k-block
 constexpr bool A_SPLIT_STATIC = A_CHUNKS % PT == 0;             // chunk j of every thread belongs to the same operand
+template <int BNL>
 struct ChunkMap {  // chunk j of a thread: global chunk id ptid + j * PT over [A chunks | B chunks]
+  static constexpr int B_CHUNKS = BNL * KM_CHUNKS;
+  static constexpr int CPT = (A_CHUNKS + B_CHUNKS) / PT;        // chunks per producer thread per k-block
+  static_assert(CPT * PT == A_CHUNKS + B_CHUNKS, "producer threads must divide the chunks of a k-block");
   uint32_t goff[CPT];   // global offset (floats) relative to the operand's tile origin at k-block 0
   uint32_t soff[CPT];   // byte offset inside a ring slot (A tile at 0, B tile at A_BYTES)
   uint32_t amask;       // bit j set: chunk j is an A chunk
@@ -167,7 +231,7 @@ struct ChunkMap {  // chunk j of a thread: global chunk id ptid + j * PT over [A
       const bool isa = i < A_CHUNKS;
       if (isa) amask |= 1u << j;
       else i -= A_CHUNKS;
-      const int rows = isa ? BM : BN, ld = isa ? lda : ldb;
+      const int rows = isa ? BM : BNL, ld = isa ? lda : ldb;
       const uint32_t base = isa ? 0u : (uint32_t)A_BYTES;
       if (isa ? a_km : b_km) {
         const int r = i / KM_CHUNKS, c = i % KM_CHUNKS;
@@ -186,8 +250,11 @@ struct ChunkMap {  // chunk j of a thread: global chunk id ptid + j * PT over [A
 
 // EPI: 0 plain store, 1 bias + relu, 2 relu-derivative mask, 3 generic (runtime bias / activation / mask),
 //      4 bias + relu + fused linear head (the next, final layer of the MLP computed from the accumulator row in registers)
-template <int EPI>
+template <int EPI, int CG>
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
+  constexpr int NH = Geo<CG>::NH, NL = Geo<CG>::NL, SLOT_BYTES = Geo<CG>::SLOT_BYTES, BNL = Geo<CG>::BNL;
+  using CMap = ChunkMap<BNL>;
+  constexpr int CPT = CMap::CPT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
@@ -206,19 +273,35 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GemmArgs& g = p.g;
   const int nkb = g.K / BK;
+  // CTA group (a single CTA, or the pair of a 2-CTA cluster): the unit that owns one (CG * 128) x 256 output tile
+  const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();
+  const int gid = (int)blockIdx.x / CG, n_groups = (int)gridDim.x / CG;
+  // signals a barrier of the group's leader CTA (rank 0), which issues the MMAs for both CTAs
+  auto arrive_leader = [&](uint32_t bar) {
+    if (CG == 1) mbar_arrive(bar);
+    else mbar_arrive_remote(bar, 0u);
+  };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NH; ++s) { mbar_init(full_bar(s), N_PRODUCER_WARPS); mbar_init(empty_bar(s), 1); }
+    // full / tmem_empty collect the arrivals of every CTA of the group on the leader; empty / lo_empty / tmem_full are
+    // signalled in every CTA by the (multicast) tcgen05.commit
+    for (int s = 0; s < NH; ++s) { mbar_init(full_bar(s), CG * N_PRODUCER_WARPS); mbar_init(empty_bar(s), 1); }
     for (int l = 0; l < NL; ++l) mbar_init(lo_empty_bar(l), 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), N_EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), CG * N_EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == N_EPI_WARPS) {  // TMEM allocation by the MMA warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == N_EPI_WARPS) {  // TMEM allocation by the MMA warp (of every CTA)
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 1) __syncthreads();
+  else cluster_sync_all();  // the peer's barriers are initialised before anyone arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -230,27 +313,27 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
     // is the hi operand (truncated) and lo = x - trunc_tf32(x) is exact in fp32.
     const int ptid = threadIdx.x - (N_EPI_WARPS + 1) * 32;
     const bool a_km = g.a_kmajor != 0, b_km = g.b_kmajor != 0, split = p.split != 0;
-    ChunkMap cm;
+    CMap cm;
     cm.init(g.lda, a_km, g.ldb, b_km, ptid);
     const int64_t a_kstep = a_km ? BK : (int64_t)BK * g.lda, b_kstep = b_km ? BK : (int64_t)BK * g.ldb;  // floats per k-block
     const uint32_t stage0 = smem_u32(stage_base);
-    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int my_tiles = (p.n_tiles - gid + n_groups - 1) / n_groups;
     const int total_kb = my_tiles * nkb;
     // running position of the next k-block to copy (no divisions in the steady state)
-    int iss_tile = blockIdx.x, iss_kb = 0, iss_slot = 0;
+    int iss_tile = gid, iss_kb = 0, iss_slot = 0;
     uint32_t iss_par = 1;  // parity to wait for on the slot's empty barrier (a fresh barrier passes parity 1)
     const float *iss_a = nullptr, *iss_b = nullptr;
     auto issue = [&]() {  // async copies of this CTA's next k-block into the next raw slot
       if (iss_kb == 0) {
-        const int grp = iss_tile / p.tiles_m, m0 = (iss_tile % p.tiles_m) * BM;
+        const int grp = iss_tile / p.tiles_m, m0 = (iss_tile % p.tiles_m) * (BM * CG) + (int)rank * BM, n0 = (int)rank * BNL;
         iss_a = g.A + (int64_t)(grp / g.a_gdiv) * g.a_gs + (a_km ? (int64_t)m0 * g.lda : (int64_t)m0);
-        iss_b = g.B + (int64_t)(grp / g.b_gdiv) * g.b_gs;
+        iss_b = g.B + (int64_t)(grp / g.b_gdiv) * g.b_gs + (b_km ? (int64_t)n0 * g.ldb : (int64_t)n0);  // this CTA's rows of the B operand
       }
       const float* A = iss_a;
       const float* B = iss_b;
       iss_a += a_kstep;
       iss_b += b_kstep;
-      if (++iss_kb == nkb) { iss_kb = 0; iss_tile += gridDim.x; }
+      if (++iss_kb == nkb) { iss_kb = 0; iss_tile += n_groups; }
       if (lane == 0) mbar_wait(empty_bar(iss_slot), iss_par);
       __syncwarp();
       const uint32_t st = stage0 + iss_slot * SLOT_BYTES;
@@ -287,7 +370,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
       }
       fence_proxy_async();  // generic-proxy / cp.async writes -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) mbar_arrive(full_bar(hs));
+      if (lane == 0) arrive_leader(full_bar(hs));
       if (++hs == NH) hs = 0;
       if (idx + NH - 1 < total_kb) issue();  // waits for the MMAs that last read that raw slot, then refills it
       else asm volatile("cp.async.commit_group;" ::: "memory");
@@ -299,25 +382,28 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
     // every MMA in a divergence loop and left the issuing thread, not the tensor pipe, as the bottleneck.)
     uint32_t leader;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    if (rank == 0) {  // in a CTA pair only the leader CTA issues (for both)
     // InstrDescriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), a_major bit 15, b_major bit 16 (1 = MN-major),
     // N>>3 at bit 17, M>>4 at bit 24
     const bool a_km = g.a_kmajor != 0, b_km = g.b_kmajor != 0, split = p.split != 0;
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((a_km ? 0u : 1u) << 15) | ((b_km ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((a_km ? 0u : 1u) << 15) | ((b_km ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
     // per-MMA (K = 8 tf32) advance: 32 bytes inside the swizzled 64-byte row (K-major) or two 4-k groups (MN-major)
     const uint32_t a_lbo = a_km ? 16u : 512u, a_sbo = a_km ? 8u * KM_ROW_BYTES : (uint32_t)(BM / 32) * 512u, a_kadv = a_km ? 32u : 2u * a_sbo, a_lt = a_km ? KM_LAYOUT : 1u;
-    const uint32_t b_lbo = b_km ? 16u : 512u, b_sbo = b_km ? 8u * KM_ROW_BYTES : (uint32_t)(BN / 32) * 512u, b_kadv = b_km ? 32u : 2u * b_sbo, b_lt = b_km ? KM_LAYOUT : 1u;
+    const uint32_t b_lbo = b_km ? 16u : 512u, b_sbo = b_km ? 8u * KM_ROW_BYTES : (uint32_t)(BNL / 32) * 512u, b_kadv = b_km ? 32u : 2u * b_sbo, b_lt = b_km ? KM_LAYOUT : 1u;
     // descriptors = kernel-invariant part + (shared address >> 4) in the low 14 bits (shared addresses are < 256 KB)
     const uint64_t a_desc0 = make_desc(0, a_lbo, a_sbo, a_lt), b_desc0 = make_desc(0, b_lbo, b_sbo, b_lt);
     const uint32_t ring0 = smem_u32(stage_base);
     uint32_t it = 0, hpar = 0;
     int hs = 0, ls = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = gid; tile < p.n_tiles; tile += n_groups, ++it) {
       const int acc = it & 1;
-      mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
+      if (CG == 1) mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
+      else mbar_wait_cluster(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(full_bar(hs), hpar);
+        if (CG == 1) mbar_wait(full_bar(hs), hpar);
+        else mbar_wait_cluster(full_bar(hs), hpar);
         tc_fence_after();
         const uint32_t a_hi = ring0 + hs * SLOT_BYTES, b_hi = a_hi + A_BYTES, a_lo = ring0 + (NH + ls) * SLOT_BYTES, b_lo = a_lo + A_BYTES;
 #pragma unroll
@@ -326,18 +412,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
           const uint64_t bh = b_desc0 + ((b_hi + kk * b_kadv) >> 4), bl = b_desc0 + ((b_lo + kk * b_kadv) >> 4);
           const uint32_t first = (kb == 0 && kk == 0) ? 0u : 1u;
           if (split) {
-            tc_mma_tf32(d_tmem, al, bh, idesc, first, leader);
-            tc_mma_tf32(d_tmem, ah, bl, idesc, 1u, leader);
-            tc_mma_tf32(d_tmem, ah, bh, idesc, 1u, leader);
+            tc_mma_tf32<CG>(d_tmem, al, bh, idesc, first, leader);
+            tc_mma_tf32<CG>(d_tmem, ah, bl, idesc, 1u, leader);
+            tc_mma_tf32<CG>(d_tmem, ah, bh, idesc, 1u, leader);
           } else {
-            tc_mma_tf32(d_tmem, ah, bh, idesc, first, leader);
+            tc_mma_tf32<CG>(d_tmem, ah, bh, idesc, first, leader);
           }
         }
-        tc_commit(empty_bar(hs), leader);  // frees the raw slot once these MMAs have read it (implicit before_thread_sync fence)
-        if (split) { tc_commit(lo_empty_bar(ls), leader); if (++ls == NL) ls = 0; }
+        tc_commit<CG>(empty_bar(hs), leader);  // frees the raw slot once these MMAs have read it (implicit before_thread_sync fence)
+        if (split) { tc_commit<CG>(lo_empty_bar(ls), leader); if (++ls == NL) ls = 0; }
         if (++hs == NH) { hs = 0; hpar ^= 1u; }
       }
-      tc_commit(tfull_bar(acc), leader);  // accumulator complete -> epilogue
+      tc_commit<CG>(tfull_bar(acc), leader);  // accumulator complete -> epilogue
+    }
     }
     __syncwarp();
   } else {
@@ -345,9 +432,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
     const uint32_t stg = smem_u32(epi) + (uint32_t)(warp * 32 * EPI_LD * 4);
     const int cq = (lane & 7) * 4, rsub = lane >> 3;
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = gid; tile < p.n_tiles; tile += n_groups, ++it) {
       const int acc = it & 1;
-      const int grp = tile / p.tiles_m, m0 = (tile % p.tiles_m) * BM;
+      const int grp = tile / p.tiles_m, m0 = (tile % p.tiles_m) * (BM * CG) + (int)rank * BM;
       mbar_wait(tfull_bar(acc), (it >> 1) & 1);
       tc_fence_after();
       float* C = g.C + (int64_t)grp * g.c_gs + (int64_t)(m0 + warp * 32 + rsub) * g.ldc + cq;
@@ -437,15 +524,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator drained
+      if (lane == 0) arrive_leader(tempty_bar(acc));  // accumulator drained
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 1) __syncthreads();
+  else cluster_sync_all();  // the peer may still be signalling this CTA's barriers / reading its operands until here
   if (warp == N_EPI_WARPS) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -471,12 +560,57 @@ bool tc_gemm_eligible(const GemmArgs& a) {
   return true;
 }
 
+template <int EPI, int CG>
+int tc_set_attr() {
+  IL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  return 0;
+}
+
 int tc_gemm_init() {
-  IL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  IL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  IL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  IL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  IL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  IL_TRY((tc_set_attr<0, 1>())); IL_TRY((tc_set_attr<1, 1>())); IL_TRY((tc_set_attr<2, 1>())); IL_TRY((tc_set_attr<3, 1>())); IL_TRY((tc_set_attr<4, 1>()));
+  IL_TRY((tc_set_attr<0, 2>())); IL_TRY((tc_set_attr<1, 2>())); IL_TRY((tc_set_attr<2, 2>())); IL_TRY((tc_set_attr<3, 2>())); IL_TRY((tc_set_attr<4, 2>()));
+  return 0;
+}
+
+// CTA pairs (tcgen05.mma.cta_group::2, one 256 x 256 tile per 2-CTA cluster) whenever the rows come in multiples of 256
+static bool tc_use_pairs(const il_handle* h, const GemmArgs& a) { return h->tc_pairs && a.M % (2 * BM) == 0 && h->sm_count >= 2; }
+
+template <int EPI>
+static int tc_launch(il_handle* h, TcParams& p, cudaStream_t stream) {
+  const GemmArgs& a = p.g;
+  const bool pairs = tc_use_pairs(h, a);
+  const int cg = pairs ? 2 : 1;
+  p.tiles_m = a.M / (BM * cg);
+  p.n_tiles = a.G * p.tiles_m;
+  if (!pairs) {
+    const int groups = p.n_tiles < h->sm_count ? p.n_tiles : h->sm_count;
+    IL_LAUNCH(h, (tc_gemm_kernel<EPI, 1>), groups, THREADS, SMEM_BYTES, stream, p);
+    return 0;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(h->sm_count & ~1);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // The persistent grid must be co-resident: a 2-CTA cluster needs both SMs of a TPC, and on parts with TPCs that
+  // have a single enabled SM fewer than sm_count / 2 clusters fit at once (a second wave would double the time).
+  if (h->tc_pair_groups == 0) {
+    int n = 0;
+    IL_CUDA(cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel<EPI, 2>, &cfg));
+    IL_CHECK(n >= 1, "tc_gemm: no 2-CTA cluster of the tcgen05 kernel fits on this device");
+    h->tc_pair_groups = n;
+    if (getenv("IL_TC_VERBOSE")) fprintf(stderr, "[il_b200] tcgen05 pair kernel: %d co-resident 2-CTA clusters on %d SMs\n", n, h->sm_count);
+  }
+  const int groups = p.n_tiles < h->tc_pair_groups ? p.n_tiles : h->tc_pair_groups;
+  cfg.gridDim = dim3(groups * 2);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<EPI, 2>, p);
+  h->launches++;
+  if (e != cudaSuccess) IL_FAIL("cluster launch of tc_gemm_kernel<%d, 2> failed: %s", EPI, cudaGetErrorString(e));
   return 0;
 }
 
@@ -489,30 +623,23 @@ int launch_tc_gemm_head(il_handle* h, const GemmArgs& a, const float* head_w, co
   IL_CHECK(tc_head_fusable(h, a, head_n), "tc_gemm_head: not fusable");
   TcParams p{};
   p.g = a;
-  p.tiles_m = a.M / BM;
-  p.n_tiles = a.G * p.tiles_m;
   p.split = h->gemm_mode == IL_GEMM_TF32X3 ? 1 : 0;
   p.head_w = head_w; p.head_b = head_b; p.head_out = head_out; p.head_gs = head_gs; p.head_out_gs = head_out_gs; p.head_n = head_n; p.store_c = store_c;
-  const int grid = p.n_tiles < h->sm_count ? p.n_tiles : h->sm_count;
-  IL_LAUNCH(h, tc_gemm_kernel<4>, grid, THREADS, SMEM_BYTES, stream, p);
-  return 0;
+  return tc_launch<4>(h, p, stream);
 }
 
 int launch_tc_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   IL_CHECK(tc_gemm_eligible(a), "tc_gemm: shape/layout not eligible (M=%d N=%d K=%d)", a.M, a.N, a.K);
   TcParams p{};
   p.g = a;
-  p.tiles_m = a.M / BM;
-  p.n_tiles = a.G * p.tiles_m;
   p.split = h->gemm_mode == IL_GEMM_TF32X3 ? 1 : 0;
-  const int grid = p.n_tiles < h->sm_count ? p.n_tiles : h->sm_count;
   const bool plain = !a.bias && a.act < 0 && !a.mask;
   const bool bias_relu = a.bias && a.act == IL_ACT_RELU && !a.mask;
   const bool mask_relu = !a.bias && a.act < 0 && a.mask && a.mask_act == IL_ACT_RELU;
-  if (plain) IL_LAUNCH(h, tc_gemm_kernel<0>, grid, THREADS, SMEM_BYTES, stream, p);
-  else if (bias_relu) IL_LAUNCH(h, tc_gemm_kernel<1>, grid, THREADS, SMEM_BYTES, stream, p);
-  else if (mask_relu) IL_LAUNCH(h, tc_gemm_kernel<2>, grid, THREADS, SMEM_BYTES, stream, p);
-  else IL_LAUNCH(h, tc_gemm_kernel<3>, grid, THREADS, SMEM_BYTES, stream, p);
+  if (plain) IL_TRY(tc_launch<0>(h, p, stream));
+  else if (bias_relu) IL_TRY(tc_launch<1>(h, p, stream));
+  else if (mask_relu) IL_TRY(tc_launch<2>(h, p, stream));
+  else IL_TRY(tc_launch<3>(h, p, stream));
   if (a.colsum) {
     dim3 cg((a.M + 127) / 128, a.G);
     IL_LAUNCH(h, colsum_kernel, cg, 128, 0, stream, a.A, a.a_gs, a.a_gdiv, a.lda, a.K, a.M, a.colsum, a.colsum_gs);
