@@ -197,7 +197,7 @@ def run_b200(a):
   try:
     roof = measure_dense_gemm(tr, a)
   except Exception as e:  # never lose the headline number to the diagnostic
-    roof = dict(bound='tensor', achieved=None, peak=None, unit='TFLOP/s', frac=None, traffic=None, error=str(e))
+    roof = dict(bound='hbm', achieved=None, peak=None, unit='GB/s', frac=None, traffic=None, error=str(e))
 
   # ---- end-to-end arm: indices' uniforms drawn by numpy on the host and copied H2D every step, results read back every step
   e2e = None
@@ -237,6 +237,9 @@ def measure_dense_gemm(tr, a):
   torch.cuda.synchronize()
   ms, flops, n = C.c_double(), C.c_double(), C.c_int64()
   lib.il_profile_end(h, C.byref(ms), C.byref(flops), C.byref(n))
+  nbytes = C.c_double()
+  lib.il_profile_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+  lib.il_profile_bytes(h, C.byref(nbytes))
   tr.use_graphs = saved
   peaks = {}
   try:
@@ -244,19 +247,29 @@ def measure_dense_gemm(tr, a):
   except Exception:
     pass
   bf16 = peaks.get('bf16_tflops_sustained')
-  peak, src = (bf16, 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)') if bf16 else (1400.0, 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)')
-  achieved = flops.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else None
+  t_peak, t_src = (bf16, 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)') if bf16 else (1400.0, 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)')
+  hbm = peaks.get('hbm_gbs')
+  h_peak, h_src = (hbm, 'MEASURED_PEAKS.json hbm_gbs (copy bandwidth)') if hbm else (6500.0, 'fallback 6.5 TB/s (B200_PROFILING.md)')
+  if not ms.value > 0: return dict(bound='hbm', achieved=None, peak=h_peak, unit='GB/s', frac=None, traffic=None)
+  sec = ms.value * 1e-3
+  tflops = flops.value / sec / 1e12
+  gbs = nbytes.value / sec / 1e9
   traffic = None
   try:
     traffic = json.load(open(os.path.join(ROOT, 'profiles', 'dense_gemm_traffic.json'))).get('dram_bytes_per_launch')
   except Exception:
     pass
-  return dict(bound='tensor', kernel='grouped dense-layer GEMM (256x256x256 per net, fwd / dX / dW) of the SAC update', achieved=achieved, peak=peak, unit='TFLOP/s',
-              frac=(achieved / peak) if achieved else None, traffic=traffic, launches=int(n.value), avg_launch_ms=ms.value / max(n.value, 1),
-              algorithmic_flops_per_launch=flops.value / max(n.value, 1), peak_source=src, arithmetic=a.gemm_mode,
-              mma_tflops=(achieved * (3 if a.gemm_mode == 'tf32x3' else 1)) if achieved else None,
-              note='tf32x3 issues 3 tf32 MMAs per algorithmic product (fp32-level accuracy); dense tf32 peak is half the bf16 denominator, so the ceiling of this '
-                   'arithmetic is peak/6 algorithmic TFLOP/s' if a.gemm_mode == 'tf32x3' else None)
+  # Which roof binds: fp32 operands in and out give 2*256^3 flops per 768 KB, i.e. the minimum HBM time of a launch
+  # (bytes / peak bandwidth) is ~5x its minimum tensor time at the bf16 dense peak -> the kernel is HBM-bound.
+  t_hbm, t_tensor = nbytes.value / (h_peak * 1e9), flops.value / (t_peak * 1e12)
+  tensor = dict(achieved=tflops, peak=t_peak, unit='TFLOP/s', frac=tflops / t_peak, peak_source=t_src, arithmetic=a.gemm_mode,
+                mma_tflops=tflops * (3 if a.gemm_mode == 'tf32x3' else 1),
+                note='tf32x3 issues 3 tf32 MMAs per algorithmic product (fp32-level accuracy); dense tf32 peak is half the bf16 denominator, so the ceiling '
+                     'of this arithmetic is peak/6 algorithmic TFLOP/s' if a.gemm_mode == 'tf32x3' else None)
+  return dict(bound='hbm' if t_hbm >= t_tensor else 'tensor', kernel='tc_gemm_kernel: grouped dense-layer GEMM (256x256x256 per net, fwd(+head) / dX / dW) of the SAC update',
+              achieved=gbs, peak=h_peak, unit='GB/s', frac=gbs / h_peak, traffic=traffic, launches=int(n.value), avg_launch_ms=ms.value / max(n.value, 1),
+              algorithmic_bytes_per_launch=nbytes.value / max(n.value, 1), algorithmic_flops_per_launch=flops.value / max(n.value, 1), peak_source=h_src,
+              min_time_ratio_hbm_over_tensor=t_hbm / t_tensor, tensor=tensor)
 
 
 def main():

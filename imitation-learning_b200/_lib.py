@@ -87,6 +87,7 @@ SIGNATURES = {
   'il_row_layout': (C.c_int, [C.c_int, C.c_int, P(i32), P(i32)]),
   'il_profile_begin': (C.c_int, [vp]),
   'il_profile_end': (C.c_int, [vp, P(C.c_double), P(C.c_double), P(i64)]),
+  'il_profile_bytes': (C.c_int, [vp, P(C.c_double)]),
   'il_debug_gemm': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, i64, C.c_int, C.c_int, vp, i64, C.c_int, C.c_int, vp, i64, C.c_int, vp, i64, C.c_int, vp, i64, C.c_int,
                               C.c_int, vp, i64, vp]),
   'il_fill_normal': (C.c_int, [vp, vp, i64, u64, u64, vp, vp]),

@@ -35,6 +35,7 @@ extern "C" int il_create(int device, il_handle** out) {
   }
   h->launches = 0;
   h->profiling = 0;
+  h->profiled_bytes = 0.0;
   *out = h;
   return 0;
 }

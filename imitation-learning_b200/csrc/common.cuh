@@ -12,6 +12,7 @@
 struct ProfiledLaunch {
   cudaEvent_t start, stop;
   double flops;
+  double bytes;   // algorithmic (compulsory) HBM bytes of the launch: unique operand bytes read + output bytes written
 };
 struct il_handle {
   int device;
@@ -22,6 +23,7 @@ struct il_handle {
   long long launches;
   int profiling;                        // il_profile_begin/end: CUDA events around every dense-layer GEMM launch
   std::vector<ProfiledLaunch> profiled;
+  double profiled_bytes;                // summed by the last il_profile_end
 };
 
 extern thread_local char g_il_error[512];
@@ -178,6 +180,9 @@ struct GemmArgs {
   int M, N, K, G;
 };
 int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream);
+double gemm_algorithmic_bytes(const GemmArgs& a, bool stores_c);
+int profile_open(il_handle* h, ProfiledLaunch* pl, double flops, double bytes, cudaStream_t stream);
+int profile_close(il_handle* h, ProfiledLaunch* pl, cudaStream_t stream);
 
 // tcgen05 engine (tc_gemm.cu): dense M%128==0, N==256, K%32==0 problems when il_set_gemm_mode != IL_GEMM_FP32
 bool tc_gemm_eligible(const GemmArgs& a);

@@ -430,6 +430,29 @@ int gemm_init() {
   return 0;
 }
 
+// Compulsory HBM traffic of one grouped GEMM: every distinct operand element read once, every output written once.
+double gemm_algorithmic_bytes(const GemmArgs& a, bool stores_c) {
+  const double ga = (a.G + a.a_gdiv - 1) / a.a_gdiv, gb = (a.G + a.b_gdiv - 1) / a.b_gdiv;
+  double b = 4.0 * (ga * a.M * a.K + gb * a.K * a.N);
+  if (stores_c) b += 4.0 * a.G * (double)a.M * a.N;
+  if (a.mask) b += 4.0 * a.G * (double)a.M * a.N;
+  if (a.bias) b += 4.0 * a.G * a.N;
+  return b;
+}
+int profile_open(il_handle* h, ProfiledLaunch* pl, double flops, double bytes, cudaStream_t stream) {
+  IL_CUDA(cudaEventCreate(&pl->start));
+  IL_CUDA(cudaEventCreate(&pl->stop));
+  pl->flops = flops;
+  pl->bytes = bytes;
+  IL_CUDA(cudaEventRecord(pl->start, stream));
+  return 0;
+}
+int profile_close(il_handle* h, ProfiledLaunch* pl, cudaStream_t stream) {
+  IL_CUDA(cudaEventRecord(pl->stop, stream));
+  h->profiled.push_back(*pl);
+  return 0;
+}
+
 int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   IL_CHECK(a.M > 0 && a.N > 0 && a.K > 0 && a.G > 0, "gemm: empty problem M=%d N=%d K=%d G=%d", a.M, a.N, a.K, a.G);
   IL_CHECK(a.G <= 65535, "gemm: too many groups (%d)", a.G);
@@ -459,13 +482,9 @@ int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   auto run = [&]() { return tc ? launch_tc_gemm(h, a, stream) : launch_cfg<128, 128, 8, 8>(h, a, stream); };
   if (h->profiling && dense) {
     ProfiledLaunch pl;
-    IL_CUDA(cudaEventCreate(&pl.start));
-    IL_CUDA(cudaEventCreate(&pl.stop));
-    pl.flops = 2.0 * a.M * a.N * a.K * a.G;
-    IL_CUDA(cudaEventRecord(pl.start, stream));
+    IL_TRY(profile_open(h, &pl, 2.0 * a.M * a.N * a.K * a.G, gemm_algorithmic_bytes(a, true), stream));
     const int rc = run();
-    IL_CUDA(cudaEventRecord(pl.stop, stream));
-    h->profiled.push_back(pl);
+    IL_TRY(profile_close(h, &pl, stream));
     return rc;
   }
   return run();
@@ -496,16 +515,24 @@ extern "C" int il_profile_end(il_handle* h, double* total_ms, double* total_flop
   IL_CHECK(h && total_ms && total_flops && launches, "il_profile_end: null argument");
   h->profiling = 0;
   IL_CUDA(cudaDeviceSynchronize());
-  double ms = 0.0, fl = 0.0;
+  double ms = 0.0, fl = 0.0, by = 0.0;
   for (auto& pl : h->profiled) {
     float e = 0.f;
     IL_CUDA(cudaEventElapsedTime(&e, pl.start, pl.stop));
     ms += e;
     fl += pl.flops;
+    by += pl.bytes;
     cudaEventDestroy(pl.start);
     cudaEventDestroy(pl.stop);
   }
   *total_ms = ms; *total_flops = fl; *launches = (int64_t)h->profiled.size();
+  h->profiled_bytes = by;
   h->profiled.clear();
+  return 0;
+}
+
+extern "C" int il_profile_bytes(il_handle* h, double* total_bytes) {
+  IL_CHECK(h && total_bytes, "il_profile_bytes: null argument");
+  *total_bytes = h->profiled_bytes;
   return 0;
 }

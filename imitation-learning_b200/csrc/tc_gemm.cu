@@ -625,6 +625,13 @@ int launch_tc_gemm_head(il_handle* h, const GemmArgs& a, const float* head_w, co
   p.g = a;
   p.split = h->gemm_mode == IL_GEMM_TF32X3 ? 1 : 0;
   p.head_w = head_w; p.head_b = head_b; p.head_out = head_out; p.head_gs = head_gs; p.head_out_gs = head_out_gs; p.head_n = head_n; p.store_c = store_c;
+  if (h->profiling) {  // the fused layer-2 + head launches are dense-layer launches too (head flops / bytes are negligible)
+    ProfiledLaunch pl;
+    IL_TRY(profile_open(h, &pl, 2.0 * a.M * a.N * a.K * a.G, gemm_algorithmic_bytes(a, store_c != 0) + 4.0 * a.G * (double)a.M * head_n, stream));
+    const int rc = tc_launch<4>(h, p, stream);
+    IL_TRY(profile_close(h, &pl, stream));
+    return rc;
+  }
   return tc_launch<4>(h, p, stream);
 }
 

@@ -87,9 +87,11 @@ int         il_row_layout(int S, int A, int32_t* offsets8, int32_t* row_len); /*
 
 /* Measurement aid for bench.py: between begin/end (eager launches, no graph capture) every dense hidden-layer GEMM launch
  * is bracketed by CUDA events on its own stream; end() synchronises and returns the summed device time, the summed
- * algorithmic FLOPs (2 M N K G per launch) and the number of launches. */
+ * algorithmic FLOPs (2 M N K G per launch) and the number of launches; il_profile_bytes then returns the summed
+ * algorithmic HBM bytes of those launches (each distinct operand element read once, each output element written once). */
 int il_profile_begin(il_handle* h);
 int il_profile_end(il_handle* h, double* total_ms, double* total_flops, int64_t* launches);
+int il_profile_bytes(il_handle* h, double* total_bytes);
 
 /* Test / diagnostics entry: one grouped GEMM C[g] = A[g] B[g] with the fused epilogues (bias, activation act >= 0,
  * activation-derivative mask, bias-gradient column sums), dispatched exactly like the MLP programs dispatch it
