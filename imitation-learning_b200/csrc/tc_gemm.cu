@@ -1,21 +1,26 @@
 // tcgen05 engine for the dense H x H layers of the replica-batched MLPs (sm_100a only).
 //
 //   C[g] (M x N) = A[g] (M x K) * B[g] (K x N), fp32 in / fp32 out, tensor-core arithmetic:
-//     IL_GEMM_TF32X3 : each operand is split x = hi + lo (hi = rna_tf32(x), lo = rna_tf32(x - hi)) and the product
-//                      is hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM — fp32-level accuracy (error ~2^-21
-//                      per product, the dropped lo*lo term) at 3 MMAs per product ("3xTF32").
+//     IL_GEMM_TF32X3 : each operand is split x = hi + lo (hi = trunc_tf32(x), the top 19 bits the tensor core reads
+//                      anyway; lo = x - hi, exact in fp32) and the product is lo*hi + hi*lo + hi*hi with fp32
+//                      accumulation in TMEM — fp32-level accuracy (error ~2^-21 per product, the dropped lo*lo term)
+//                      at 3 MMAs per product ("3xTF32").
 //     IL_GEMM_TF32   : hi*hi only (10-bit mantissa operands).
 //
-// Structure (one persistent CTA per SM, 13 warps):
-//   warps 5..12  producers : global (fp32, either operand layout) -> registers -> hi/lo split -> shared memory in
-//                            the canonical K-major SWIZZLE_128B UMMA layout (MN-major sources are transposed in
-//                            registers with quad shuffles), fence.proxy.async, mbarrier arrive.     [2 stages x 96 KB]
-//   warp  4      MMA issuer: one elected thread issues tcgen05.mma.kind::tf32 (M128 x N256 x K8) on shared-memory
-//                            descriptors, accumulating into TMEM; tcgen05.commit releases stages / publishes tiles.
-//   warps 0..3   epilogue  : tcgen05.ld (32 lanes x 32 columns) -> bias / activation / activation-derivative mask
-//                            -> transposed through shared memory -> coalesced 128-bit global stores.
+// Structure (persistent, one CTA per SM, 13 warps; CG = 2: the two CTAs of a 2-CTA cluster share one 256 x 256 tile):
+//   warps 5..12  producers : cp.async (16 B, L2 only) copies raw fp32 chunks from either operand layout straight into the
+//                            canonical UMMA shared-memory layout of a RAW ring slot (K-major SWIZZLE_64B rows of 16
+//                            floats, or MN-major SWIZZLE_128B_BASE32B — no transposes); when the copies of a k-block
+//                            have landed the same thread derives the LO tile of its own chunks into a short second
+//                            ring, fence.proxy.async, mbarrier arrive (on the leader CTA's barrier in pair mode).
+//   warp  4      MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma.kind::tf32 (M128 x N256 x K8, or
+//                            cta_group::2 M256 x N256 x K8 for the pair) on shared-memory descriptors, accumulating in
+//                            TMEM; tcgen05.commit (multicast to both CTAs in pair mode) releases slots / publishes tiles.
+//   warps 0..3   epilogue  : tcgen05.ld (32 lanes x 32 columns) -> bias / activation / activation-derivative mask /
+//                            fused final linear layer -> transposed through shared memory -> coalesced 128-bit stores.
 //   TMEM holds two 128 x 256 fp32 accumulators (512 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
-// A TMA path is not used because every operand needs the hi/lo split (a CUDA-core pass over the tile) anyway.
+// A TMA path is not used because every operand needs the hi/lo split (a CUDA-core pass over the tile) anyway and cp.async
+// already lands the data in its final layout.
 #include "common.cuh"
 #include <cstdio>
 #include <cstdlib>
