@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(256, 2) gemm_grouped_kernel(const GemmArgs p) 
 // the last layer (K = head width). These products are pure output bandwidth, so the tile loop of the general kernel is
 // replaced by: B (K x 256) and 32 rows of A in shared memory, 8 x 4 outputs per thread, 128-bit coalesced stores.
 constexpr int TK_MAXK = 32, TK_ROWS = 32, TK_ITERS = 4, TK_COLS = 256, TK_LDA = TK_MAXK + 4;  // a CTA covers 4 x 32 rows
+// (8 x 32 rows per CTA with a coalesced, bank-spread staging of the [N, K] weights measured 1.4 % slower on the whole step.)
 template <bool B_KMAJOR>
 __global__ void __launch_bounds__(256, 3) gemm_thin_k_kernel(const GemmArgs p) {
   __shared__ __align__(16) float Bs[TK_MAXK][TK_COLS];
@@ -359,10 +360,19 @@ __global__ void __launch_bounds__(256) gemm_stream_tn_kernel(const GemmArgs p) {
   if (w < W) {
     const float* tp = T + w;
     int k = 0;
+    float tn[8];  // software pipeline: the next 8 rows are in flight while the current 8 are consumed (the loop is latency-bound)
+    if (K >= 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) tn[u] = __ldg(tp + (int64_t)u * ldt);
+    }
     for (; k + 8 <= K; k += 8) {
       float t[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) t[u] = __ldg(tp + (int64_t)(k + u) * ldt);
+      for (int u = 0; u < 8; ++u) t[u] = tn[u];
+      if (k + 16 <= K) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) tn[u] = __ldg(tp + (int64_t)(k + 8 + u) * ldt);
+      }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         tsum += t[u];
