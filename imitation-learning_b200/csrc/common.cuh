@@ -19,6 +19,7 @@ struct il_handle {
   int sm_count;
   int gemm_mode;
   int tc_pair_groups;                   // co-resident 2-CTA clusters of the tcgen05 pair kernel (0 = not queried yet)
+  int thin_hoist;                       // K-thin kernel: hoisted mask loads for the masked (dX) variant (IL_THIN_HOIST=0/1)
   int tc_pairs;                         // tcgen05 engine: use CTA pairs (cta_group::2) when rows are a multiple of 256 (IL_TC_PAIRS=0 disables)
   long long launches;
   int profiling;                        // il_profile_begin/end: CUDA events around every dense-layer GEMM launch

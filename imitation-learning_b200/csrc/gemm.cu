@@ -247,8 +247,10 @@ __global__ void __launch_bounds__(256, 2) gemm_grouped_kernel(const GemmArgs p) 
 // replaced by: B (K x 256) and 32 rows of A in shared memory, 8 x 4 outputs per thread, 128-bit coalesced stores.
 constexpr int TK_MAXK = 32, TK_ROWS = 32, TK_ITERS = 4, TK_COLS = 256, TK_LDA = TK_MAXK + 4;  // a CTA covers 4 x 32 rows
 // (8 x 32 rows per CTA with a coalesced, bank-spread staging of the [N, K] weights measured 1.4 % slower on the whole step.)
-template <bool B_KMAJOR>
-__global__ void __launch_bounds__(256, 3) gemm_thin_k_kernel(const GemmArgs p) {
+// HOIST_MASK: the activation-derivative mask rows of an iteration are loaded before the FMA loop (8 x 128-bit loads in
+// flight per thread, 2 CTAs/SM) instead of one by one inside the store loop (the masked variant is latency-bound).
+template <bool B_KMAJOR, bool HOIST_MASK>
+__global__ void __launch_bounds__(256, HOIST_MASK ? 2 : 3) gemm_thin_k_kernel(const GemmArgs p) {
   __shared__ __align__(16) float Bs[TK_MAXK][TK_COLS];
   __shared__ __align__(16) float As[TK_ROWS][TK_LDA];  // K zero-padded to a multiple of 4 so rows are read as float4
   const int tid = threadIdx.x, g = blockIdx.z, n0 = blockIdx.x * TK_COLS;
@@ -292,6 +294,14 @@ __global__ void __launch_bounds__(256, 3) gemm_thin_k_kernel(const GemmArgs p) {
     __syncthreads();
     if (it + 1 < TK_ITERS && m0 + TK_ROWS < M) fetch_a(m0 + TK_ROWS);
     if (n >= ncols) continue;
+    float4 mvh[HOIST_MASK ? 8 : 1];
+    if (HOIST_MASK) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + tr + 4 * i;
+        mvh[i] = m < M ? __ldg(reinterpret_cast<const float4*>(mask + (int64_t)m * p.ldmask + n0 + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     float acc[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
@@ -314,7 +324,7 @@ __global__ void __launch_bounds__(256, 3) gemm_thin_k_kernel(const GemmArgs p) {
       float4 v = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
       if (p.act >= 0) { v.x = act_apply(v.x, p.act); v.y = act_apply(v.y, p.act); v.z = act_apply(v.z, p.act); v.w = act_apply(v.w, p.act); }
       if (mask) {
-        const float4 mv = __ldg(reinterpret_cast<const float4*>(mask + (int64_t)m * p.ldmask + n0 + n));
+        const float4 mv = HOIST_MASK ? mvh[i] : __ldg(reinterpret_cast<const float4*>(mask + (int64_t)m * p.ldmask + n0 + n));
         v.x *= act_grad_from_output(mv.x, p.mask_act); v.y *= act_grad_from_output(mv.y, p.mask_act);
         v.z *= act_grad_from_output(mv.z, p.mask_act); v.w *= act_grad_from_output(mv.w, p.mask_act);
       }
@@ -480,8 +490,13 @@ int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   }
   if (a.M > 16 && thin_k_eligible(a)) {
     dim3 grid((a.N + TK_COLS - 1) / TK_COLS, (a.M + TK_ROWS * TK_ITERS - 1) / (TK_ROWS * TK_ITERS), a.G);
-    if (a.b_kmajor) IL_LAUNCH(h, gemm_thin_k_kernel<true>, grid, 256, 0, stream, a);
-    else IL_LAUNCH(h, gemm_thin_k_kernel<false>, grid, 256, 0, stream, a);
+    if (a.mask && h->thin_hoist) {
+      if (a.b_kmajor) IL_LAUNCH(h, (gemm_thin_k_kernel<true, true>), grid, 256, 0, stream, a);
+      else IL_LAUNCH(h, (gemm_thin_k_kernel<false, true>), grid, 256, 0, stream, a);
+      return 0;
+    }
+    if (a.b_kmajor) IL_LAUNCH(h, (gemm_thin_k_kernel<true, false>), grid, 256, 0, stream, a);
+    else IL_LAUNCH(h, (gemm_thin_k_kernel<false, false>), grid, 256, 0, stream, a);
     return 0;
   }
   if (a.M <= 16) return launch_cfg<16, 128, 1, 8>(h, a, stream);
