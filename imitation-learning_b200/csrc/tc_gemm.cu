@@ -157,11 +157,6 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
         : "memory");
 }
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO >> 4 at bit 16 | SBO >> 4 at bit 32 |
 // version 1 at bit 46 | layout type at bit 61 (2 = SWIZZLE_128B for K-major, 1 = SWIZZLE_128B_BASE32B for MN-major tf32).
 //   K-major : LBO unused (1), SBO = 1024 (next 8-row atom).   MN-major: LBO = 512 (next 32-row atom along MN),
@@ -198,20 +193,9 @@ struct TcParams {
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
-// hi = x rounded to tf32 (round-half-away on the 13 dropped bits, two integer ops); lo = x - hi is exact in fp32 and
-// is stored unrounded: the tensor core reads only the top 19 bits of each 32-bit tf32 container.
-__device__ __forceinline__ void store_split(uint32_t hi_addr, uint32_t lo_addr, float4 v, bool split) {
-  const uint32_t hx = (__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u, hy = (__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u;
-  const uint32_t hz = (__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u, hw = (__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u;
-  sts128(hi_addr, hx, hy, hz, hw);
-  if (split)
-    sts128(lo_addr, __float_as_uint(v.x - __uint_as_float(hx)), __float_as_uint(v.y - __uint_as_float(hy)), __float_as_uint(v.z - __uint_as_float(hz)),
-           __float_as_uint(v.w - __uint_as_float(hw)));
-}
-
-// Per-thread, kernel-invariant addressing of one operand tile (ROWS x 32 k floats per stage):
-//  K-major source  (element (r, k) at src[r * ld + k]) -> canonical K-major SWIZZLE_128B tile: row r = 128 B, 8-row atoms
-//                   1024 B apart (SBO), 16-byte chunk c stored at c ^ (r % 8).
+// Per-thread, kernel-invariant addressing of one k-block (16 floats of k) of the operand tiles:
+//  K-major source  (element (r, k) at src[r * ld + k]) -> canonical K-major SWIZZLE_64B tile: row r = 64 B, 8-row atoms
+//                   512 B apart (SBO), 16-byte chunk c stored at c ^ ((r / 2) % 4).
 //  MN-major source (element (r, k) at src[k * ld + r]) -> no transpose: the canonical MN-major layout for 32-bit
 //                   operands, SWIZZLE_128B_BASE32B (cute Layout_MN_SW128_32B_Atom, the only MN-major layout tf32 has):
 //                   atom = 4 k-rows x 128 B (32 consecutive r), 32-byte chunk q of a row stored at q ^ (k % 4);
