@@ -33,6 +33,14 @@ CASES: Dict[str, dict] = {
   'gail_mixup': dict(kind='gail', S=12, A=3, H=64, B=64, steps=2, seed=34, spectral_norm=True, grad_penalty=0.0, entropy_bonus=0.0, loss='Mixup', lr=1e-3, wd=0.0, reward='AIRL'),
   'gail_ant': dict(kind='gail', S=112, A=8, H=64, B=96, steps=2, seed=35, spectral_norm=True, grad_penalty=1.0, entropy_bonus=0.05, loss='BCE', lr=3e-5, wd=10.0, reward='AIRL'),
   'gmmil_ant': dict(kind='gmmil', S=112, A=8, B=300, seed=43),
+  # SURVEY §8f row 3 variants (oracle pinned; CUDA path is next-round work): shaping f = g(s,a) + (1-t)(gamma h(s') - h(s)) with a
+  # linear g (models.py:157-160), subtract_log_policy (:175), deeper / tanh / sigmoid / state-only discriminators
+  'gailx_shaping': dict(kind='gailx', cuda=False, S=12, A=3, H=32, depth=1, activation='relu', B=48, steps=2, seed=36, spectral_norm=True, grad_penalty=1.0, entropy_bonus=0.05, loss='BCE',
+                        lr=1e-3, wd=0.1, reward='AIRL', reward_shaping=True, subtract_log_policy=True, state_only=False),
+  'gailx_depth2_tanh': dict(kind='gailx', cuda=False, S=12, A=3, H=32, depth=2, activation='tanh', B=48, steps=2, seed=37, spectral_norm=True, grad_penalty=1.0, entropy_bonus=0.0, loss='BCE',
+                            lr=1e-3, wd=0.1, reward='GAIL', reward_shaping=False, subtract_log_policy=False, state_only=False),
+  'gailx_state_only_sigmoid': dict(kind='gailx', cuda=False, S=18, A=6, H=32, depth=2, activation='sigmoid', B=48, steps=2, seed=38, spectral_norm=False, grad_penalty=0.0, entropy_bonus=0.1, loss='Mixup',
+                                   lr=1e-3, wd=0.0, reward='FAIRL', reward_shaping=True, subtract_log_policy=False, state_only=True),
   'gmmil_hopper': dict(kind='gmmil', S=12, A=3, B=64, seed=41),
   'gmmil_halfcheetah': dict(kind='gmmil', S=18, A=6, B=256, seed=42),
   'pwil_small': dict(kind='pwil', S=12, A=3, N=150, T=40, steps=100, seed=51),
@@ -105,6 +113,26 @@ def make_inputs(name: str, seed_offset: int = 0) -> Dict[str, np.ndarray]:
       for l, (h, w) in enumerate(((H, S + A), (1, H))):
         inp[f'u_{l}'] = rs.standard_normal(h).astype(np.float32)
         inp[f'v_{l}'] = rs.standard_normal(w).astype(np.float32)
+  elif k == 'gailx':
+    S, A, H = c['S'], c['A'], c['H']
+    din = S if c['state_only'] else S + A
+    g_sizes, h_sizes = ([din, 1], [S] + [H] * c['depth'] + [1]) if c['reward_shaping'] else ([din] + [H] * c['depth'] + [1], None)
+    for i, w in enumerate(_mlp_weights(rs, g_sizes, scale=1.5)): inp[f'g_{i}'] = w
+    if h_sizes is not None:
+      for i, w in enumerate(_mlp_weights(rs, h_sizes, scale=1.5)): inp[f'h_{i}'] = w
+    if c['subtract_log_policy']:
+      for i, w in enumerate(_mlp_weights(rs, [S, 32, 32, 2 * A])): inp[f'actor_{i}'] = w
+    for s in range(c['steps']):
+      for key, v in _batch(rs, c['B'], S, A).items(): inp[f'p{s}_{key}'] = v
+      for key, v in _batch(rs, c['B'], S, A).items(): inp[f'e{s}_{key}'] = v
+      inp[f's{s}_eps_gp'] = rs.uniform(size=c['B']).astype(np.float32)
+      inp[f's{s}_eps_mix'] = rs.beta(1.0, 1.0, size=c['B']).astype(np.float32)
+    if c['spectral_norm']:
+      for net, sizes in (('g', g_sizes), ('h', h_sizes)):
+        if sizes is None: continue
+        for l in range(len(sizes) - 1):
+          inp[f'{net}u_{l}'] = rs.standard_normal(sizes[l + 1]).astype(np.float32)
+          inp[f'{net}v_{l}'] = rs.standard_normal(sizes[l]).astype(np.float32)
   elif k == 'gmmil':
     for pre in ('p', 'e'):
       for key, v in _batch(rs, c['B'], c['S'], c['A']).items(): inp[f'{pre}_{key}'] = v
@@ -190,6 +218,29 @@ def run_port(name: str, inp: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
       out[f'adam_m_{i}'], out[f'adam_v_{i}'] = _np(opt.state[p]['exp_avg']), _np(opt.state[p]['exp_avg_sq'])
     if sn is not None:
       for l, (u, v) in enumerate(disc.g_sn): out[f'u_{l}'], out[f'v_{l}'] = _np(u), _np(v)
+  elif k == 'gailx':
+    ng, nh = sum(key.startswith('g_') for key in inp), sum(key.startswith('h_') for key in inp)
+    g, h = [_t(inp[f'g_{i}']) for i in range(ng)], ([_t(inp[f'h_{i}']) for i in range(nh)] if nh else None)
+    sn = lambda net, n: [(port._l2_normalise(_t(inp[f'{net}u_{l}'])), port._l2_normalise(_t(inp[f'{net}v_{l}']))) for l in range(n // 2)] if c['spectral_norm'] else None
+    actor = [_t(inp[f'actor_{i}']) for i in range(6)] if c['subtract_log_policy'] else None
+    disc = port.GailDiscriminator(g, sn('g', ng), discount=0.97, activation=c['activation'], reward_function=c['reward'], state_only=c['state_only'],
+                                  subtract_log_policy=c['subtract_log_policy'], h=h, h_sn=sn('h', nh) if nh else None)
+    opt = torch.optim.AdamW(disc.parameters(), lr=c['lr'], weight_decay=c['wd'])
+    for s in range(c['steps']):
+      pol, exp = _batch_from(inp, f'p{s}_'), _batch_from(inp, f'e{s}_')
+      port.gail_update(disc, opt, pol, exp, _t(inp[f's{s}_eps_gp']), loss_function=c['loss'], grad_penalty=c['grad_penalty'], entropy_bonus=c['entropy_bonus'],
+                       eps_mixup=_t(inp[f's{s}_eps_mix']), actor=actor)
+      with torch.no_grad():
+        lp = port.actor_log_prob(actor, pol['states'], pol['actions']) if actor is not None else None
+        out[f's{s}_reward'] = _np(disc.predict_reward(pol['states'], pol['actions'], pol['next_states'], pol['terminals'], lp))
+        out[f's{s}_logits'] = _np(disc.forward(pol['states'], pol['actions'], pol['next_states'], pol['terminals'], lp))
+    for net, params, bufs in (('g', disc.g, disc.g_sn), ('h', disc.h, disc.h_sn)):
+      if params is None: continue
+      for i, p in enumerate(params):
+        out[f'{net}_{i}'] = _np(p)
+        out[f'adam_{net}_m_{i}'], out[f'adam_{net}_v_{i}'] = _np(opt.state[p]['exp_avg']), _np(opt.state[p]['exp_avg_sq'])
+      if bufs is not None:
+        for l, (u, v) in enumerate(bufs): out[f'{net}u_{l}'], out[f'{net}v_{l}'] = _np(u), _np(v)
   elif k == 'gmmil':
     d = port.GmmilDiscriminator()
     p, e, p2 = _batch_from(inp, 'p_'), _batch_from(inp, 'e_'), _batch_from(inp, 'p2_')
@@ -338,6 +389,51 @@ def run_reference(name: str, inp: Dict[str, np.ndarray]) -> Dict[str, np.ndarray
       out[f'adam_m_{i}'], out[f'adam_v_{i}'] = _np(opt.state[p]['exp_avg']), _np(opt.state[p]['exp_avg_sq'])
     if c['spectral_norm']:
       for l, lin in enumerate(lins): out[f'u_{l}'], out[f'v_{l}'] = _np(lin.parametrizations.weight[0]._u), _np(lin.parametrizations.weight[0]._v)
+  elif k == 'gailx':
+    S, A, H = c['S'], c['A'], c['H']
+    icfg = DC(state_only=c['state_only'], spectral_norm=c['spectral_norm'], loss_function=c['loss'], grad_penalty=c['grad_penalty'], mixup_alpha=1, entropy_bonus=c['entropy_bonus'],
+              pos_class_prior=0.7, nonnegative_margin=float('inf'),
+              discriminator=DC(hidden_size=H, depth=c['depth'], activation=c['activation'], input_dropout=0.5, dropout=0.75, reward_shaping=c['reward_shaping'],
+                               subtract_log_policy=c['subtract_log_policy'], reward_function=c['reward']))
+    disc = ref.models.GAILDiscriminator(S, A, icfg, 0.97)
+    actor = None
+    if c['subtract_log_policy']:
+      actor = ref.models.SoftActor(S, A, DC(hidden_size=32, depth=2, activation='relu'))
+      _load_mlp(actor.actor, [inp[f'actor_{i}'] for i in range(6)])
+    nets, plists = {}, {}
+    for net in ('g', 'h'):
+      mod = getattr(disc, net, None)
+      if mod is None: continue
+      lins = [mod] if isinstance(mod, torch.nn.Linear) else [m for m in mod if isinstance(m, torch.nn.Linear)]
+      nets[net], plists[net] = lins, []
+      with torch.no_grad():
+        for l, lin in enumerate(lins):
+          if c['spectral_norm']:
+            lin.parametrizations.weight.original.copy_(_t(inp[f'{net}_{2 * l}']))
+            lin.parametrizations.weight[0]._u.copy_(port._l2_normalise(_t(inp[f'{net}u_{l}'])))
+            lin.parametrizations.weight[0]._v.copy_(port._l2_normalise(_t(inp[f'{net}v_{l}'])))
+          else:
+            lin.weight.copy_(_t(inp[f'{net}_{2 * l}']))
+          lin.bias.copy_(_t(inp[f'{net}_{2 * l + 1}']))
+          plists[net] += [lin.parametrizations.weight.original if c['spectral_norm'] else lin.weight, lin.bias]
+    opt = torch.optim.AdamW(disc.parameters(), lr=c['lr'], weight_decay=c['wd'])
+    disc.eval()
+    for s in range(c['steps']):
+      pol, exp = _batch_from(inp, f'p{s}_'), _batch_from(inp, f'e{s}_')
+      disc.train()
+      with injected_noise([], [_t(inp[f's{s}_eps_gp'])], [_t(inp[f's{s}_eps_mix'])]):
+        ref.training.adversarial_imitation_update(actor, disc, pol, exp, opt, icfg)
+      disc.eval()
+      with torch.inference_mode():
+        gi = ref.models.make_gail_input(pol['states'], pol['actions'], pol['next_states'], pol['terminals'], actor, c['reward_shaping'], c['subtract_log_policy'])
+        out[f's{s}_reward'] = _np(disc.predict_reward(**gi))
+        out[f's{s}_logits'] = _np(disc(**gi))
+    for net, plist in plists.items():
+      for i, p in enumerate(plist):
+        out[f'{net}_{i}'] = _np(p)
+        out[f'adam_{net}_m_{i}'], out[f'adam_{net}_v_{i}'] = _np(opt.state[p]['exp_avg']), _np(opt.state[p]['exp_avg_sq'])
+      if c['spectral_norm']:
+        for l, lin in enumerate(nets[net]): out[f'{net}u_{l}'], out[f'{net}v_{l}'] = _np(lin.parametrizations.weight[0]._u), _np(lin.parametrizations.weight[0]._v)
   elif k == 'gmmil':
     d = ref.models.GMMILDiscriminator(c['S'], c['A'], DC(state_only=False))
     p, e, p2 = _batch_from(inp, 'p_'), _batch_from(inp, 'e_'), _batch_from(inp, 'p2_')

@@ -21,7 +21,8 @@ def _tol(name):
   return (RTOL, ATOL)
 
 
-@pytest.mark.parametrize('name', list(cases.CASES))
+# cases marked cuda=False pin the oracle for rows that are not on the accelerated path yet; the product raises for them
+@pytest.mark.parametrize('name', [n for n, c in cases.CASES.items() if c.get('cuda', True)])
 def test_cuda_matches_reference_fixture(name):
   from cuda_cases import run_cuda
   out = run_cuda(name, [cases.make_inputs(name)])[0]

@@ -17,7 +17,8 @@ def test_port_matches_golden(name):
 
 
 @pytest.mark.skipif(not refstub.available(), reason='reference tree not present (GPU box)')
-@pytest.mark.parametrize('name', ['actor_small', 'sac_small', 'bc_small', 'gail_default', 'gail_mixup', 'gmmil_hopper', 'pwil_small', 'replay_ring'])
+@pytest.mark.parametrize('name', ['actor_small', 'sac_small', 'bc_small', 'gail_default', 'gail_mixup', 'gmmil_hopper', 'pwil_small', 'replay_ring',
+                                  'gailx_shaping', 'gailx_depth2_tanh', 'gailx_state_only_sigmoid'])
 def test_port_matches_live_reference(name):
   inp = cases.make_inputs(name)
   ref = cases.run_reference(name, inp)
