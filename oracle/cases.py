@@ -41,6 +41,10 @@ CASES: Dict[str, dict] = {
                             lr=1e-3, wd=0.1, reward='GAIL', reward_shaping=False, subtract_log_policy=False, state_only=False),
   'gailx_state_only_sigmoid': dict(kind='gailx', cuda=False, S=18, A=6, H=32, depth=2, activation='sigmoid', B=48, steps=2, seed=38, spectral_norm=False, grad_penalty=0.0, entropy_bonus=0.1, loss='Mixup',
                                    lr=1e-3, wd=0.0, reward='FAIRL', reward_shaping=True, subtract_log_policy=False, state_only=True),
+  # expert-data ingest (environments.py:63-125) on a D4RL-shaped raw buffer — host logic, no CUDA
+  'ingest_absorbing_sub4': dict(kind='ingest', cuda=False, obs=11, A=3, N=900, trajectories=4, subsample=4, absorbing=True, seed=71),
+  'ingest_plain_all': dict(kind='ingest', cuda=False, obs=17, A=6, N=500, trajectories=0, subsample=1, absorbing=False, seed=72),
+  'ingest_absorbing_sub1': dict(kind='ingest', cuda=False, obs=11, A=3, N=700, trajectories=3, subsample=1, absorbing=True, seed=73),
   'gmmil_hopper': dict(kind='gmmil', S=12, A=3, B=64, seed=41),
   'gmmil_halfcheetah': dict(kind='gmmil', S=18, A=6, B=256, seed=42),
   'pwil_small': dict(kind='pwil', S=12, A=3, N=150, T=40, steps=100, seed=51),
@@ -133,6 +137,17 @@ def make_inputs(name: str, seed_offset: int = 0) -> Dict[str, np.ndarray]:
         for l in range(len(sizes) - 1):
           inp[f'{net}u_{l}'] = rs.standard_normal(sizes[l + 1]).astype(np.float32)
           inp[f'{net}v_{l}'] = rs.standard_normal(sizes[l]).astype(np.float32)
+  elif k == 'ingest':
+    N = c['N']
+    inp['observations'] = rs.standard_normal((N, c['obs'])).astype(np.float32)
+    inp['next_observations'] = rs.standard_normal((N, c['obs'])).astype(np.float32)
+    inp['actions'] = np.tanh(rs.standard_normal((N, c['A']))).astype(np.float32)
+    inp['rewards'] = rs.standard_normal(N).astype(np.float32)
+    ends = np.sort(rs.choice(np.arange(20, N - 1), size=6, replace=False))  # 7 episodes of ragged length; the last one ends at N - 1
+    terminals, timeouts = np.zeros(N, np.float32), np.zeros(N, np.float32)
+    for j, e in enumerate(list(ends) + [N - 1]): (timeouts if j % 3 == 1 else terminals)[e] = 1  # episodes 1, 4 end by time limit
+    inp['terminals'], inp['timeouts'] = terminals, timeouts
+    inp['np_seed'] = np.int64([c['seed'] + 7])
   elif k == 'gmmil':
     for pre in ('p', 'e'):
       for key, v in _batch(rs, c['B'], c['S'], c['A']).items(): inp[f'{pre}_{key}'] = v
@@ -241,6 +256,11 @@ def run_port(name: str, inp: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
         out[f'adam_{net}_m_{i}'], out[f'adam_{net}_v_{i}'] = _np(opt.state[p]['exp_avg']), _np(opt.state[p]['exp_avg_sq'])
       if bufs is not None:
         for l, (u, v) in enumerate(bufs): out[f'{net}u_{l}'], out[f'{net}v_{l}'] = _np(u), _np(v)
+  elif k == 'ingest':
+    raw = {key: _t(inp[key]) for key in ('observations', 'next_observations', 'actions', 'terminals', 'timeouts')}
+    tr = port.build_expert_transitions(raw, c['trajectories'], c['subsample'], c['absorbing'], rng=np.random.RandomState(int(inp['np_seed'][0])))
+    for key in ('states', 'actions', 'next_states', 'terminals', 'timeouts', 'weights', 'rewards'): out[key] = _np(tr[key])
+    out['meta'] = np.int64([tr['num_trajectories'], tr['states'].shape[0]])
   elif k == 'gmmil':
     d = port.GmmilDiscriminator()
     p, e, p2 = _batch_from(inp, 'p_'), _batch_from(inp, 'e_'), _batch_from(inp, 'p2_')
@@ -434,6 +454,19 @@ def run_reference(name: str, inp: Dict[str, np.ndarray]) -> Dict[str, np.ndarray
         out[f'adam_{net}_m_{i}'], out[f'adam_{net}_v_{i}'] = _np(opt.state[p]['exp_avg']), _np(opt.state[p]['exp_avg_sq'])
       if c['spectral_norm']:
         for l, lin in enumerate(nets[net]): out[f'{net}u_{l}'], out[f'{net}v_{l}'] = _np(lin.parametrizations.weight[0]._u), _np(lin.parametrizations.weight[0]._v)
+  elif k == 'ingest':
+    import types
+    D4RLEnv = ref.evaluation.D4RLEnv  # evaluation.py:6 imports it from environments.py (gym / d4rl stubbed)
+    # copies: get_dataset rewrites terminal flags through views of the dataset arrays (environments.py:100)
+    fake = types.SimpleNamespace(dataset={key: inp[key].copy() for key in ('observations', 'next_observations', 'actions', 'rewards', 'terminals', 'timeouts')}, absorbing=c['absorbing'])
+    state = np.random.get_state()
+    np.random.seed(int(inp['np_seed'][0]))  # environments.py:113 draws the subsampling offsets from the global numpy stream
+    try:
+      mem = D4RLEnv.get_dataset(fake, trajectories=c['trajectories'], subsample=c['subsample'])
+    finally:
+      np.random.set_state(state)
+    for key in ('states', 'actions', 'next_states', 'terminals', 'timeouts', 'weights', 'rewards'): out[key] = _np(getattr(mem, key))
+    out['meta'] = np.int64([mem.num_trajectories, mem.states.shape[0]])
   elif k == 'gmmil':
     d = ref.models.GMMILDiscriminator(c['S'], c['A'], DC(state_only=False))
     p, e, p2 = _batch_from(inp, 'p_'), _batch_from(inp, 'e_'), _batch_from(inp, 'p2_')
