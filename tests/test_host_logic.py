@@ -106,3 +106,41 @@ def test_conf_tree_carries_the_reference_values():
       with open(os.path.join(ROOT, 'conf', 'optimised_hyperparameters', name)) as f: mine = _flat(yaml.safe_load(f) or {})
       theirs = _flat({k: v for k, v in (_reference_conf('optimised_hyperparameters', name) or {}).items() if k not in ('defaults', 'hydra')})
       assert mine == theirs, (name, set(mine.items()) ^ set(theirs.items()))
+
+
+@pytest.mark.skipif(not refstub.available(), reason='reference tree not present (GPU box)')
+def test_parameter_initialisation_consumes_the_reference_rng_stream():
+  """train.py:51-66 seeds torch once and builds actor, then the twin critic; replica r of this build must initialise
+  like a reference run with seed + r (net.ReplicaRNG + net.init_fcnn_params, CPU side of ReplicaMLP)."""
+  from il_b200 import net
+  ref = refstub.load()
+  S, A, H = 12, 3, 256
+  mc = ref.DictConfig(hidden_size=H, depth=2, activation='relu')
+  rng = net.ReplicaRNG(seed=7, replicas=3)
+  for r in range(3):
+    torch.manual_seed(7 + r)
+    actor, critic = ref.models.SoftActor(S, A, mc), ref.models.TwinCritic(S, A, mc)
+    with rng.replica(r):
+      mine_actor = net.init_fcnn_params([S, H, H, 2 * A], 'relu')
+      mine_c1, mine_c2 = net.init_fcnn_params([S + A, H, H, 1], 'relu'), net.init_fcnn_params([S + A, H, H, 1], 'relu')
+    for mine, theirs in ((mine_actor, actor.actor), (mine_c1, critic.critic_1.critic), (mine_c2, critic.critic_2.critic)):
+      lins = [m for m in theirs if isinstance(m, torch.nn.Linear)]
+      assert len(lins) * 2 == len(mine)
+      for l, lin in enumerate(lins):
+        assert torch.equal(mine[2 * l], lin.weight.detach()) and torch.equal(mine[2 * l + 1], lin.bias.detach())
+  # the global stream is left untouched by the per-replica streams
+  torch.manual_seed(123)
+  a = torch.rand(3)
+  torch.manual_seed(123)
+  with rng.replica(0): net.init_fcnn_params([4, 4], 'relu')
+  assert torch.equal(a, torch.rand(3))
+
+
+def test_shard_and_statistics_helpers():
+  from il_b200 import distributed
+  for total, world in ((1024, 1), (1024, 8), (10, 4), (7, 8)):
+    spans = [distributed.shard(total, rank, world) for rank in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == total
+    assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+    sizes = [hi - lo for lo, hi in spans]
+    assert max(sizes) - min(sizes) <= 1
