@@ -45,6 +45,9 @@ CASES: Dict[str, dict] = {
   'ingest_absorbing_sub4': dict(kind='ingest', cuda=False, obs=11, A=3, N=900, trajectories=4, subsample=4, absorbing=True, seed=71),
   'ingest_plain_all': dict(kind='ingest', cuda=False, obs=17, A=6, N=500, trajectories=0, subsample=1, absorbing=False, seed=72),
   'ingest_absorbing_sub1': dict(kind='ingest', cuda=False, obs=11, A=3, N=700, trajectories=3, subsample=1, absorbing=True, seed=73),
+  # a17: evaluation.py:11-35 on the synthetic env twin (greedy policy, sum of rewards per episode)
+  'eval_hopper': dict(kind='eval', cuda=False, env='hopper', H=32, episodes=4, max_steps=80, seed=81),
+  'eval_halfcheetah': dict(kind='eval', cuda=False, env='halfcheetah', H=32, episodes=3, max_steps=50, seed=82),
   'gmmil_hopper': dict(kind='gmmil', S=12, A=3, B=64, seed=41),
   'gmmil_halfcheetah': dict(kind='gmmil', S=18, A=6, B=256, seed=42),
   'pwil_small': dict(kind='pwil', S=12, A=3, N=150, T=40, steps=100, seed=51),
@@ -148,6 +151,10 @@ def make_inputs(name: str, seed_offset: int = 0) -> Dict[str, np.ndarray]:
     for j, e in enumerate(list(ends) + [N - 1]): (timeouts if j % 3 == 1 else terminals)[e] = 1  # episodes 1, 4 end by time limit
     inp['terminals'], inp['timeouts'] = terminals, timeouts
     inp['np_seed'] = np.int64([c['seed'] + 7])
+  elif k == 'eval':
+    env = port.SyntheticEnv(c['env'], True, c['max_steps'])
+    for i, w in enumerate(_mlp_weights(rs, [env.state_size, c['H'], c['H'], 2 * env.act], scale=2.0)): inp[f'actor_{i}'] = w
+    inp['reset_u'] = rs.uniform(size=(c['episodes'], env.obs)).astype(np.float32)
   elif k == 'gmmil':
     for pre in ('p', 'e'):
       for key, v in _batch(rs, c['B'], c['S'], c['A']).items(): inp[f'{pre}_{key}'] = v
@@ -261,6 +268,10 @@ def run_port(name: str, inp: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
     tr = port.build_expert_transitions(raw, c['trajectories'], c['subsample'], c['absorbing'], rng=np.random.RandomState(int(inp['np_seed'][0])))
     for key in ('states', 'actions', 'next_states', 'terminals', 'timeouts', 'weights', 'rewards'): out[key] = _np(tr[key])
     out['meta'] = np.int64([tr['num_trajectories'], tr['states'].shape[0]])
+  elif k == 'eval':
+    env = port.SyntheticEnv(c['env'], True, c['max_steps'])
+    rets = port.evaluate_agent([_t(inp[f'actor_{i}']) for i in range(6)], env, c['episodes'], [_t(u) for u in inp['reset_u']])
+    out['returns'] = np.float32(rets)
   elif k == 'gmmil':
     d = port.GmmilDiscriminator()
     p, e, p2 = _batch_from(inp, 'p_'), _batch_from(inp, 'e_'), _batch_from(inp, 'p2_')
@@ -467,6 +478,16 @@ def run_reference(name: str, inp: Dict[str, np.ndarray]) -> Dict[str, np.ndarray
       np.random.set_state(state)
     for key in ('states', 'actions', 'next_states', 'terminals', 'timeouts', 'weights', 'rewards'): out[key] = _np(getattr(mem, key))
     out['meta'] = np.int64([mem.num_trajectories, mem.states.shape[0]])
+  elif k == 'eval':
+    env = port.SyntheticEnv(c['env'], True, c['max_steps'])
+    actor = ref.models.SoftActor(env.state_size, env.act, model_cfg(c['H']))
+    _load_mlp(actor.actor, [inp[f'actor_{i}'] for i in range(6)])
+    noise = [_t(u) for u in inp['reset_u']]
+
+    class Adapter:  # the D4RLEnv surface evaluate_agent touches (environments.py:29-40): reset() / step(action)
+      def reset(self): return env.reset(noise.pop(0))
+      def step(self, action): return env.step(action)
+    out['returns'] = np.float32(ref.evaluation.evaluate_agent(actor, Adapter(), c['episodes']))
   elif k == 'gmmil':
     d = ref.models.GMMILDiscriminator(c['S'], c['A'], DC(state_only=False))
     p, e, p2 = _batch_from(inp, 'p_'), _batch_from(inp, 'e_'), _batch_from(inp, 'p2_')
