@@ -48,6 +48,9 @@ CASES: Dict[str, dict] = {
   # a17: evaluation.py:11-35 on the synthetic env twin (greedy policy, sum of rewards per episode)
   'eval_hopper': dict(kind='eval', cuda=False, env='hopper', H=32, episodes=4, max_steps=80, seed=81),
   'eval_halfcheetah': dict(kind='eval', cuda=False, env='halfcheetah', H=32, episodes=3, max_steps=50, seed=82),
+  # a7 / a8 / a16 around expert data: ReplayMemory(transitions=...) prefill (memory.py:18-23), transfer_transitions (:46-48), the
+  # "never the last row" sampling rule of a pre-filled memory (:22-23, 55) and mix_expert_agent_transitions (models.py:287-290)
+  'prefill_mix': dict(kind='mix', cuda=False, S=12, A=3, Ne=40, size=64, extra=9, B=16, seed=91),
   'gmmil_hopper': dict(kind='gmmil', S=12, A=3, B=64, seed=41),
   'gmmil_halfcheetah': dict(kind='gmmil', S=18, A=6, B=256, seed=42),
   'pwil_small': dict(kind='pwil', S=12, A=3, N=150, T=40, steps=100, seed=51),
@@ -155,6 +158,12 @@ def make_inputs(name: str, seed_offset: int = 0) -> Dict[str, np.ndarray]:
     env = port.SyntheticEnv(c['env'], True, c['max_steps'])
     for i, w in enumerate(_mlp_weights(rs, [env.state_size, c['H'], c['H'], 2 * env.act], scale=2.0)): inp[f'actor_{i}'] = w
     inp['reset_u'] = rs.uniform(size=(c['episodes'], env.obs)).astype(np.float32)
+  elif k == 'mix':
+    Ne, S, A = c['Ne'], c['S'], c['A']
+    for key, v in _batch(rs, Ne, S, A).items(): inp[f'e_{key}'] = v
+    inp['e_timeouts'] = (rs.uniform(size=Ne) < 0.05).astype(np.float32)
+    for key, v in _batch(rs, c['extra'], S, A).items(): inp[f'x_{key}'] = v
+    inp['np_seed'] = np.int64([c['seed'] + 3])
   elif k == 'gmmil':
     for pre in ('p', 'e'):
       for key, v in _batch(rs, c['B'], c['S'], c['A']).items(): inp[f'{pre}_{key}'] = v
@@ -272,6 +281,22 @@ def run_port(name: str, inp: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
     env = port.SyntheticEnv(c['env'], True, c['max_steps'])
     rets = port.evaluate_agent([_t(inp[f'actor_{i}']) for i in range(6)], env, c['episodes'], [_t(u) for u in inp['reset_u']])
     out['returns'] = np.float32(rets)
+  elif k == 'mix':
+    S, A = c['S'], c['A']
+    tr = {key: _t(inp[f'e_{key}']) for key in ('states', 'actions', 'rewards', 'next_states', 'terminals', 'timeouts', 'weights')}
+    tr['num_trajectories'] = 3
+    em = port.Replay(c['Ne'], S, A, True, transitions=tr)
+    am = port.Replay(c['size'], S, A, True)
+    am.transfer_transitions(em)
+    for i in range(c['extra']):
+      am.append(100 + i, _t(inp['x_states'][i]), _t(inp['x_actions'][i]), float(inp['x_rewards'][i]), _t(inp['x_next_states'][i]), bool(inp['x_terminals'][i]), False)
+    rng = np.random.RandomState(int(inp['np_seed'][0]))
+    ia, ie = am.draw_indices(c['B'], rng), em.draw_indices(c['B'], rng)
+    ta, te = am.gather(ia), em.gather(ie)
+    port.mix_expert_agent_transitions(ta, te)
+    out['idx_agent'], out['idx_expert'] = ia, ie
+    for key, v in ta.items(): out[f'mixed_{key}'] = _np(v)
+    out['meta'] = np.int64([am.idx, int(am.full), am.num_trajectories, em.idx, int(em.full), em.num_trajectories])
   elif k == 'gmmil':
     d = port.GmmilDiscriminator()
     p, e, p2 = _batch_from(inp, 'p_'), _batch_from(inp, 'e_'), _batch_from(inp, 'p2_')
@@ -488,6 +513,35 @@ def run_reference(name: str, inp: Dict[str, np.ndarray]) -> Dict[str, np.ndarray
       def reset(self): return env.reset(noise.pop(0))
       def step(self, action): return env.step(action)
     out['returns'] = np.float32(ref.evaluation.evaluate_agent(actor, Adapter(), c['episodes']))
+  elif k == 'mix':
+    S, A = c['S'], c['A']
+    tr = {key: _t(inp[f'e_{key}']) for key in ('states', 'actions', 'rewards', 'next_states', 'terminals', 'timeouts', 'weights')}
+    tr['num_trajectories'] = 3
+    em = ref.memory.ReplayMemory(c['Ne'], S, A, True, transitions=tr)
+    am = ref.memory.ReplayMemory(c['size'], S, A, True)
+    am.transfer_transitions(em)
+    for i in range(c['extra']):
+      am.append(100 + i, _t(inp['x_states'][i]), _t(inp['x_actions'][i]), float(inp['x_rewards'][i]), _t(inp['x_next_states'][i]), bool(inp['x_terminals'][i]), False)
+    # record the index stream of memory.py:51-56 while sampling with the global numpy RNG
+    drawn = []
+    orig = ref.memory.ReplayMemory._sample_idx
+    def spy(self):
+      i = orig(self)
+      drawn.append(i)
+      return i
+    state = np.random.get_state()
+    np.random.seed(int(inp['np_seed'][0]))
+    ref.memory.ReplayMemory._sample_idx = spy
+    try:
+      ta = am.sample(c['B'])
+      te = em.sample(c['B'])
+    finally:
+      ref.memory.ReplayMemory._sample_idx = orig
+      np.random.set_state(state)
+    ref.models.mix_expert_agent_transitions(ta, te)
+    out['idx_agent'], out['idx_expert'] = np.int64(drawn[:c['B']]), np.int64(drawn[c['B']:])
+    for key, v in ta.items(): out[f'mixed_{key}'] = _np(v)
+    out['meta'] = np.int64([am.idx, int(am.full), am.num_trajectories, em.idx, int(em.full), em.num_trajectories])
   elif k == 'gmmil':
     d = ref.models.GMMILDiscriminator(c['S'], c['A'], DC(state_only=False))
     p, e, p2 = _batch_from(inp, 'p_'), _batch_from(inp, 'e_'), _batch_from(inp, 'p2_')

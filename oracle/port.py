@@ -436,6 +436,12 @@ class Replay:
     self.full = self.full or self.idx == 0
     if terminal or timeout: self.num_trajectories += 1
 
+  def transfer_transitions(self, memory: 'Replay'):
+    """memory.py:46-48: every row of `memory` (all `size` of them, in storage order) appended with weight 1."""
+    for i in range(memory.size):
+      d = memory.data
+      self.append(d['step'][i].item(), d['states'][i], d['actions'][i], d['rewards'][i].item(), d['next_states'][i], bool(d['terminals'][i]), bool(d['timeouts'][i]))
+
   def draw_indices(self, n: int, rng=np.random) -> np.ndarray:
     """memory.py:51-56, n times (memory.py:59): global-RNG randint with rejection of the newest row."""
     out = []
