@@ -19,6 +19,8 @@ class NoiseSource:
   """Default noise: the reference's own RNG calls (torch global RNG for policy / GP noise, numpy global RNG for
   replay indices, a per-env generator for resets). Tests replace the methods to inject recorded noise."""
 
+  uses_reference_rng_streams = True  # also reproduces RNG-stream side effects that do not touch the math (see OracleLoop.run_step)
+
   def __init__(self, seed: int, obs: int):
     self.gen = torch.Generator().manual_seed(seed)
     self.obs = obs
@@ -50,11 +52,12 @@ class OracleLoop:
     self.noise = NoiseSource(seed, self.env.obs)
     S, A = self.env.state_size, self.env.act
     self.S, self.A = S, A
+    # train.py:60 loads the expert dataset for EVERY algorithm, SAC included, and train.py:173 samples it every update:
+    # SAC never uses that batch, but its index draws advance the global numpy stream. With the default NoiseSource
+    # (the reference's own RNG calls) the loop reproduces that; injected noise sources skip it (see run_step).
     self.expert_memory = None
-    if algorithm != 'SAC':
-      raw = expert_raw if expert_raw is not None else synthesize_raw_dataset(env_name, absorbing, max(trajectories, 5), max_episode_steps)
-      tr = port.build_expert_transitions(raw, trajectories, subsample, absorbing)
-      self.expert_memory = port.Replay(tr['states'].size(0), S, A, absorbing, transitions=tr)
+    self._expert_args = (expert_raw, env_name, absorbing, trajectories, subsample, max_episode_steps, S, A)
+    if algorithm != 'SAC': self._build_expert_memory()
     # train.py:64-66 (construction order fixes the RNG stream: actor, critic_1, critic_2, then the discriminator)
     sizes_a, sizes_c = [S] + [hidden_size] * depth + [2 * A], [S + A] + [hidden_size] * depth + [1]
     if init is None:
@@ -87,6 +90,12 @@ class OracleLoop:
     self.episode_returns = []
     self.last = {}
 
+  def _build_expert_memory(self):
+    expert_raw, env_name, absorbing, trajectories, subsample, max_episode_steps, S, A = self._expert_args
+    raw = expert_raw if expert_raw is not None else synthesize_raw_dataset(env_name, absorbing, max(trajectories, 5), max_episode_steps)
+    tr = port.build_expert_transitions(raw, trajectories, subsample, absorbing)
+    self.expert_memory = port.Replay(tr['states'].size(0), S, A, absorbing, transitions=tr)
+
   def run_step(self):
     """One iteration of train.py:149-211."""
     self.step += 1
@@ -107,7 +116,13 @@ class OracleLoop:
     if step >= self.start:  # train.py:171 (interval 1)
       B = self.B
       transitions = self.memory.gather(self.noise.policy_indices(self.memory, B))
-      expert = self.expert_memory.gather(self.noise.expert_indices(self.expert_memory, B)) if self.expert_memory is not None else None
+      if self.algorithm != 'SAC':
+        expert = self.expert_memory.gather(self.noise.expert_indices(self.expert_memory, B))  # train.py:173
+      else:
+        expert = None
+        if getattr(self.noise, 'uses_reference_rng_streams', False):  # the unused expert batch of train.py:173
+          if self.expert_memory is None: self._build_expert_memory()
+          self.noise.expert_indices(self.expert_memory, B)
       if self.algorithm == 'GAIL':  # train.py:177-180
         self.last['gail'] = port.gail_update(self.disc, self.disc_opt, transitions, expert, self.noise.gp_eps(B), loss_function=self.im['loss_function'],
                                              grad_penalty=self.im['grad_penalty'], entropy_bonus=self.im['entropy_bonus'])

@@ -49,16 +49,23 @@ def load():
       if name == 'gym':
         m.logger = types.SimpleNamespace(set_level=lambda *_: None)
       if name == 'gym.spaces':
-        m.Box, m.Space = object, object
+        class Box:  # the attributes environments.py:23-27 and train.py:61 touch
+          def __init__(self, low, high):
+            import numpy as np
+            self.low, self.high = np.asarray(low), np.asarray(high)
+            self.shape = self.low.shape
+        m.Box, m.Space = Box, object
       sys.modules[name] = m
   sys.modules['gym'].spaces = sys.modules['gym.spaces']
+  if not hasattr(sys.modules['gym'], 'make'): sys.modules['gym'].make = lambda name: (_ for _ in ()).throw(RuntimeError('gym is stubbed; patch gym.make (oracle/ref_train.py)'))
   # The reference uses top-level module names (memory, models, training, ...); import them under
   # those names from REFERENCE_DIR without leaving it on sys.path permanently shadowing ours.
   saved = {k: sys.modules.pop(k) for k in ('memory', 'models', 'training', 'evaluation', 'environments') if k in sys.modules}
   sys.path.insert(0, REFERENCE_DIR)
   try:
     import memory, models, training, evaluation  # noqa: E401
-    mods = types.SimpleNamespace(memory=memory, models=models, training=training, evaluation=evaluation, DictConfig=DictConfig)
+    import environments
+    mods = types.SimpleNamespace(memory=memory, models=models, training=training, evaluation=evaluation, environments=environments, DictConfig=DictConfig)
   finally:
     sys.path.remove(REFERENCE_DIR)
     for k in ('memory', 'models', 'training', 'evaluation', 'environments'):
