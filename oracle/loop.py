@@ -30,6 +30,7 @@ class NoiseSource:
   def policy_indices(self, mem, n): return mem.draw_indices(n)
   def expert_indices(self, mem, n): return mem.draw_indices(n)
   def gp_eps(self, B): return torch.rand(B)
+  def mixup_eps(self, B, alpha): return torch.distributions.Beta(torch.full((B, ), float(alpha)), torch.full((B, ), float(alpha))).sample()  # training.py:106
   def sac_eps(self, B, A): return torch.randn(B, A), torch.randn(B, A)
 
 
@@ -37,14 +38,16 @@ class OracleLoop:
   def __init__(self, algorithm: str = 'GAIL', env_name: str = 'hopper', seed: int = 0, batch_size: int = 256, start: int = 1000, memory_size: int = 100000,
                hidden_size: int = 256, depth: int = 2, lr: float = 3e-4, weight_decay: float = 0.0, trajectories: int = 5, subsample: int = 1, absorbing: bool = True,
                mix_expert_data: str = 'none', imitation: Optional[dict] = None, discount: Optional[float] = None, polyak: Optional[float] = None,
-               target_temperature: Optional[float] = None, max_episode_steps: int = 1000, expert_raw: Optional[Dict[str, torch.Tensor]] = None, init: Optional[dict] = None):
+               target_temperature: Optional[float] = None, max_episode_steps: int = 1000, expert_raw: Optional[Dict[str, torch.Tensor]] = None, init: Optional[dict] = None,
+               bc_aux_loss: bool = False, build_expert_memory: bool = False):
     gail = algorithm == 'GAIL'
     self.algorithm, self.B, self.start, self.absorbing, self.mix = algorithm, batch_size, start, absorbing, mix_expert_data
+    self.bc_aux_loss = bc_aux_loss  # train.py:201
     self.discount = (0.97 if gail else 0.99) if discount is None else discount  # GAIL.yaml:5 / train_config.yaml:36
     self.polyak = (0.99 if gail else 0.995) if polyak is None else polyak  # GAIL.yaml:7 / train_config.yaml:38
     tt = (-0.5 if gail else -1.0) if target_temperature is None else target_temperature  # GAIL.yaml:6 / train_config.yaml:37
     self.im = dict(hidden_size=64, learning_rate=3e-5, weight_decay=10.0, grad_penalty=1.0, spectral_norm=True, entropy_bonus=0.0, loss_function='BCE', reward_function='AIRL',
-                   reward_scale=5.0, reward_bandwidth_scale=5.0)  # GAIL.yaml:8-27, PWIL.yaml:4-6
+                   mixup_alpha=1.0, pos_class_prior=0.7, nonnegative_margin=float('inf'), reward_scale=5.0, reward_bandwidth_scale=5.0)  # GAIL.yaml:8-27, PWIL.yaml:4-6
     self.im.update(imitation or {})
     np.random.seed(seed)
     torch.manual_seed(seed)  # train.py:51-52
@@ -57,7 +60,7 @@ class OracleLoop:
     # (the reference's own RNG calls) the loop reproduces that; injected noise sources skip it (see run_step).
     self.expert_memory = None
     self._expert_args = (expert_raw, env_name, absorbing, trajectories, subsample, max_episode_steps, S, A)
-    if algorithm != 'SAC': self._build_expert_memory()
+    if algorithm != 'SAC' or build_expert_memory: self._build_expert_memory()
     # train.py:64-66 (construction order fixes the RNG stream: actor, critic_1, critic_2, then the discriminator)
     sizes_a, sizes_c = [S] + [hidden_size] * depth + [2 * A], [S + A] + [hidden_size] * depth + [1]
     if init is None:
@@ -85,6 +88,13 @@ class OracleLoop:
     elif algorithm == 'PWIL':
       self.disc = port.PwilDiscriminator(self.expert_memory.data['states'], self.expert_memory.data['actions'], max_episode_steps, self.im['reward_scale'],
                                          self.im['reward_bandwidth_scale'])
+    if algorithm == 'PWIL' and mix_expert_data != 'none':  # train.py:136-140: greedy PWIL rewards for the expert's own transitions
+      with torch.inference_mode():
+        d = self.expert_memory.data
+        for i in range(self.expert_memory.size):
+          d['rewards'][i] = self.disc.compute_reward(d['states'][i].unsqueeze(0), d['actions'][i].unsqueeze(0))
+          if d['terminals'][i] or d['timeouts'][i]: self.disc.reset()
+    if algorithm in ('PWIL', 'GMMIL') and mix_expert_data == 'prefill_memory': self.memory.transfer_transitions(self.expert_memory)  # train.py:141,143
     self.t, self.train_return, self.step = 0, 0.0, 0
     self.state = self.env.reset(self.noise.reset_u())  # train.py:146
     self.episode_returns = []
@@ -124,17 +134,38 @@ class OracleLoop:
           if self.expert_memory is None: self._build_expert_memory()
           self.noise.expert_indices(self.expert_memory, B)
       if self.algorithm == 'GAIL':  # train.py:177-180
-        self.last['gail'] = port.gail_update(self.disc, self.disc_opt, transitions, expert, self.noise.gp_eps(B), loss_function=self.im['loss_function'],
-                                             grad_penalty=self.im['grad_penalty'], entropy_bonus=self.im['entropy_bonus'])
+        eps_mix = self.noise.mixup_eps(B, self.im['mixup_alpha']) if self.im['loss_function'] == 'Mixup' else None  # drawn before the GP noise (training.py:106 then :118)
+        eps_gp = self.noise.gp_eps(B) if self.im['grad_penalty'] > 0 else None
+        self.last['gail'] = port.gail_update(self.disc, self.disc_opt, transitions, expert, eps_gp, loss_function=self.im['loss_function'],
+                                             grad_penalty=self.im['grad_penalty'], entropy_bonus=self.im['entropy_bonus'], pos_class_prior=self.im['pos_class_prior'],
+                                             nonnegative_margin=self.im['nonnegative_margin'], eps_mixup=eps_mix)
       if self.algorithm in ('GAIL', 'GMMIL'):
         if self.mix == 'mixed_batch': port.mix_expert_agent_transitions(transitions, expert)  # train.py:183
         with torch.inference_mode():
           if self.algorithm == 'GAIL': rewards = self.disc.predict_reward(transitions['states'], transitions['actions'])  # train.py:194
           else: rewards = self.disc.predict_reward(transitions['states'], transitions['actions'], expert['states'], expert['actions'], transitions['weights'], expert['weights'])
         transitions['rewards'] = rewards.clone()
+      if self.bc_aux_loss: port.behavioural_cloning_update(agent.actor, agent.opt_actor, expert)  # train.py:201 (the SAC actor optimiser)
       e1, e2 = self.noise.sac_eps(B, self.A)
       self.last['sac'] = port.sac_update(agent, transitions, e1, e2, self.discount, self.entropy_target, self.polyak)  # train.py:203
       self.last['rewards'] = transitions['rewards']
+
+  def bc_pretrain(self, iterations: int, learning_rate: float, weight_decay: float):
+    """train.py:95-101: behavioural cloning on shuffled expert minibatches (DataLoader(shuffle=True, drop_last=True), cycled)
+    with a separate AdamW. Per epoch the global torch stream gives one draw to the DataLoader iterator (base seed) and one
+    to the RandomSampler, which seeds the generator of that epoch's permutation."""
+    opt = torch.optim.AdamW(self.agent.actor, lr=learning_rate, weight_decay=weight_decay)
+    n, B, done = self.expert_memory.size, self.B, 0
+    while done < iterations:
+      torch.empty((), dtype=torch.int64).random_()  # the DataLoader iterator's base seed (torch/utils/data/dataloader.py, _BaseDataLoaderIter.__init__)
+      seed = int(torch.empty((), dtype=torch.int64).random_().item())  # then torch/utils/data/sampler.py RandomSampler.__iter__
+      perm = torch.randperm(n, generator=torch.Generator().manual_seed(seed)).tolist()
+      for b in range(n // B):
+        if done == iterations: break
+        idx = perm[b * B:(b + 1) * B]
+        batch = {k: self.expert_memory.data[k][idx] for k in port.FIELDS}
+        port.behavioural_cloning_update(self.agent.actor, opt, batch)
+        done += 1
 
   def prefill(self, n: int):
     """Runs the warm-up phase of train.py:171 (`training.start` env steps without updates)."""

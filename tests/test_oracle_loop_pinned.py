@@ -31,20 +31,39 @@ def _close(name, ref, mine):
   assert err <= ATOL * max(1.0, float(ref.abs().max())), f'{name}: max abs err {err:.3e}'
 
 
-@pytest.mark.parametrize('algorithm,env,mix', [('GAIL', 'hopper', 'none'), ('GAIL', 'walker2d', 'mixed_batch'), ('SAC', 'hopper', 'none'), ('GMMIL', 'halfcheetah', 'none'),
-                                               ('GMMIL', 'hopper', 'mixed_batch'), ('PWIL', 'hopper', 'none')])
-def test_restated_loop_equals_the_reference_train_function(algorithm, env, mix):
+CONFIGS = [
+  # (algorithm, env, reference-side overrides, oracle-loop kwargs)
+  ('GAIL', 'hopper', (), {}),
+  ('GAIL', 'walker2d', ('imitation.mix_expert_data=mixed_batch', ), dict(mix_expert_data='mixed_batch')),
+  ('GAIL', 'hopper', ('imitation.loss_function=Mixup', 'imitation.entropy_bonus=0.1', 'imitation.grad_penalty=0.5'), dict(imitation=dict(loss_function='Mixup', entropy_bonus=0.1, grad_penalty=0.5))),
+  ('GAIL', 'hopper', ('imitation.loss_function=PUGAIL', 'imitation.nonnegative_margin=0.3', 'imitation.grad_penalty=0', 'imitation.spectral_norm=false',
+                      'imitation.discriminator.reward_function=FAIRL'),
+   dict(imitation=dict(loss_function='PUGAIL', nonnegative_margin=0.3, grad_penalty=0.0, spectral_norm=False, reward_function='FAIRL'))),
+  ('GAIL', 'hopper', ('imitation.bc_aux_loss=true', ), dict(bc_aux_loss=True)),
+  ('SAC', 'hopper', (), {}),
+  ('SAC', 'ant', ('training.weight_decay=0.01', ), dict(weight_decay=0.01)),
+  ('GMMIL', 'halfcheetah', (), {}),
+  ('GMMIL', 'hopper', ('imitation.mix_expert_data=mixed_batch', ), dict(mix_expert_data='mixed_batch')),
+  ('GMMIL', 'hopper', ('imitation.mix_expert_data=prefill_memory', ), dict(mix_expert_data='prefill_memory')),
+  ('PWIL', 'hopper', (), {}),
+  ('PWIL', 'hopper', ('imitation.mix_expert_data=mixed_batch', ), dict(mix_expert_data='mixed_batch')),
+  ('PWIL', 'walker2d', ('imitation.mix_expert_data=prefill_memory', ), dict(mix_expert_data='prefill_memory')),
+]
+
+
+@pytest.mark.parametrize('algorithm,env,extra,kwargs', CONFIGS, ids=[f'{a}-{e}-{i}' for i, (a, e, _, _) in enumerate(CONFIGS)])
+def test_restated_loop_equals_the_reference_train_function(algorithm, env, extra, kwargs):
   from oracle import ref_train
   seed = 3
-  cfg = _cfg(algorithm, env, seed, [f'imitation.mix_expert_data={mix}'])
+  cfg = _cfg(algorithm, env, seed, extra)
   raw = loop.synthesize_raw_dataset(env, True, 5, MAX_EPISODE_STEPS)
   ref = ref_train.run_reference_train(cfg, raw, MAX_EPISODE_STEPS)
 
   threads = torch.get_num_threads()
   torch.set_num_threads(1)
   try:
-    ol = loop.OracleLoop(algorithm, env, seed=seed, batch_size=B, start=START, memory_size=STEPS, hidden_size=H, trajectories=3, mix_expert_data=mix,
-                         max_episode_steps=MAX_EPISODE_STEPS, expert_raw=raw)
+    ol = loop.OracleLoop(algorithm, env, seed=seed, batch_size=B, start=START, memory_size=STEPS, hidden_size=H, trajectories=3, max_episode_steps=MAX_EPISODE_STEPS,
+                         expert_raw=raw, **kwargs)
     for _ in range(STEPS): ol.run_step()
   finally:
     torch.set_num_threads(threads)
@@ -56,12 +75,13 @@ def test_restated_loop_equals_the_reference_train_function(algorithm, env, mix):
     for i in range(6): _close(f'critic.{critic[6 * t + i][0]}', critic[6 * t + i][1], ol.agent.twin[t][i])
   _close('log_alpha', ref['agent']['log_alpha'], ol.agent.log_alpha)
   if algorithm == 'GAIL':
-    sd = ref['discriminator']
+    sd, sn = ref['discriminator'], ol.disc.g_sn is not None
     for l in range(2):
-      _close(f'g.{l}.weight', sd[f'g.{2 * l}.parametrizations.weight.original'], ol.disc.g[2 * l])
+      _close(f'g.{l}.weight', sd[f'g.{2 * l}.parametrizations.weight.original' if sn else f'g.{2 * l}.weight'], ol.disc.g[2 * l])
       _close(f'g.{l}.bias', sd[f'g.{2 * l}.bias'], ol.disc.g[2 * l + 1])
-      _close(f'g.{l}.u', sd[f'g.{2 * l}.parametrizations.weight.0._u'], ol.disc.g_sn[l][0])
-      _close(f'g.{l}.v', sd[f'g.{2 * l}.parametrizations.weight.0._v'], ol.disc.g_sn[l][1])
+      if sn:
+        _close(f'g.{l}.u', sd[f'g.{2 * l}.parametrizations.weight.0._u'], ol.disc.g_sn[l][0])
+        _close(f'g.{l}.v', sd[f'g.{2 * l}.parametrizations.weight.0._v'], ol.disc.g_sn[l][1])
   # episode bookkeeping (train.py:161-168) and the logged tensors of the last logging step (train.py:205-210)
   got = [r[0] for r in ref['metrics']['train_returns']]
   assert len(got) == len(ol.episode_returns) and np.allclose(got, ol.episode_returns, rtol=1e-5, atol=1e-6)
@@ -69,3 +89,36 @@ def test_restated_loop_equals_the_reference_train_function(algorithm, env, mix):
   _close('predicted_rewards', ref['metrics']['predicted_rewards'][-1], ol.last['rewards'])
   _close('q_values', ref['metrics']['Q_values'][-1], ol.last['sac']['q_values'])
   _close('entropies', ref['metrics']['entropies'][-1], -ol.last['sac']['log_probs'])
+
+
+@pytest.mark.parametrize('algorithm,iterations', [('BC', 25), ('GAIL', 7)])
+def test_bc_pretraining_equals_the_reference(algorithm, iterations):
+  """train.py:95-115: BC on shuffled expert minibatches (the DataLoader's shuffling stream restated in OracleLoop.bc_pretrain);
+  algorithm=BC returns after pretraining + evaluation, any other algorithm continues into the loop with the pretrained actor."""
+  from oracle import port, ref_train
+  seed, env = 5, 'hopper'
+  cfg = _cfg(algorithm, env, seed, [f'bc_pretraining.iterations={iterations}', 'bc_pretraining.learning_rate=0.001', 'bc_pretraining.weight_decay=0.01'])
+  raw = loop.synthesize_raw_dataset(env, True, 5, MAX_EPISODE_STEPS)
+  ref = ref_train.run_reference_train(cfg, raw, MAX_EPISODE_STEPS)
+  threads = torch.get_num_threads()
+  torch.set_num_threads(1)
+  try:
+    ol = loop.OracleLoop('SAC' if algorithm == 'BC' else algorithm, env, seed=seed, batch_size=B, start=START, memory_size=STEPS, hidden_size=H, trajectories=3,
+                         max_episode_steps=MAX_EPISODE_STEPS, expert_raw=raw, build_expert_memory=True)
+    ol.bc_pretrain(iterations, 0.001, 0.01)
+    if algorithm != 'BC':
+      for _ in range(STEPS): ol.run_step()
+  finally:
+    torch.set_num_threads(threads)
+  for i, (k, v) in enumerate(ref['agent']['actor'].items()): _close(f'actor.{k}', v, ol.agent.actor[i])
+  if algorithm == 'BC':
+    assert set(ref['agent']) == {'actor'}  # train.py:111
+    # the evaluation of train.py:104 on the evaluation env's own reset stream (second env made, oracle/ref_train.py)
+    g = torch.Generator().manual_seed(seed + 10007)
+    eval_env = port.SyntheticEnv(env, True, MAX_EPISODE_STEPS)
+    noise = [torch.rand(eval_env.obs, generator=g) for _ in range(2)]
+    mine = port.evaluate_agent(ol.agent.actor, eval_env, 2, noise)
+    assert np.allclose(ref['metrics']['test_returns'][0], mine, rtol=1e-5, atol=1e-6)
+    assert abs(ref['score'] - np.mean(mine) / 1000.0) < 1e-7
+  else:
+    _close('log_alpha', ref['agent']['log_alpha'], ol.agent.log_alpha)
