@@ -47,7 +47,8 @@ class OracleLoop:
     self.polyak = (0.99 if gail else 0.995) if polyak is None else polyak  # GAIL.yaml:7 / train_config.yaml:38
     tt = (-0.5 if gail else -1.0) if target_temperature is None else target_temperature  # GAIL.yaml:6 / train_config.yaml:37
     self.im = dict(hidden_size=64, learning_rate=3e-5, weight_decay=10.0, grad_penalty=1.0, spectral_norm=True, entropy_bonus=0.0, loss_function='BCE', reward_function='AIRL',
-                   mixup_alpha=1.0, pos_class_prior=0.7, nonnegative_margin=float('inf'), reward_scale=5.0, reward_bandwidth_scale=5.0)  # GAIL.yaml:8-27, PWIL.yaml:4-6
+                   mixup_alpha=1.0, pos_class_prior=0.7, nonnegative_margin=float('inf'), reward_scale=5.0, reward_bandwidth_scale=5.0,
+                   depth=1, activation='relu', reward_shaping=False, subtract_log_policy=False, state_only=False)  # GAIL.yaml:8-27, PWIL.yaml:4-6, train_config.yaml:45
     self.im.update(imitation or {})
     np.random.seed(seed)
     torch.manual_seed(seed)  # train.py:51-52
@@ -72,16 +73,31 @@ class OracleLoop:
     self.memory = port.Replay(memory_size, S, A, absorbing)
     self.disc = None
     if gail:
-      H = self.im['hidden_size']
+      im = self.im
+      H, din = im['hidden_size'], (S if im['state_only'] else S + A)
+
+      def fcnn(sizes):  # models.py:48-69 with spectral_norm: per layer Linear() draws, orthogonal_ draws, then the u / v draws of the parametrization
+        params, bufs = [], []
+        for l in range(len(sizes) - 1):
+          last = l == len(sizes) - 2
+          p = port.init_mlp([sizes[l], sizes[l + 1]], final_gain=1.0 if last else torch.nn.init.calculate_gain(im['activation']))
+          params += p
+          if im['spectral_norm']: bufs.append(port.spectral_norm_init(p[0]))
+        return params, bufs
+
+      h = h_sn = None
       if init is None or 'g' not in init:
-        g, sn = [], []
-        for l, (i, o) in enumerate(((S + A, H), (H, 1))):  # models.py:162 via _create_fcnn with spectral_norm
-          p = port.init_mlp([i, o], final_gain=math.sqrt(2) if l == 0 else 1.0)
-          g += p
-          if self.im['spectral_norm']: sn.append(port.spectral_norm_init(p[0]))
+        if im['reward_shaping']:  # models.py:157-160: g is a plain nn.Linear (default init), h the MLP
+          lin = torch.nn.Linear(din, 1)
+          g, sn = [lin.weight.detach().clone(), lin.bias.detach().clone()], []
+          if im['spectral_norm']: sn.append(port.spectral_norm_init(g[0]))
+          h, h_sn = fcnn([S] + [H] * im['depth'] + [1])
+        else:
+          g, sn = fcnn([din] + [H] * im['depth'] + [1])  # models.py:162
       else:
         g, sn = init['g'], init.get('sn')
-      self.disc = port.GailDiscriminator(g, sn if self.im['spectral_norm'] else None, self.discount, reward_function=self.im['reward_function'])
+      self.disc = port.GailDiscriminator(g, sn if im['spectral_norm'] else None, self.discount, activation=im['activation'], reward_function=im['reward_function'],
+                                         state_only=im['state_only'], subtract_log_policy=im['subtract_log_policy'], h=h, h_sn=h_sn if im['spectral_norm'] else None)
       self.disc_opt = torch.optim.AdamW(self.disc.parameters(), lr=self.im['learning_rate'], weight_decay=self.im['weight_decay'])  # train.py:84
     elif algorithm == 'GMMIL':
       self.disc = port.GmmilDiscriminator()
@@ -138,11 +154,13 @@ class OracleLoop:
         eps_gp = self.noise.gp_eps(B) if self.im['grad_penalty'] > 0 else None
         self.last['gail'] = port.gail_update(self.disc, self.disc_opt, transitions, expert, eps_gp, loss_function=self.im['loss_function'],
                                              grad_penalty=self.im['grad_penalty'], entropy_bonus=self.im['entropy_bonus'], pos_class_prior=self.im['pos_class_prior'],
-                                             nonnegative_margin=self.im['nonnegative_margin'], eps_mixup=eps_mix)
+                                             nonnegative_margin=self.im['nonnegative_margin'], eps_mixup=eps_mix, actor=agent.actor)
       if self.algorithm in ('GAIL', 'GMMIL'):
         if self.mix == 'mixed_batch': port.mix_expert_agent_transitions(transitions, expert)  # train.py:183
         with torch.inference_mode():
-          if self.algorithm == 'GAIL': rewards = self.disc.predict_reward(transitions['states'], transitions['actions'])  # train.py:194
+          if self.algorithm == 'GAIL':  # train.py:194 via make_gail_input (models.py:145-149)
+            lp = port.actor_log_prob(agent.actor, transitions['states'], transitions['actions']) if self.disc.subtract_log_policy else None
+            rewards = self.disc.predict_reward(transitions['states'], transitions['actions'], transitions['next_states'], transitions['terminals'], lp)
           else: rewards = self.disc.predict_reward(transitions['states'], transitions['actions'], expert['states'], expert['actions'], transitions['weights'], expert['weights'])
         transitions['rewards'] = rewards.clone()
       if self.bc_aux_loss: port.behavioural_cloning_update(agent.actor, agent.opt_actor, expert)  # train.py:201 (the SAC actor optimiser)
