@@ -185,7 +185,7 @@ double gemm_algorithmic_bytes(const GemmArgs& a, bool stores_c);
 int profile_open(il_handle* h, ProfiledLaunch* pl, double flops, double bytes, cudaStream_t stream);
 int profile_close(il_handle* h, ProfiledLaunch* pl, cudaStream_t stream);
 
-// tcgen05 engine (tc_gemm.cu): dense M%128==0, N==256, K%32==0 problems when il_set_gemm_mode != IL_GEMM_FP32
+// tcgen05 engine (tc_gemm.cu): dense M%128==0 (CTA pairs when M%256==0), N==256, K%16==0 problems when il_set_gemm_mode != IL_GEMM_FP32
 bool tc_gemm_eligible(const GemmArgs& a);
 int launch_tc_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream);
 int tc_gemm_init();
