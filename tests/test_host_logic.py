@@ -84,6 +84,7 @@ def test_config_defaults_and_overrides():
   tuned = config.load_config(['algorithm=GAIL', 'optimised_hyperparameters=GAIL_5_trajectories'])
   assert tuned.training.batch_size == 1024 and tuned.imitation.loss_function == 'Mixup'
   with pytest.raises(FileNotFoundError): config.load_config(['algorithm=NOPE'])
+  with pytest.raises(NotImplementedError): config.load_config(['algorithm=RED'])
   with pytest.raises(AttributeError): _ = cfg.training.no_such_key
 
 
