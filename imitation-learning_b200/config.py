@@ -38,6 +38,17 @@ def _merge(dst: Dict[str, Any], src: Dict[str, Any]) -> Dict[str, Any]:
 
 
 def _parse(v: str) -> Any:
+  """Override values the way Hydra's grammar reads them: ints, then floats (3e-4, 1e6, inf, nan — YAML 1.1 would hand
+  these back as strings), then YAML for the rest (true / false / null / lists / quoted strings)."""
+  t = v.strip()
+  try:
+    return int(t)
+  except ValueError:
+    pass
+  try:
+    return float(t)
+  except ValueError:
+    pass
   return yaml.safe_load(v)
 
 

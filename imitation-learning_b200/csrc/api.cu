@@ -32,6 +32,8 @@ extern "C" int il_create(int device, il_handle** out) {
     const char* e = getenv("IL_TC_PAIRS");
     h->tc_pairs = (e && e[0] == '0') ? 0 : 1;
     h->tc_pair_groups = 0;
+    const char* fl = getenv("IL_TC_FUSE_L1");
+    h->tc_fuse_l1 = (fl && fl[0] == '0') ? 0 : 1;
     const char* th = getenv("IL_THIN_HOIST");
     h->thin_hoist = (th && th[0] == '0') ? 0 : 1;  // default on: +2.3 % step throughput (A/B in one gpurun call, parity suite green both ways)
   }

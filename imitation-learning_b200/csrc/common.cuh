@@ -21,6 +21,7 @@ struct il_handle {
   int tc_pair_groups;                   // co-resident 2-CTA clusters of the tcgen05 pair kernel (0 = not queried yet)
   int thin_hoist;                       // K-thin kernel: hoisted mask loads for the masked (dX) variant (IL_THIN_HOIST=0/1)
   int tc_pairs;                         // tcgen05 engine: use CTA pairs (cta_group::2) when rows are a multiple of 256 (IL_TC_PAIRS=0 disables)
+  int tc_fuse_l1;                       // tcgen05 engine: compute the first MLP layer inside the producers of the second (IL_TC_FUSE_L1=0 disables)
   long long launches;
   int profiling;                        // il_profile_begin/end: CUDA events around every dense-layer GEMM launch
   std::vector<ProfiledLaunch> profiled;
@@ -189,7 +190,20 @@ int profile_close(il_handle* h, ProfiledLaunch* pl, cudaStream_t stream);
 bool tc_gemm_eligible(const GemmArgs& a);
 int launch_tc_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream);
 int tc_gemm_init();
+// First MLP layer fused into the producers of the tcgen05 engine: the A operand of the dense product is
+// relu(X W1^T + b1) (K0 = x_k <= 16 input columns), computed chunk by chunk into the operand tile instead of being read from HBM.
+struct TcFuseL1 {
+  const float* x;        // input rows: element (g, m, j) at x + (g / x_gdiv) * x_gs + m * x_ld + j
+  int64_t x_gs;
+  int x_gdiv, x_ld, x_k;
+  const float* w1;       // [H, x_k] row-major per group (group stride gs), H = K of the dense product
+  const float* b1;       // [H]
+  int64_t gs;
+  float* store;          // optional [G, M, H]: the first hidden activation, written when a backward pass needs it
+  int64_t store_gs;
+};
 // dense hidden layer + bias + ReLU with the following (final, <= 8 units) linear layer fused into the epilogue
 bool tc_head_fusable(const il_handle* h, const GemmArgs& a, int head_n);
+bool tc_l1_fusable(const il_handle* h, const GemmArgs& a, int x_k);
 int launch_tc_gemm_head(il_handle* h, const GemmArgs& a, const float* head_w, const float* head_b, int64_t head_gs, int head_n, float* head_out, int64_t head_out_gs, int store_c,
-                        cudaStream_t stream);
+                        cudaStream_t stream, const TcFuseL1* l1 = nullptr);

@@ -38,38 +38,44 @@ char* mlp_acts_carve(const il_mlp* m, int G, int n, char* ws, MlpActs* acts) {
 int mlp_forward(il_handle* h, const il_mlp* m, int G, int n, MatView X, const MlpActs& acts, float* out, int64_t out_gs, int ld_out, cudaStream_t stream, bool keep_hidden) {
   const MlpOffsets o = mlp_offsets(m->dims, m->n_layers);
   const int L = m->n_layers;
+  auto layer_args = [&](int l) {
+    GemmArgs a{};
+    if (l == 0) { a.A = X.ptr; a.a_gs = X.gs; a.a_gdiv = X.gdiv; a.lda = X.ld; }
+    else { a.A = acts.hid[l - 1]; a.a_gs = (int64_t)n * m->dims[l]; a.a_gdiv = 1; a.lda = m->dims[l]; }
+    a.a_kmajor = 1;
+    a.B = m->params + o.w[l]; a.b_gs = m->stride; a.b_gdiv = 1; a.ldb = m->dims[l]; a.b_kmajor = 1;
+    a.bias = m->params + o.b[l]; a.bias_gs = m->stride;
+    if (l == L - 1) { a.C = out; a.c_gs = out_gs; a.ldc = ld_out; a.act = -1; }
+    else { a.C = acts.hid[l]; a.c_gs = (int64_t)n * m->dims[l + 1]; a.ldc = m->dims[l + 1]; a.act = m->activation; }
+    a.M = n; a.N = m->dims[l + 1]; a.K = m->dims[l]; a.G = G;
+    return a;
+  };
+  // the last hidden layer runs on the tensor-core engine with the final linear layer (N <= 8) fused into its epilogue
+  const bool head_shape = L >= 2 && m->activation == IL_ACT_RELU && ld_out == m->dims[L] && out_gs == (int64_t)n * m->dims[L];
   for (int l = 0; l < L; ++l) {
-    if (l == L - 2 && L >= 2 && m->activation == IL_ACT_RELU && ld_out == m->dims[L] && out_gs == (int64_t)n * m->dims[L]) {
-      // last hidden layer on the tensor-core engine: fuse the final linear layer (N <= 8) into its epilogue
-      GemmArgs a{};
-      if (l == 0) { a.A = X.ptr; a.a_gs = X.gs; a.a_gdiv = X.gdiv; a.lda = X.ld; }
-      else { a.A = acts.hid[l - 1]; a.a_gs = (int64_t)n * m->dims[l]; a.a_gdiv = 1; a.lda = m->dims[l]; }
-      a.a_kmajor = 1;
-      a.B = m->params + o.w[l]; a.b_gs = m->stride; a.b_gdiv = 1; a.ldb = m->dims[l]; a.b_kmajor = 1;
-      a.bias = m->params + o.b[l]; a.bias_gs = m->stride;
-      a.C = acts.hid[l]; a.c_gs = (int64_t)n * m->dims[l + 1]; a.ldc = m->dims[l + 1]; a.act = m->activation;
-      a.M = n; a.N = m->dims[l + 1]; a.K = m->dims[l]; a.G = G;
+    if (head_shape && l == L - 2) {
+      const GemmArgs a = layer_args(l);
       if (tc_head_fusable(h, a, m->dims[L])) {
         IL_TRY(launch_tc_gemm_head(h, a, m->params + o.w[L - 1], m->params + o.b[L - 1], m->stride, m->dims[L], out, out_gs, keep_hidden ? 1 : 0, stream));
         return 0;
       }
     }
-    GemmArgs a{};
-    if (l == 0) {
-      a.A = X.ptr; a.a_gs = X.gs; a.a_gdiv = X.gdiv; a.lda = X.ld;
-    } else {
-      a.A = acts.hid[l - 1]; a.a_gs = (int64_t)n * m->dims[l]; a.a_gdiv = 1; a.lda = m->dims[l];
+    if (head_shape && l == 0 && L == 3) {
+      // depth-2 nets (every actor / critic of the reference, conf/train_config.yaml:28-35): the first layer (K0 = state or
+      // state + action columns) is computed inside the producers of the second layer's tensor-core launch, so its output
+      // is written to HBM only when a backward pass needs it — and never read back by the forward pass
+      GemmArgs a1 = layer_args(1);
+      a1.A = nullptr; a1.a_gs = 0; a1.a_gdiv = 1; a1.lda = m->dims[1];
+      if (tc_head_fusable(h, a1, m->dims[L]) && tc_l1_fusable(h, a1, m->dims[0])) {
+        TcFuseL1 f{};
+        f.x = X.ptr; f.x_gs = X.gs; f.x_gdiv = X.gdiv; f.x_ld = X.ld; f.x_k = m->dims[0];
+        f.w1 = m->params + o.w[0]; f.b1 = m->params + o.b[0]; f.gs = m->stride;
+        f.store = keep_hidden ? acts.hid[0] : nullptr; f.store_gs = (int64_t)n * m->dims[1];
+        IL_TRY(launch_tc_gemm_head(h, a1, m->params + o.w[L - 1], m->params + o.b[L - 1], m->stride, m->dims[L], out, out_gs, keep_hidden ? 1 : 0, stream, &f));
+        return 0;
+      }
     }
-    a.a_kmajor = 1;
-    a.B = m->params + o.w[l]; a.b_gs = m->stride; a.b_gdiv = 1; a.ldb = m->dims[l]; a.b_kmajor = 1;
-    a.bias = m->params + o.b[l]; a.bias_gs = m->stride;
-    if (l == L - 1) {
-      a.C = out; a.c_gs = out_gs; a.ldc = ld_out; a.act = -1;
-    } else {
-      a.C = acts.hid[l]; a.c_gs = (int64_t)n * m->dims[l + 1]; a.ldc = m->dims[l + 1]; a.act = m->activation;
-    }
-    a.M = n; a.N = m->dims[l + 1]; a.K = m->dims[l]; a.G = G;
-    IL_TRY(launch_gemm(h, a, stream));
+    IL_TRY(launch_gemm(h, layer_args(l), stream));
   }
   return 0;
 }

@@ -53,16 +53,27 @@ constexpr int A_BYTES = BM * BK * 4;                                 // 8 KB per
 // Per-CTA geometry for CG = 1 (one CTA computes a 128 x 256 tile) and CG = 2 (a CTA pair computes 256 x 256 with
 // tcgen05.mma.cta_group::2: each CTA stages its own 128 rows of A and HALF of B, i.e. 128 of the 256 output columns'
 // operand rows, so per-CTA shared-memory and L2 traffic per flop drop by a third and the rings get deeper).
-template <int CG>
+// FUSE (pair mode only): the A operand is not loaded but COMPUTED by the producers — the previous (first) MLP layer
+// relu(X W1^T + b1) with K0 <= 16 input columns, evaluated chunk by chunk straight into the swizzled operand slot — so
+// the first hidden activation never round-trips HBM. The raw ring then carries only B (the weights), and the computed
+// hi tile of A lives next to the lo tiles in the short second ring.
+constexpr int L1_MAXK = 16, L1_ROWS = 256;
+constexpr int L1_W_BYTES = L1_ROWS * L1_MAXK * 4, L1_B_BYTES = L1_ROWS * 4;
+template <int CG, bool FUSE = false>
 struct Geo {
+  static_assert(!FUSE || CG == 2, "the fused first layer is implemented for CTA pairs");
   static constexpr int BNL = BN / CG;                                // rows of the B operand tile staged by this CTA
   static constexpr int B_BYTES = BNL * BK * 4;                       // 16 KB / 8 KB
-  static constexpr int SLOT_BYTES = A_BYTES + B_BYTES;               // one k-block of A then B: 24 KB / 16 KB
-  static constexpr int NH = CG == 1 ? IL_TC_NH : 9, NL = CG == 1 ? IL_TC_NL : 3;
-  static constexpr int RING_BYTES = (NH + NL) * SLOT_BYTES;          // 192 KB
+  static constexpr int RAW_BYTES = FUSE ? B_BYTES : A_BYTES + B_BYTES;                 // raw slot: one k-block of [A | B] (24 / 16 KB), or [B] alone
+  static constexpr int RAW_B_OFF = FUSE ? 0 : A_BYTES;
+  static constexpr int LO_BYTES = FUSE ? 2 * A_BYTES + B_BYTES : A_BYTES + B_BYTES;    // lo slot: [A_lo | B_lo] (+ [A_hi] when A is computed)
+  static constexpr int NH = FUSE ? 10 : (CG == 1 ? IL_TC_NH : 9), NL = CG == 1 ? IL_TC_NL : 3;
+  static constexpr int RING_BYTES = NH * RAW_BYTES + NL * LO_BYTES;  // 192 KB (FUSE: 152 KB)
+  static constexpr int L1_BYTES = FUSE ? 2 * (L1_W_BYTES + L1_B_BYTES) : 0;            // double-buffered W1 [256][16] (zero padded, chunk-swizzled) + b1 [256]
 };
 constexpr int RING_BYTES = Geo<1>::RING_BYTES;
 static_assert(Geo<2>::RING_BYTES <= RING_BYTES, "the pair kernel uses the same shared-memory carve-up");
+static_assert(Geo<2, true>::RING_BYTES + Geo<2, true>::L1_BYTES <= RING_BYTES, "the fused-first-layer variant fits the same carve-up");
 constexpr int EPI_LD = 33;                                           // padded row of the epilogue staging tile
 constexpr int EPI_BYTES = N_EPI_WARPS * 32 * EPI_LD * 4;
 constexpr int HEAD_MAX = 8;                                          // fused head: up to 8 output units (N = 1 critic, 2A <= 8 actor)
@@ -188,6 +199,8 @@ struct TcParams {
   float* head_out;
   int64_t head_gs, head_out_gs;  // group strides of head_w / head_b (same buffer family) and of head_out
   int head_n, store_c;           // head units (<= HEAD_MAX); store_c == 0: the hidden output itself is not needed (no backward)
+  TcFuseL1 l1;                   // FUSE: the first layer whose output is this product's A operand
+  int l1_vec;                    // W1 rows are 16-byte multiples (K0 % 4 == 0): 16-byte staging copies
 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
@@ -239,9 +252,10 @@ struct ChunkMap {  // chunk j of a thread: global chunk id ptid + j * PT over [A
 
 // EPI: 0 plain store, 1 bias + relu, 2 relu-derivative mask, 3 generic (runtime bias / activation / mask),
 //      4 bias + relu + fused linear head (the next, final layer of the MLP computed from the accumulator row in registers)
-template <int EPI, int CG>
+template <int EPI, int CG, bool FUSE = false>
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
-  constexpr int NH = Geo<CG>::NH, NL = Geo<CG>::NL, SLOT_BYTES = Geo<CG>::SLOT_BYTES, BNL = Geo<CG>::BNL;
+  using G_ = Geo<CG, FUSE>;
+  constexpr int NH = G_::NH, NL = G_::NL, RAW_BYTES = G_::RAW_BYTES, LO_BYTES = G_::LO_BYTES, RAW_B_OFF = G_::RAW_B_OFF, LO_RING = NH * G_::RAW_BYTES, BNL = G_::BNL;
   using CMap = ChunkMap<BNL>;
   constexpr int CPT = CMap::CPT;
   extern __shared__ uint8_t smem_raw[];
@@ -301,7 +315,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
     // cross-thread hazard). The tensor core reads only the top 19 bits of each 32-bit tf32 container, so the raw tile
     // is the hi operand (truncated) and lo = x - trunc_tf32(x) is exact in fp32.
     const int ptid = threadIdx.x - (N_EPI_WARPS + 1) * 32;
-    const bool a_km = g.a_kmajor != 0, b_km = g.b_kmajor != 0, split = p.split != 0;
+    const bool a_km = FUSE || g.a_kmajor != 0, b_km = g.b_kmajor != 0, split = p.split != 0;
     CMap cm;
     cm.init(g.lda, a_km, g.ldb, b_km, ptid);
     const int64_t a_kstep = a_km ? BK : (int64_t)BK * g.lda, b_kstep = b_km ? BK : (int64_t)BK * g.ldb;  // floats per k-block
@@ -312,29 +326,85 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
     int iss_tile = gid, iss_kb = 0, iss_slot = 0;
     uint32_t iss_par = 1;  // parity to wait for on the slot's empty barrier (a fresh barrier passes parity 1)
     const float *iss_a = nullptr, *iss_b = nullptr;
+    // FUSE: first-layer parameters of the tile's group are staged (double-buffered) with the copies of the tile's first
+    // k-block, so they have landed when that k-block's commit group has; W1 row k = 64 bytes, 16-byte chunk q at q ^ ((k >> 2) & 3)
+    constexpr int NA = FUSE ? A_CHUNKS / PT : 0;       // chunks of the (computed, not copied) A tile per thread
+    static_assert(!FUSE || (A_SPLIT_STATIC && NA == 2 && KM_CHUNKS == 4 && PT == 256), "fused first layer: 2 A chunks per producer thread (rows r and r + 64, same chunk)");
+    const uint32_t l1s = stage0 + (uint32_t)G_::RING_BYTES;   // W1s[2] then b1s[2]
+    uint32_t iss_buf = 0;
     auto issue = [&]() {  // async copies of this CTA's next k-block into the next raw slot
       if (iss_kb == 0) {
         const int grp = iss_tile / p.tiles_m, m0 = (iss_tile % p.tiles_m) * (BM * CG) + (int)rank * BM, n0 = (int)rank * BNL;
-        iss_a = g.A + (int64_t)(grp / g.a_gdiv) * g.a_gs + (a_km ? (int64_t)m0 * g.lda : (int64_t)m0);
+        if (!FUSE) iss_a = g.A + (int64_t)(grp / g.a_gdiv) * g.a_gs + (a_km ? (int64_t)m0 * g.lda : (int64_t)m0);
         iss_b = g.B + (int64_t)(grp / g.b_gdiv) * g.b_gs + (b_km ? (int64_t)n0 * g.ldb : (int64_t)n0);  // this CTA's rows of the B operand
       }
       const float* A = iss_a;
       const float* B = iss_b;
       iss_a += a_kstep;
       iss_b += b_kstep;
-      if (++iss_kb == nkb) { iss_kb = 0; iss_tile += n_groups; }
       if (lane == 0) mbar_wait(empty_bar(iss_slot), iss_par);
       __syncwarp();
-      const uint32_t st = stage0 + iss_slot * SLOT_BYTES;
+      const uint32_t st = stage0 + iss_slot * RAW_BYTES;
       if (++iss_slot == NH) { iss_slot = 0; iss_par ^= 1u; }
+      if (FUSE) {
+        if (iss_kb == 0) {
+          const int grp = iss_tile / p.tiles_m, xk = p.l1.x_k;
+          const float* w1 = p.l1.w1 + (int64_t)grp * p.l1.gs;
+          const uint32_t wdst = l1s + iss_buf * (uint32_t)L1_W_BYTES;
+          if (p.l1_vec) {
+            const int cpr = xk >> 2, n16 = g.K * cpr;
+            for (int i = ptid; i < n16; i += PT) {
+              const int k = i / cpr, q = i - k * cpr;
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wdst + (uint32_t)(k * 64 + ((q ^ ((k >> 2) & 3)) << 4))), "l"(w1 + (int64_t)k * xk + q * 4) : "memory");
+            }
+          } else {
+            const int n4 = g.K * xk;
+            for (int i = ptid; i < n4; i += PT) {
+              const int k = i / xk, j = i - k * xk;
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(wdst + (uint32_t)(k * 64 + (((j >> 2) ^ ((k >> 2) & 3)) << 4) + ((j & 3) << 2))), "l"(w1 + i) : "memory");
+            }
+          }
+          if (ptid * 4 < g.K)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(l1s + 2u * L1_W_BYTES + iss_buf * (uint32_t)L1_B_BYTES + (uint32_t)ptid * 16u),
+                         "l"(p.l1.b1 + (int64_t)grp * p.l1.gs + ptid * 4) : "memory");
+          iss_buf ^= 1u;
+        }
 #pragma unroll
-      for (int j = 0; j < CPT; ++j) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + cm.soff[j]), "l"((cm.is_a(j) ? A : B) + cm.goff[j]) : "memory");
+        for (int j = NA; j < CPT; ++j) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + cm.soff[j] - (uint32_t)A_BYTES), "l"(B + cm.goff[j]) : "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + cm.soff[j]), "l"((cm.is_a(j) ? A : B) + cm.goff[j]) : "memory");
+      }
       asm volatile("cp.async.commit_group;" ::: "memory");
+      if (++iss_kb == nkb) { iss_kb = 0; iss_tile += n_groups; }
     };
     auto lds128 = [&](uint32_t addr, uint32_t (&v)[4]) {
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
     };
     auto lo_of = [](uint32_t x) { return __float_as_uint(__uint_as_float(x) - __uint_as_float(x & 0xFFFFE000u)); };
+    // FUSE: per-tile state of the computed A operand — this thread's two input rows (registers), the staging buffer parity
+    // and the optional global store of the first hidden activation
+    float x0[L1_MAXK], x1[L1_MAXK];
+    const int fr = ptid >> 2, fc = ptid & 3;   // A chunks of this thread: rows fr and fr + 64 of the CTA's 128, 16-byte chunk fc of the k-block
+    int cons_tile = gid, cons_kb = 0;
+    uint32_t cons_buf = 0;
+    float* hstore = nullptr;
+    auto load_x = [&](int tile) {
+      const int grp = tile / p.tiles_m, m0 = (tile % p.tiles_m) * (BM * CG) + (int)rank * BM;
+      const float* xp = p.l1.x + (int64_t)(grp / p.l1.x_gdiv) * p.l1.x_gs + (int64_t)(m0 + fr) * p.l1.x_ld;
+      const float* xq = xp + (int64_t)64 * p.l1.x_ld;
+#pragma unroll
+      for (int j = 0; j < L1_MAXK; ++j) {
+        x0[j] = j < p.l1.x_k ? __ldg(xp + j) : 0.f;
+        x1[j] = j < p.l1.x_k ? __ldg(xq + j) : 0.f;
+      }
+    };
+    if (FUSE) {
+      // pad columns (j >= K0) of the W1 staging buffers are never written by the copies: zero them once, before any copy is issued
+      for (int i = ptid; i < 2 * L1_W_BYTES / 16; i += PT) sts128(l1s + (uint32_t)i * 16u, 0u, 0u, 0u, 0u);
+      asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");
+      if (total_kb > 0) load_x(gid);
+    }
     // NH - 1 k-blocks of copies are kept in flight; one commit group per loop iteration (empty at the tail) keeps the
     // wait_group bookkeeping uniform
     for (int i = 0; i < NH - 1; ++i) {
@@ -345,14 +415,71 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
     uint32_t lo_par = 1;
     for (int idx = 0; idx < total_kb; ++idx) {
       asm volatile("cp.async.wait_group %0;" ::"n"(NH - 2) : "memory");  // this thread's copies of k-block idx have landed
-      const uint32_t st = stage0 + hs * SLOT_BYTES;
-      if (split) {  // all loads first (independent, in flight together), then the lo tiles into the next lo slot
+      const uint32_t st = stage0 + hs * RAW_BYTES;
+      if (FUSE) {
+        if (cons_kb == 0) {
+          // every producer's staging copies of this tile's W1 / b1 have landed (they share the commit group of k-block 0)
+          asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");
+          if (p.l1.store) {
+            const int grp = cons_tile / p.tiles_m, m0 = (cons_tile % p.tiles_m) * (BM * CG) + (int)rank * BM;
+            hstore = p.l1.store + (int64_t)grp * p.l1.store_gs + (int64_t)(m0 + fr) * g.K + fc * 4;
+          }
+        }
+        // A chunk values: relu(b1[k] + sum_j x[j] W1[k][j]) for k = 16 kb + 4 fc + {0..3}, rows fr and fr + 64
+        const uint32_t wb = l1s + cons_buf * (uint32_t)L1_W_BYTES + (uint32_t)((cons_kb * 16 + fc * 4) * 64);
+        const int np = (p.l1.x_k + 3) >> 2;
+        uint32_t bq[4];
+        lds128(l1s + 2u * L1_W_BYTES + cons_buf * (uint32_t)L1_B_BYTES + (uint32_t)((cons_kb * 16 + fc * 4) * 4), bq);
+        uint32_t a0[4], a1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float s0 = __uint_as_float(bq[q]), s1 = s0;
+#pragma unroll
+          for (int c4 = 0; c4 < L1_MAXK / 4; ++c4) {
+            if (c4 < np) {
+              uint32_t w[4];
+              lds128(wb + (uint32_t)(q * 64 + ((c4 ^ fc) << 4)), w);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                s0 = fmaf(x0[c4 * 4 + e], __uint_as_float(w[e]), s0);
+                s1 = fmaf(x1[c4 * 4 + e], __uint_as_float(w[e]), s1);
+              }
+            }
+          }
+          a0[q] = __float_as_uint(fmaxf(s0, 0.f));
+          a1[q] = __float_as_uint(fmaxf(s1, 0.f));
+        }
+        if (++cons_kb == nkb) {  // the input rows of the next tile load while this k-block is finished
+          cons_kb = 0; cons_tile += n_groups; cons_buf ^= 1u;
+          if (idx + 1 < total_kb) load_x(cons_tile);
+        }
+        uint32_t v[CPT][4];
+#pragma unroll
+        for (int j = NA; j < CPT; ++j) lds128(st + cm.soff[j] - (uint32_t)A_BYTES, v[j]);
+        if (lane == 0) mbar_wait(lo_empty_bar(ls), lo_par);  // the MMAs that read this slot NL k-blocks ago are done
+        __syncwarp();
+        const uint32_t lo = stage0 + LO_RING + ls * LO_BYTES, ahi = lo + (uint32_t)(A_BYTES + G_::B_BYTES);
+        if (++ls == NL) { ls = 0; lo_par ^= 1u; }
+        sts128(ahi + cm.soff[0], a0[0], a0[1], a0[2], a0[3]);
+        sts128(ahi + cm.soff[1], a1[0], a1[1], a1[2], a1[3]);
+        if (split) {
+          sts128(lo + cm.soff[0], lo_of(a0[0]), lo_of(a0[1]), lo_of(a0[2]), lo_of(a0[3]));
+          sts128(lo + cm.soff[1], lo_of(a1[0]), lo_of(a1[1]), lo_of(a1[2]), lo_of(a1[3]));
+#pragma unroll
+          for (int j = NA; j < CPT; ++j) sts128(lo + cm.soff[j], lo_of(v[j][0]), lo_of(v[j][1]), lo_of(v[j][2]), lo_of(v[j][3]));
+        }
+        if (hstore) {  // the first hidden activation, for the backward pass
+          *reinterpret_cast<uint4*>(hstore) = make_uint4(a0[0], a0[1], a0[2], a0[3]);
+          *reinterpret_cast<uint4*>(hstore + (int64_t)64 * g.K) = make_uint4(a1[0], a1[1], a1[2], a1[3]);
+          hstore += BK;
+        }
+      } else if (split) {  // all loads first (independent, in flight together), then the lo tiles into the next lo slot
         uint32_t v[CPT][4];
 #pragma unroll
         for (int j = 0; j < CPT; ++j) lds128(st + cm.soff[j], v[j]);
         if (lane == 0) mbar_wait(lo_empty_bar(ls), lo_par);  // the MMAs that read this lo slot NL k-blocks ago are done
         __syncwarp();
-        const uint32_t lo = stage0 + (NH + ls) * SLOT_BYTES;
+        const uint32_t lo = stage0 + LO_RING + ls * LO_BYTES;
         if (++ls == NL) { ls = 0; lo_par ^= 1u; }
 #pragma unroll
         for (int j = 0; j < CPT; ++j) sts128(lo + cm.soff[j], lo_of(v[j][0]), lo_of(v[j][1]), lo_of(v[j][2]), lo_of(v[j][3]));
@@ -374,7 +501,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
     if (rank == 0) {  // in a CTA pair only the leader CTA issues (for both)
     // InstrDescriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), a_major bit 15, b_major bit 16 (1 = MN-major),
     // N>>3 at bit 17, M>>4 at bit 24
-    const bool a_km = g.a_kmajor != 0, b_km = g.b_kmajor != 0, split = p.split != 0;
+    const bool a_km = FUSE || g.a_kmajor != 0, b_km = g.b_kmajor != 0, split = p.split != 0;
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((a_km ? 0u : 1u) << 15) | ((b_km ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
     // per-MMA (K = 8 tf32) advance: 32 bytes inside the swizzled 64-byte row (K-major) or two 4-k groups (MN-major)
     const uint32_t a_lbo = a_km ? 16u : 512u, a_sbo = a_km ? 8u * KM_ROW_BYTES : (uint32_t)(BM / 32) * 512u, a_kadv = a_km ? 32u : 2u * a_sbo, a_lt = a_km ? KM_LAYOUT : 1u;
@@ -394,7 +521,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
         if (CG == 1) mbar_wait(full_bar(hs), hpar);
         else mbar_wait_cluster(full_bar(hs), hpar);
         tc_fence_after();
-        const uint32_t a_hi = ring0 + hs * SLOT_BYTES, b_hi = a_hi + A_BYTES, a_lo = ring0 + (NH + ls) * SLOT_BYTES, b_lo = a_lo + A_BYTES;
+        const uint32_t a_lo = ring0 + LO_RING + ls * LO_BYTES, b_lo = a_lo + A_BYTES, b_hi = ring0 + hs * RAW_BYTES + RAW_B_OFF;
+        const uint32_t a_hi = FUSE ? a_lo + (uint32_t)(A_BYTES + G_::B_BYTES) : ring0 + hs * RAW_BYTES;
 #pragma unroll
         for (int kk = 0; kk < BK / 8; ++kk) {
           const uint64_t ah = a_desc0 + ((a_hi + kk * a_kadv) >> 4), al = a_desc0 + ((a_lo + kk * a_kadv) >> 4);
@@ -409,7 +537,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
           }
         }
         tc_commit<CG>(empty_bar(hs), leader);  // frees the raw slot once these MMAs have read it (implicit before_thread_sync fence)
-        if (split) { tc_commit<CG>(lo_empty_bar(ls), leader); if (++ls == NL) ls = 0; }
+        if (split || FUSE) { tc_commit<CG>(lo_empty_bar(ls), leader); if (++ls == NL) ls = 0; }
         if (++hs == NH) { hs = 0; hpar ^= 1u; }
       }
       tc_commit<CG>(tfull_bar(acc), leader);  // accumulator complete -> epilogue
@@ -549,22 +677,23 @@ bool tc_gemm_eligible(const GemmArgs& a) {
   return true;
 }
 
-template <int EPI, int CG>
+template <int EPI, int CG, bool FUSE = false>
 int tc_set_attr() {
-  IL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  IL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI, CG, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   return 0;
 }
 
 int tc_gemm_init() {
   IL_TRY((tc_set_attr<0, 1>())); IL_TRY((tc_set_attr<1, 1>())); IL_TRY((tc_set_attr<2, 1>())); IL_TRY((tc_set_attr<3, 1>())); IL_TRY((tc_set_attr<4, 1>()));
   IL_TRY((tc_set_attr<0, 2>())); IL_TRY((tc_set_attr<1, 2>())); IL_TRY((tc_set_attr<2, 2>())); IL_TRY((tc_set_attr<3, 2>())); IL_TRY((tc_set_attr<4, 2>()));
+  IL_TRY((tc_set_attr<4, 2, true>()));
   return 0;
 }
 
 // CTA pairs (tcgen05.mma.cta_group::2, one 256 x 256 tile per 2-CTA cluster) whenever the rows come in multiples of 256
 static bool tc_use_pairs(const il_handle* h, const GemmArgs& a) { return h->tc_pairs && a.M % (2 * BM) == 0 && h->sm_count >= 2; }
 
-template <int EPI>
+template <int EPI, bool FUSE = false>
 static int tc_launch(il_handle* h, TcParams& p, cudaStream_t stream) {
   const GemmArgs& a = p.g;
   const bool pairs = tc_use_pairs(h, a);
@@ -572,6 +701,7 @@ static int tc_launch(il_handle* h, TcParams& p, cudaStream_t stream) {
   p.tiles_m = a.M / (BM * cg);
   p.n_tiles = a.G * p.tiles_m;
   if (!pairs) {
+    IL_CHECK(!FUSE, "tc_gemm: the fused first layer needs CTA pairs (rows %% 256 == 0)");
     const int groups = p.n_tiles < h->sm_count ? p.n_tiles : h->sm_count;
     IL_LAUNCH(h, (tc_gemm_kernel<EPI, 1>), groups, THREADS, SMEM_BYTES, stream, p);
     return 0;
@@ -590,14 +720,14 @@ static int tc_launch(il_handle* h, TcParams& p, cudaStream_t stream) {
   // have a single enabled SM fewer than sm_count / 2 clusters fit at once (a second wave would double the time).
   if (h->tc_pair_groups == 0) {
     int n = 0;
-    IL_CUDA(cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel<EPI, 2>, &cfg));
+    IL_CUDA(cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel<EPI, 2, FUSE>, &cfg));
     IL_CHECK(n >= 1, "tc_gemm: no 2-CTA cluster of the tcgen05 kernel fits on this device");
     h->tc_pair_groups = n;
     if (getenv("IL_TC_VERBOSE")) fprintf(stderr, "[il_b200] tcgen05 pair kernel: %d co-resident 2-CTA clusters on %d SMs\n", n, h->sm_count);
   }
   const int groups = p.n_tiles < h->tc_pair_groups ? p.n_tiles : h->tc_pair_groups;
   cfg.gridDim = dim3(groups * 2);
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<EPI, 2>, p);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<EPI, 2, FUSE>, p);
   h->launches++;
   if (e != cudaSuccess) IL_FAIL("cluster launch of tc_gemm_kernel<%d, 2> failed: %s", EPI, cudaGetErrorString(e));
   return 0;
@@ -607,21 +737,40 @@ bool tc_head_fusable(const il_handle* h, const GemmArgs& a, int head_n) {
   return h->gemm_mode != IL_GEMM_FP32 && tc_gemm_eligible(a) && a.bias && a.act == IL_ACT_RELU && !a.mask && !a.colsum && head_n >= 1 && head_n <= HEAD_MAX;
 }
 
+// The first layer can be computed by the producers when the dense product runs on CTA pairs and the staging buffers fit:
+// K0 <= 16 input columns, hidden width (the K of the dense product) <= 256 and deep enough to cover the load pipeline.
+bool tc_l1_fusable(const il_handle* h, const GemmArgs& a, int x_k) {
+  return h->tc_fuse_l1 && tc_use_pairs(h, a) && x_k >= 1 && x_k <= L1_MAXK && a.K <= L1_ROWS && a.K / BK >= Geo<2, true>::NH && a.a_kmajor;
+}
+
 int launch_tc_gemm_head(il_handle* h, const GemmArgs& a, const float* head_w, const float* head_b, int64_t head_gs, int head_n, float* head_out, int64_t head_out_gs, int store_c,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, const TcFuseL1* l1) {
   IL_CHECK(tc_head_fusable(h, a, head_n), "tc_gemm_head: not fusable");
   TcParams p{};
   p.g = a;
   p.split = h->gemm_mode == IL_GEMM_TF32X3 ? 1 : 0;
   p.head_w = head_w; p.head_b = head_b; p.head_out = head_out; p.head_gs = head_gs; p.head_out_gs = head_out_gs; p.head_n = head_n; p.store_c = store_c;
+  double bytes = gemm_algorithmic_bytes(a, store_c != 0) + 4.0 * a.G * (double)a.M * head_n, flops = 2.0 * a.M * a.N * a.K * a.G;
+  if (l1) {
+    IL_CHECK(tc_l1_fusable(h, a, l1->x_k), "tc_gemm_head: first layer not fusable (K0=%d)", l1->x_k);
+    IL_CHECK(l1->x && l1->w1 && l1->b1 && (reinterpret_cast<uintptr_t>(l1->b1) & 15) == 0 && l1->gs % 4 == 0, "tc_gemm_head: bad first-layer buffers");
+    IL_CHECK(!l1->store || ((reinterpret_cast<uintptr_t>(l1->store) & 15) == 0 && l1->store_gs % 4 == 0), "tc_gemm_head: unaligned hidden store");
+    p.l1 = *l1;
+    p.l1_vec = (l1->x_k % 4 == 0 && (reinterpret_cast<uintptr_t>(l1->w1) & 15) == 0) ? 1 : 0;
+    // algorithmic traffic: the A operand is not read; X, W1, b1 are, and the hidden store (if any) is written
+    const double gx = (a.G + l1->x_gdiv - 1) / l1->x_gdiv;
+    bytes += -4.0 * a.G * (double)a.M * a.K + 4.0 * (gx * a.M * l1->x_k + (double)a.G * a.K * (l1->x_k + 1)) + (l1->store ? 4.0 * a.G * (double)a.M * a.K : 0.0);
+    flops += 2.0 * a.G * (double)a.M * a.K * l1->x_k;
+  }
+  auto run = [&]() { return l1 ? tc_launch<4, true>(h, p, stream) : tc_launch<4>(h, p, stream); };
   if (h->profiling) {  // the fused layer-2 + head launches are dense-layer launches too (head flops / bytes are negligible)
     ProfiledLaunch pl;
-    IL_TRY(profile_open(h, &pl, 2.0 * a.M * a.N * a.K * a.G, gemm_algorithmic_bytes(a, store_c != 0) + 4.0 * a.G * (double)a.M * head_n, stream));
-    const int rc = tc_launch<4>(h, p, stream);
+    IL_TRY(profile_open(h, &pl, flops, bytes, stream));
+    const int rc = run();
     IL_TRY(profile_close(h, &pl, stream));
     return rc;
   }
-  return tc_launch<4>(h, p, stream);
+  return run();
 }
 
 int launch_tc_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {

@@ -59,7 +59,7 @@ class Trainer:
     self.device = dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
     self.lib, self.h = _lib.lib(), _lib.handle(dev.index)
     _lib.check(self.lib.il_set_gemm_mode(self.h, _lib.GEMM_MODE[cfg.get('gemm_mode', 'fp32')]))
-    seed = cfg.seed + seed_offset
+    self.seed = seed = cfg.seed + seed_offset
     np.random.seed(seed)
     torch.manual_seed(seed)  # train.py:51-52
     self.algorithm = cfg.algorithm
@@ -84,6 +84,11 @@ class Trainer:
     lr, wd = cfg.training.learning_rate, cfg.training.weight_decay
     self.actor_optimiser, self.critic_optimiser = AdamW(self.actor.parameters(), lr=lr, weight_decay=wd), AdamW(self.critic.parameters(), lr=lr, weight_decay=wd)
     self.temperature_optimiser = Adam([self.log_alpha], lr=lr)
+    need = R * int(cfg.memory.size) * _lib.py_row_layout(S, A)[1] * 4
+    free = torch.cuda.mem_get_info(dev)[0]
+    if need > 0.9 * free:
+      raise MemoryError(f'replay rings need {need / 2**30:.1f} GiB ({R} replicas x memory.size {cfg.memory.size} rows x {_lib.py_row_layout(S, A)[1] * 4} B) but only {free / 2**30:.1f} GiB '
+                        f'are free on {dev}; lower memory.size (train.py:30 caps it at `steps`) or `replicas`')
     self.memory = ReplayMemory(cfg.memory.size, S, A, absorbing, replicas=R, device=dev)
     self.memory.seed = seed
     # train.py:70-84
@@ -248,7 +253,7 @@ class Trainer:
         if getattr(self, '_pin', None) is None:
           self._pin = [torch.empty(2, self.R, self.B, pin_memory=True) for _ in range(2)]  # double-buffered pinned staging
           self._pin_ev = [None, None]
-          self._host_rng = np.random.default_rng(self.cfg.seed)
+          self._host_rng = np.random.default_rng(self.seed)  # per-rank stream: seed + first replica of this shard
         slot = self.step & 1
         if self._pin_ev[slot] is not None: self._pin_ev[slot].synchronize()  # the H2D copy that last used this buffer is done
         self._host_rng.random(out=self._pin[slot].numpy(), dtype=np.float32)
@@ -309,7 +314,7 @@ def train(cfg: Config, file_prefix: str = '') -> float:
       return float(np.mean(normalized))
   for step in range(1, cfg.steps + 1):
     trainer.train_step()
-    if cfg.logging.interval > 0 and step % cfg.logging.interval == 0 and trainer.updates > 0: trainer.log_aux()
+    if cfg.logging.interval > 0 and step % cfg.logging.interval == 0 and trainer._will_update(step): trainer.log_aux()  # train.py:205: only inside the update branch
     if step % cfg.evaluation.interval == 0 and not cfg.check_time_usage:  # train.py:213
       returns = trainer.evaluate()
       mean, std, n = distributed.return_statistics(returns)

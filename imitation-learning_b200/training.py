@@ -13,15 +13,17 @@ from .memory import TransitionBatch
 from .models import GAILDiscriminator, SoftActor, TwinCritic, default_rng
 from .optim import Adam
 
-_workspaces: Dict[Tuple[int, str], Tensor] = {}
-
-
-def _workspace(key: str, nbytes: int, device) -> Tensor:
-  k = (torch.device(device).index or 0, key)
-  ws = _workspaces.get(k)
+def _workspace(owner, key: str, nbytes: int, device) -> Tensor:
+  """Scratch for one fused update, owned by the module that is updated (so two trainers never share it and a buffer whose
+  address is baked into a captured CUDA graph is never freed behind the graph's back: a larger request allocates a new
+  buffer and the old one stays alive in `owner._ws_retired`). Zero-initialised once: the 4 / 32-float alignment pads of
+  the flat gradient buffers are never written by the kernels but are streamed by the AdamW pass."""
+  cache = owner.__dict__.setdefault('_ws_cache', {})
+  ws = cache.get(key)
   if ws is None or ws.numel() < nbytes:
-    ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
-    _workspaces[k] = ws
+    if ws is not None: owner.__dict__.setdefault('_ws_retired', []).append(ws)
+    ws = torch.zeros(max(nbytes, 256), dtype=torch.uint8, device=device)
+    cache[key] = ws
   return ws
 
 
@@ -58,7 +60,7 @@ def sac_update(actor: SoftActor, critic: TwinCritic, log_alpha: Tensor, target_c
   a.discount, a.entropy_target, a.polyak_factor = discount, entropy_target, polyak_factor
   a.out_log_probs, a.out_q_values, a.out_losses = out['log_probs'].data_ptr(), out['q_values'].data_ptr(), out['losses'].data_ptr()
   need = _lib.lib().il_sac_workspace_bytes(C.byref(a))
-  ws = _workspace('sac', need, device)
+  ws = _workspace(actor, 'sac', need, device)
   a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
   _lib.check(_lib.lib().il_sac_update(_lib.handle(), C.byref(a), _lib.stream()))
   sq = (lambda t: t[0]) if R == 1 else (lambda t: t)
@@ -96,7 +98,7 @@ def behavioural_cloning_update(actor: SoftActor, expert_transition, actor_optimi
   a = _lib.BcArgs()
   a.actor, a.opt, a.batch, a.R, a.out_loss = actor.mlp.c_struct(), actor_optimiser.c_struct(), batch.c_struct(), R, _lib.ptr(out_loss)
   need = _lib.lib().il_bc_workspace_bytes(C.byref(a))
-  ws = _workspace('bc', need, device)
+  ws = _workspace(actor, 'bc', need, device)
   a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
   _lib.check(_lib.lib().il_bc_update(_lib.handle(), C.byref(a), _lib.stream()))
 

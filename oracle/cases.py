@@ -32,6 +32,12 @@ CASES: Dict[str, dict] = {
   'gail_pugail': dict(kind='gail', S=12, A=3, H=64, B=64, steps=2, seed=33, spectral_norm=True, grad_penalty=1.0, entropy_bonus=0.0, loss='PUGAIL', lr=1e-3, wd=0.0, reward='FAIRL'),
   'gail_mixup': dict(kind='gail', S=12, A=3, H=64, B=64, steps=2, seed=34, spectral_norm=True, grad_penalty=0.0, entropy_bonus=0.0, loss='Mixup', lr=1e-3, wd=0.0, reward='AIRL'),
   'gail_ant': dict(kind='gail', S=112, A=8, H=64, B=96, steps=2, seed=35, spectral_norm=True, grad_penalty=1.0, entropy_bonus=0.05, loss='BCE', lr=3e-5, wd=10.0, reward='AIRL'),
+  # the published tuned configurations (conf/optimised_hyperparameters/GAIL_{5,25}_trajectories.yaml): B = 1024 with Mixup + gradient
+  # penalty + entropy bonus + spectral norm together; a 128-wide discriminator with the GAIL reward
+  'gail_tuned5': dict(kind='gail', S=12, A=3, H=64, B=1024, steps=2, seed=301, spectral_norm=True, grad_penalty=0.2799364347010851, entropy_bonus=0.24145587952807546, loss='Mixup',
+                      lr=0.0002778119723405689, wd=8.46588535234332, reward='AIRL'),
+  'gail_tuned25': dict(kind='gail', S=12, A=3, H=128, B=256, steps=2, seed=302, spectral_norm=True, grad_penalty=0.3203035416081548, entropy_bonus=0.015492475591599941, loss='BCE',
+                       lr=7.299440972507e-05, wd=6.3524082861840725, reward='GAIL'),
   'gmmil_ant': dict(kind='gmmil', S=112, A=8, B=300, seed=43),
   # SURVEY §8f row 3 variants (oracle pinned; CUDA path is next-round work): shaping f = g(s,a) + (1-t)(gamma h(s') - h(s)) with a
   # linear g (models.py:157-160), subtract_log_policy (:175), deeper / tanh / sigmoid / state-only discriminators

@@ -82,3 +82,27 @@ def test_golden_cases_with_tensor_core_engine(name, monkeypatch):
   keys = {k.split('@')[0] for k in g} & set(out)
   bad = cases.compare(g, out, rtol=2e-4, atol=2e-5, keys=keys)
   assert not bad, '\n'.join(bad)
+
+
+def test_fused_first_layer_is_schedule_independent():
+  """The producers of the tensor-core engine compute the first MLP layer (K0 = 12 / 15 columns) chunk by chunk into the
+  operand tile of the second. 80 replicas with IDENTICAL inputs put several tiles on every CTA pair (persistent loop,
+  double-buffered W1 staging, per-tile input rows): every replica must reproduce replica 0 bit for bit, and replica 0
+  must match the reference fixture."""
+  from conftest import load_golden
+  from cuda_cases import run_cuda
+  from il_b200 import _lib
+  from oracle import cases
+  lib, h = _lib.lib(), _lib.handle()
+  inp = cases.make_inputs('sac_hopper')
+  _lib.check(lib.il_set_gemm_mode(h, _lib.GEMM_MODE['tf32x3']))
+  try:
+    outs = run_cuda('sac_hopper', [inp] * 80)
+  finally:
+    _lib.check(lib.il_set_gemm_mode(h, _lib.GEMM_MODE['fp32']))
+  g = load_golden('sac_hopper')
+  keys = {k.split('@')[0] for k in g} & set(outs[0])
+  bad = cases.compare(g, outs[0], rtol=2e-4, atol=2e-5, keys=keys)
+  assert not bad, '\n'.join(bad)
+  for r in (1, 37, 73, 74, 79):
+    for k in keys: assert np.array_equal(outs[r][k], outs[0][k]), f'replica {r} differs from replica 0 in {k}'

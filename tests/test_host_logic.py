@@ -145,3 +145,14 @@ def test_shard_and_statistics_helpers():
     assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
     sizes = [hi - lo for lo, hi in spans]
     assert max(sizes) - min(sizes) <= 1
+
+
+def test_cli_overrides_parse_like_hydra():
+  """`training.learning_rate=3e-4` and `imitation.nonnegative_margin=inf` must arrive as floats (YAML 1.1 reads them as strings)."""
+  from il_b200.config import load_config
+  cfg = load_config(['algorithm=GAIL', 'env=hopper', 'training.learning_rate=3e-4', 'imitation.nonnegative_margin=inf', 'steps=1e5', 'training.batch_size=512',
+                     'imitation.spectral_norm=false', 'imitation.loss_function=PUGAIL', 'imitation.discriminator.reward_function=FAIRL'])
+  assert isinstance(cfg.training.learning_rate, float) and cfg.training.learning_rate == 3e-4
+  assert cfg.imitation.nonnegative_margin == float('inf')
+  assert cfg.steps == 1e5 and cfg.training.batch_size == 512 and isinstance(cfg.training.batch_size, int)
+  assert cfg.imitation.spectral_norm is False and cfg.imitation.loss_function == 'PUGAIL' and cfg.imitation.discriminator.reward_function == 'FAIRL'
