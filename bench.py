@@ -33,6 +33,10 @@ def parse():
   p.add_argument('--start', type=int, default=300, help='update-free prefill steps before the timed region (training.start)')
   p.add_argument('--gemm-mode', default=os.environ.get('IL_GEMM_MODE', 'tf32x3'), choices=['fp32', 'tf32x3', 'tf32'],
                  help='arithmetic of the 256x256 layers: tf32x3 = 3xTF32 split on tcgen05 (fp32-level accuracy, parity-tested), fp32 = FFMA engine')
+  p.add_argument('--total-replicas', type=int, default=1024, help='strong-scaling record: this many replica-envs split over the N ranks (SURVEY §8d config 2)')
+  p.add_argument('--eval-episodes', type=int, default=30, help='eval record: greedy episodes per replica (conf/train_config.yaml:23)')
+  p.add_argument('--no-strong', action='store_true')
+  p.add_argument('--no-eval', action='store_true')
   p.add_argument('--no-e2e', action='store_true')
   p.add_argument('--no-cpu-baseline', action='store_true')
   p.add_argument('--ref-steps-per-step', type=int, default=10, help='reference arm: oracle loop iterations per bench step and worker')
@@ -159,19 +163,20 @@ def run_b200(a):
   for _ in range(W): tr.train_step()            # warm-up incl. CUDA-graph capture
   torch.cuda.synchronize()
 
-  def timed(n, e2e=False):
+  def timed(n, e2e=False, trainer=None):
+    tr_ = tr if trainer is None else trainer
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # e2e: every step's results (losses, returns) are copied device -> pinned host memory and consumed one step later,
     # so the read-back of step i overlaps the kernels of step i+1 (the host never skips a step's results)
-    outs = (tr.sac_out['losses'], tr.gail_losses, tr.last_return)
+    outs = (tr_.sac_out['losses'], tr_.gail_losses, tr_.last_return)
     pinned = [[torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs] for _ in range(2)]
     done = [None, None]
     consumed = 0.0
     distributed.barrier(); torch.cuda.synchronize()
-    launches0 = tr.total_launches()
+    launches0 = tr_.total_launches()
     ev0.record()
     for i in range(n):
-      tr.train_step()
+      tr_.train_step()
       if e2e:
         slot = i & 1
         for dst, src in zip(pinned[slot], outs): dst.copy_(src, non_blocking=True)
@@ -184,7 +189,7 @@ def run_b200(a):
     torch.cuda.synchronize(); distributed.barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], device='cuda')
     if world > 1: dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    return float(ms.item()), tr.total_launches() - launches0
+    return float(ms.item()), tr_.total_launches() - launches0
 
   clocks.mark()
   ms, launches = timed(K)
@@ -209,17 +214,90 @@ def run_b200(a):
     ms_e, _ = timed(K, e2e=True)
     e2e = dict(value=R * world * K / (ms_e / 1e3), unit=UNIT, h2d_bytes_per_step=2 * R * a.batch_size * 4, d2h_bytes_per_step=R * (3 + 2 + 1) * 4, ms_per_step=ms_e / K)
 
+  # ---- evaluation record ("eval excluded from the training rate and reported as eval-steps/s"): il_eval_rollout (device
+  # while-loop graph) for episodes x replicas, then the fused return reduction (stats kernel + ncclAllReduce on the same stream)
+  ev = None
+  if not a.no_eval:
+    try:
+      ev = measure_eval(tr, a, world)
+    except Exception as e:
+      ev = dict(error=str(e))
+  # ---- strong-scaling record: --total-replicas split over the ranks (at N = 1 it is the weak configuration when totals agree)
+  strong = None
+  if not a.no_strong:
+    try:
+      strong = measure_strong(a, world, rank, tr if (world == 1 and a.total_replicas == R) else None, value, ms / K, timed)
+    except Exception as e:
+      strong = dict(error=str(e))
+
   cpu = None
   if rank == 0 and world == 1 and not a.no_cpu_baseline:
-    r, procs, per_worker = cpu_reference(a, steps=4, warmup=1)
+    r, procs, per_worker = cpu_reference(a, steps=20, warmup=1)
     cpu = dict(value=r['steps_per_s'], unit=UNIT, cores=procs, kind='port',
                sample=f'{procs} single-thread processes x {per_worker} loop iterations of oracle/loop.py ({a.algorithm} {a.env}, batch {a.batch_size}) after {a.start} prefill steps')
   if rank == 0:
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
                 data='synthetic', config=workload(a), grad_updates_per_s=value, clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
-                gemm_mode=a.gemm_mode)
+                gemm_mode=a.gemm_mode, eval=ev, strong=strong)
     print(json.dumps(line), flush=True)
   distributed.barrier()
+
+
+def measure_eval(tr, a, world):
+  """Times Trainer.evaluate() (evaluation.py:11-35 for every replica: il_eval_rollout) and the return reduction (il_return_allreduce)
+  with CUDA events; max over ranks. Episodes end early in the synthetic env, so env steps are counted on the device."""
+  import torch
+  import torch.distributed as dist
+  from il_b200 import distributed
+  from il_b200.evaluation import evaluate_agent
+  E = a.eval_episodes
+  stats = {}
+  evaluate_agent(tr.actor, tr.eval_env, E, out_stats=stats)  # warm-up: builds the device graph
+  distributed.return_stats_device(torch.zeros(tr.R, E, device='cuda'))
+  distributed.barrier(); torch.cuda.synchronize()
+  e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+  e0.record()
+  returns = evaluate_agent(tr.actor, tr.eval_env, E)
+  e1.record()
+  out = distributed.return_stats_device(returns if torch.is_tensor(returns) else torch.tensor(returns, device='cuda'))
+  e2.record()
+  torch.cuda.synchronize()
+  evaluate_agent(tr.actor, tr.eval_env, E, out_stats=stats)  # same seeds are not replayed: counters of a like-for-like rollout
+  t = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2), float(stats['env_steps']), float(stats['iterations'])], device='cuda', dtype=torch.float64)
+  mx = t.clone()
+  if world > 1:
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+  rollout_ms, reduce_ms, steps_total, iters = float(mx[0]), float(mx[1]), float(t[2]), float(mx[3])
+  mean, std, n = distributed.stats_from_sums(out)
+  return dict(metric='eval_steps_per_s', value=steps_total / (rollout_ms / 1e3), unit='env-steps/s', episodes_per_replica=E, replicas_per_gpu=tr.R, env_steps=int(steps_total),
+              loop_iterations=int(iters), rollout_ms=rollout_ms, return_allreduce_us=reduce_ms * 1e3, mean_return=mean, std_return=std, episodes=n,
+              how='il_eval_rollout: one CUDA graph with a device-side WHILE node (greedy actor forward + env step per iteration, no host sync); il_return_allreduce: '
+                  'per-rank (sum, sum^2, n) kernel + ncclAllReduce on the same stream' + (' over the ranks' if world > 1 else ' (single rank: no collective)'))
+
+
+def measure_strong(a, world, rank, reuse_trainer, weak_value, weak_ms, timed):
+  """--total-replicas replica-envs split contiguously over the ranks: same K timed steps."""
+  import torch
+  from il_b200 import distributed
+  from il_b200.config import load_config
+  from il_b200.train import Trainer
+  total = a.total_replicas
+  lo, hi = distributed.shard(total, rank, world)
+  if reuse_trainer is not None:
+    return dict(total_replicas=total, replicas_per_gpu=hi - lo, value=weak_value, unit=UNIT, ms_per_step=weak_ms, note='N = 1: identical to the weak-scaling configuration above')
+  K, W = a.steps, max(a.warmup, 3)
+  total_steps = a.start + 2 * (W + K) + 64
+  cfg = load_config([f'algorithm={a.algorithm}', f'env={a.env}', f'steps={total_steps}', f'training.start={a.start}', f'training.batch_size={a.batch_size}', 'imitation.trajectories=5',
+                     f'replicas={hi - lo}', f'gemm_mode={a.gemm_mode}', f'memory.size={max(total_steps * 2, 4096)}', 'seed=0'])
+  tr = Trainer(cfg, replicas=hi - lo, seed_offset=lo, fast_init=True)
+  for _ in range(a.start - 1 + W): tr.train_step()
+  torch.cuda.synchronize()
+  ms, _ = timed(K, trainer=tr)
+  out = dict(total_replicas=total, replicas_per_gpu=hi - lo, value=total * K / (ms / 1e3), unit=UNIT, ms_per_step=ms / K)
+  del tr
+  torch.cuda.empty_cache()
+  return out
 
 
 def measure_dense_gemm(tr, a):

@@ -61,6 +61,17 @@ class GailUpdateArgs(C.Structure):
               ('nonnegative_margin', C.c_float), ('out_losses', vp), ('workspace', vp), ('workspace_bytes', C.c_int64)]
 
 
+class Gailx(C.Structure):
+  _fields_ = [('g', Mlp), ('h', Mlp), ('g_u', vp), ('g_v', vp), ('h_u', vp), ('h_v', vp), ('g_u_stride', C.c_int32), ('g_v_stride', C.c_int32), ('h_u_stride', C.c_int32),
+              ('h_v_stride', C.c_int32), ('state_only', C.c_int32), ('reward_function', C.c_int32), ('subtract_log_policy', C.c_int32), ('discount', C.c_float)]
+
+
+class GailxUpdateArgs(C.Structure):
+  _fields_ = [('disc', Gailx), ('opt', Adam), ('params_floats', C.c_int64), ('policy', Batch), ('expert', Batch), ('eps_gp', vp), ('eps_mix', vp), ('logp_policy', vp),
+              ('logp_expert', vp), ('logp_mix', vp), ('R', C.c_int32), ('loss_function', C.c_int32), ('training', C.c_int32), ('_pad', C.c_int32), ('grad_penalty', C.c_float),
+              ('entropy_bonus', C.c_float), ('pos_class_prior', C.c_float), ('nonnegative_margin', C.c_float), ('out_losses', vp), ('workspace', vp), ('workspace_bytes', C.c_int64)]
+
+
 class Pwil(C.Structure):
   _fields_ = [('atoms', vp), ('scale', vp), ('offset', vp), ('weights', vp), ('N', C.c_int32), ('d', C.c_int32), ('S', C.c_int32), ('A', C.c_int32), ('state_only', C.c_int32),
               ('time_horizon', C.c_int32), ('reward_scale', C.c_float), ('reward_bandwidth', C.c_float)]
@@ -69,6 +80,11 @@ class Pwil(C.Structure):
 class Env(C.Structure):
   _fields_ = [('M', vp), ('N', vp), ('c', vp), ('w_r', vp), ('x', vp), ('t', vp), ('obs', C.c_int32), ('act', C.c_int32), ('absorbing', C.c_int32),
               ('max_episode_steps', C.c_int32), ('early_termination', C.c_int32), ('term_threshold', C.c_float)]
+
+
+class EvalArgs(C.Structure):
+  _fields_ = [('actor', Mlp), ('env', Env), ('R', C.c_int32), ('episodes', C.c_int32), ('max_steps', C.c_int32), ('traj_T', C.c_int32), ('state', vp), ('returns', vp),
+              ('traj_states', vp), ('traj_actions', vp), ('traj_rewards', vp), ('traj_len', vp), ('out_counters', vp), ('workspace', vp), ('workspace_bytes', C.c_int64)]
 
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
@@ -105,12 +121,18 @@ SIGNATURES = {
   'il_adam_step': (C.c_int, [vp, vp, vp, P(Adam), i64, vp]),
   'il_replay_append': (C.c_int, [vp, P(Replay), C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]),
   'il_replay_wrap_absorbing': (C.c_int, [vp, P(Replay), C.c_int, vp, vp]),
+  'il_replay_transfer': (C.c_int, [vp, P(Replay), C.c_int, P(Replay), vp]),
   'il_replay_sample_indices': (C.c_int, [vp, P(Replay), C.c_int, C.c_int, vp, vp, u64, u64, vp, vp]),
   'il_replay_gather': (C.c_int, [vp, P(Replay), C.c_int, vp, P(Batch), vp]),
   'il_mix_expert_rows': (C.c_int, [vp, P(Batch), P(Batch), C.c_int, vp]),
   'il_gail_workspace_bytes': (i64, [P(GailUpdateArgs)]),
   'il_gail_update': (C.c_int, [vp, P(GailUpdateArgs), vp]),
   'il_gail_reward': (C.c_int, [vp, P(Gail), C.c_int, P(Batch), vp, i64, C.c_int, vp, vp]),
+  'il_gailx_workspace_bytes': (i64, [P(GailxUpdateArgs)]),
+  'il_gailx_update': (C.c_int, [vp, P(GailxUpdateArgs), vp]),
+  'il_gailx_reward_workspace_bytes': (i64, [P(Gailx), C.c_int, C.c_int]),
+  'il_gailx_reward': (C.c_int, [vp, P(Gailx), C.c_int, P(Batch), vp, vp, i64, C.c_int, vp, vp, i64, vp]),
+  'il_gail_mix_batch': (C.c_int, [vp, P(Batch), P(Batch), vp, C.c_int, P(Batch), vp]),
   'il_gmmil_workspace_bytes': (i64, [C.c_int, C.c_int]),
   'il_gmmil_bandwidth': (C.c_int, [vp, C.c_int, P(Batch), P(Batch), C.c_int, vp, vp, i64, vp]),
   'il_gmmil_reward': (C.c_int, [vp, C.c_int, P(Batch), P(Batch), C.c_int, vp, vp, i64, C.c_int, vp]),
@@ -121,6 +143,12 @@ SIGNATURES = {
   'il_rollout_bookkeep': (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
   'il_eval_accumulate': (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp]),
   'il_return_stats': (C.c_int, [vp, vp, i64, vp, vp]),
+  'il_eval_workspace_bytes': (i64, [P(EvalArgs)]),
+  'il_eval_rollout': (C.c_int, [vp, P(EvalArgs), vp]),
+  'il_nccl_unique_id': (C.c_int, [vp]),
+  'il_nccl_comm_create': (C.c_int, [vp, C.c_int, C.c_int, P(vp)]),
+  'il_nccl_comm_destroy': (C.c_int, [vp]),
+  'il_return_allreduce': (C.c_int, [vp, vp, vp, i64, vp, vp]),
 }
 
 _lock = threading.Lock()

@@ -40,11 +40,15 @@ extern "C" int il_create(int device, il_handle** out) {
   h->launches = 0;
   h->profiling = 0;
   h->profiled_bytes = 0.0;
+  h->eval_graph = nullptr;
+  h->build_stream = nullptr;
   *out = h;
   return 0;
 }
 
 extern "C" int il_destroy(il_handle* h) {
+  if (h) il_eval_release(h);
+  if (h && h->build_stream) cudaStreamDestroy(h->build_stream);
   delete h;
   return 0;
 }
@@ -68,6 +72,10 @@ extern "C" int il_struct_sizes(int32_t* out) {
   out[6] = (int32_t)sizeof(il_gail_update_args);
   out[7] = (int32_t)sizeof(il_pwil);
   out[8] = (int32_t)sizeof(il_env);
+  out[9] = (int32_t)sizeof(il_bc_args);
+  out[10] = (int32_t)sizeof(il_eval_args);
+  out[11] = (int32_t)sizeof(il_gailx);
+  out[12] = (int32_t)sizeof(il_gailx_update_args);
   return 0;
 }
 

@@ -26,7 +26,10 @@ struct il_handle {
   int profiling;                        // il_profile_begin/end: CUDA events around every dense-layer GEMM launch
   std::vector<ProfiledLaunch> profiled;
   double profiled_bytes;                // summed by the last il_profile_end
+  void* eval_graph;                     // cached evaluation-rollout graph (eval.cu)
+  cudaStream_t build_stream;            // private stream used only to CAPTURE graphs (the legacy default stream cannot capture)
 };
+void il_eval_release(il_handle* h);
 
 extern thread_local char g_il_error[512];
 
@@ -62,7 +65,7 @@ extern thread_local char g_il_error[512];
     if (_r != 0) return _r;   \
   } while (0)
 
-static inline int64_t il_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+__host__ __device__ static inline int64_t il_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 // ---- row layout (il_batch / il_replay) -------------------------------------------------------------------
 struct RowLayout {
@@ -86,7 +89,7 @@ __host__ __device__ inline RowLayout row_layout(int S, int A) {
 struct MlpOffsets {
   int64_t w[IL_MAX_LAYERS], b[IL_MAX_LAYERS], total;
 };
-static inline MlpOffsets mlp_offsets(const int32_t* dims, int n_layers) {
+__host__ __device__ static inline MlpOffsets mlp_offsets(const int32_t* dims, int n_layers) {
   MlpOffsets o;
   int64_t off = 0;
   for (int l = 0; l < n_layers; ++l) {

@@ -1,11 +1,9 @@
 // Synthetic batched locomotion-shaped environment (stands in for gym/MuJoCo behind
 // environments.py:29-40) + batched-evaluation bookkeeping (evaluation.py:11-35).
 //   x' = tanh(x M + a N + c),  reward = x' . w_r - 1e-3 |a|^2,  early termination |x'_0| > threshold.
-#include "common.cuh"
+#include "env.cuh"
 
 namespace {
-
-constexpr int MAX_OBS_PER_LANE = 8;  // obs <= 256
 
 // one warp per environment
 __global__ void env_step_kernel(il_env env, int n_envs, const float* __restrict__ action, float* __restrict__ next_state, float* __restrict__ reward, int32_t* __restrict__ done,
@@ -13,52 +11,11 @@ __global__ void env_step_kernel(il_env env, int n_envs, const float* __restrict_
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x & 31;
   if (e >= n_envs) return;
   if (frozen && frozen[e]) return;
-  const int obs = env.obs, act = env.act;
-  float* x = env.x + (int64_t)e * obs;
-  const float* a = action + (int64_t)e * act;
-  float nx[MAX_OBS_PER_LANE];
-#pragma unroll
-  for (int q = 0; q < MAX_OBS_PER_LANE; ++q) {
-    const int j = lane + 32 * q;
-    float acc = 0.f;
-    if (j < obs) {
-      for (int i = 0; i < obs; ++i) acc = fmaf(x[i], __ldg(env.M + (int64_t)i * obs + j), acc);
-      for (int k = 0; k < act; ++k) acc = fmaf(fminf(fmaxf(a[k], -1.f), 1.f), __ldg(env.N + (int64_t)k * obs + j), acc);  // environments.py:36 clamp
-      acc = tanhf(acc + __ldg(env.c + j));
-    }
-    nx[q] = acc;
-  }
-  __syncwarp();
-  float rew = 0.f;
-#pragma unroll
-  for (int q = 0; q < MAX_OBS_PER_LANE; ++q) {
-    const int j = lane + 32 * q;
-    if (j < obs) {
-      x[j] = nx[q];
-      rew = fmaf(nx[q], __ldg(env.w_r + j), rew);
-    }
-  }
-  float a2 = 0.f;
-  for (int k = lane; k < act; k += 32) {
-    const float ak = fminf(fmaxf(a[k], -1.f), 1.f);
-    a2 = fmaf(ak, ak, a2);
-  }
-  rew = warp_sum(rew) - 1e-3f * warp_sum(a2);
-  const float x0 = __shfl_sync(0xffffffffu, nx[0], 0);
-  const int S = obs + (env.absorbing ? 1 : 0);
-  float* ns = next_state + (int64_t)e * S;
-#pragma unroll
-  for (int q = 0; q < MAX_OBS_PER_LANE; ++q) {
-    const int j = lane + 32 * q;
-    if (j < obs) ns[j] = nx[q];
-  }
+  const int S = env.obs + (env.absorbing ? 1 : 0);
+  const EnvStepOut o = env_step_core(env, e, lane, action + (int64_t)e * env.act, next_state + (int64_t)e * S);
   if (lane == 0) {
-    if (env.absorbing) ns[obs] = 0.f;  // environments.py:39
-    const int t = env.t[e] + 1;
-    env.t[e] = t;
-    const bool tl = t >= env.max_episode_steps;
-    const bool early = env.early_termination && fabsf(x0) > env.term_threshold;
-    reward[e] = rew;
+    const bool early = o.early, tl = o.time_limit;
+    reward[e] = o.reward;
     if (done) done[e] = (early || tl) ? 1 : 0;
     if (timeout) timeout[e] = tl ? 1 : 0;
     if (terminal_f) terminal_f[e] = (early && !tl) ? 1.f : 0.f;  // train.py:157: terminal and t != max_episode_steps

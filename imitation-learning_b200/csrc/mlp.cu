@@ -178,7 +178,8 @@ struct SmallFwdArgs {
   const float* X;
   int64_t x_gs;
   int x_gdiv, ldx, n, maxd;
-  float* out;  // [G, n, dims[L]]
+  float* out;  // [G, n, dims[L]]; tanh_first = A > 0: [G, n, A] = tanh of the first A outputs (the greedy action, models.py:101-102)
+  int tanh_first;
 };
 template <int NR>
 __global__ void __launch_bounds__(256) mlp_small_forward_kernel(const SmallFwdArgs p) {
@@ -237,6 +238,14 @@ __global__ void __launch_bounds__(256) mlp_small_forward_kernel(const SmallFwdAr
   }
   const int od = p.m.dims[L];
   const float* fin = bufs[L & 1];
+  if (p.tanh_first > 0) {
+    const int A = p.tanh_first;
+    for (int idx = tid; idx < nr * A; idx += 256) {
+      const int r = idx / A, o = idx % A;
+      p.out[((int64_t)g * p.n + r0 + r) * A + o] = tanhf(fin[r * maxd + o]);
+    }
+    return;
+  }
   for (int idx = tid; idx < nr * od; idx += 256) {
     const int r = idx / od, o = idx % od;
     p.out[((int64_t)g * p.n + r0 + r) * od + o] = fin[r * maxd + o];
@@ -347,10 +356,10 @@ int launch_tick(il_handle* h, int64_t* s0, int64_t* s1, int64_t* s2, cudaStream_
 }
 
 // n <= 32 rows per net: the fused whole-MLP kernel (parameter-bandwidth bound) instead of per-layer GEMMs.
-int mlp_small_forward(il_handle* h, const il_mlp* m, int G, int n, MatView X, float* out, cudaStream_t stream) {
+int mlp_small_forward(il_handle* h, const il_mlp* m, int G, int n, MatView X, float* out, cudaStream_t stream, int tanh_first) {
   SmallFwdArgs a;
   a.m = *m; a.o = mlp_offsets(m->dims, m->n_layers);
-  a.X = X.ptr; a.x_gs = X.gs; a.x_gdiv = X.gdiv; a.ldx = X.ld; a.n = n; a.out = out;
+  a.X = X.ptr; a.x_gs = X.gs; a.x_gdiv = X.gdiv; a.ldx = X.ld; a.n = n; a.out = out; a.tanh_first = tanh_first;
   int maxd = 4;
   for (int l = 0; l <= m->n_layers; ++l) maxd = m->dims[l] > maxd ? m->dims[l] : maxd;
   a.maxd = (maxd + 3) / 4 * 4;

@@ -32,6 +32,9 @@ int mlp_forward(il_handle* h, const il_mlp* m, int G, int n, MatView X, const Ml
 int mlp_backward(il_handle* h, const il_mlp* m, int G, int n, MatView X, const MlpActs& acts, MatView dOut, float* grads, int64_t grad_stride,
                  float* dX, int64_t dx_gs, int ld_dx, int dx_col0, int dx_cols, float* tmpA, float* tmpB, cudaStream_t stream);
 
+// Whole-MLP forward in one kernel for n <= 32 rows per net (rollout / evaluation rows). tanh_first = A > 0 writes only
+// tanh of the first A outputs ([G, n, A]): the greedy action of a SoftActor (models.py:101-102).
+int mlp_small_forward(il_handle* h, const il_mlp* m, int G, int n, MatView X, float* out, cudaStream_t stream, int tanh_first = 0);
 int mlp_max_hidden(const il_mlp* m);
 int mlp_validate(const il_mlp* m, const char* what);
 

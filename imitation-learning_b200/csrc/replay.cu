@@ -130,6 +130,41 @@ __global__ void mix_rows_kernel(float* __restrict__ dst, int64_t dst_rs, const f
   reinterpret_cast<float4*>(dst + (int64_t)r * dst_rs + (int64_t)b * row4 * 4)[q] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)r * src_rs + (int64_t)b * row4 * 4) + q);
 }
 
+// transfer_transitions (memory.py:46-48): every row of `src` (a single-store memory) appended in order to every replica's
+// ring: row (idx0 + i) % size <- src row i with weight 1 (append resets it, memory.py:41). One thread per float4 of a
+// destination row; rows that a later row of the same transfer would overwrite (n > size) are skipped.
+__global__ void replay_transfer_rows_kernel(il_replay dst, int R, const float* __restrict__ src_rows, int n, int row4) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)R * n * row4) return;
+  const int q = (int)(t % row4);
+  const int64_t ri = t / row4;
+  const int r = (int)(ri / n), i = (int)(ri % n);
+  if (i < n - dst.size) return;
+  const int idx0 = dst.idx[dst.shared ? 0 : r];
+  const RowLayout L = row_layout(dst.S, dst.A);
+  float4 v = __ldg(reinterpret_cast<const float4*>(src_rows + (int64_t)i * row4 * 4) + q);
+  if (L.weight / 4 == q) reinterpret_cast<float*>(&v)[L.weight % 4] = 1.f;
+  reinterpret_cast<float4*>(dst.rows + (int64_t)r * dst.replica_stride + (int64_t)((idx0 + i) % dst.size) * row4 * 4)[q] = v;
+}
+// ring state after the rows above: idx, full, num_trajectories (+1 per terminal / timeout row, memory.py:44). One block per replica.
+__global__ void replay_transfer_state_kernel(il_replay dst, const float* __restrict__ src_rows, int n) {
+  __shared__ float red[32];
+  const int r = blockIdx.x, mi = dst.shared ? 0 : r;
+  const RowLayout L = row_layout(dst.S, dst.A);
+  float ends = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float* row = src_rows + (int64_t)i * L.len;
+    ends += (row[L.terminal] != 0.f || row[L.timeout] != 0.f) ? 1.f : 0.f;
+  }
+  ends = block_sum(ends, red);
+  if (threadIdx.x == 0) {
+    const int idx0 = dst.idx[mi];
+    dst.idx[mi] = (int)(((int64_t)idx0 + n) % dst.size);
+    dst.full[mi] = dst.full[mi] || ((int64_t)idx0 + n >= dst.size);
+    dst.num_trajectories[mi] += (int)ends;
+  }
+}
+
 int check_replay(const il_replay* m, const char* what) {
   IL_CHECK(m && m->rows && m->idx && m->full && m->num_trajectories, "%s: null replay field", what);
   IL_CHECK(m->size > 0 && m->S > 0 && m->A > 0, "%s: size=%d S=%d A=%d", what, m->size, m->S, m->A);
@@ -154,6 +189,19 @@ extern "C" int il_replay_append(il_handle* h, const il_replay* mem, int R, const
   IL_CHECK(!(wrap && mem->size < 2), "il_replay_append: absorbing wrap needs size >= 2");
   IL_LAUNCH(h, replay_append_kernel, (unsigned)((R * 32 + 127) / 128), 128, 0, (cudaStream_t)stream, *mem, R, step, state, action, reward, next_state, terminal, timeout, active,
             wrap);
+  return 0;
+}
+
+extern "C" int il_replay_transfer(il_handle* h, const il_replay* dst, int R, const il_replay* src, void* stream) {
+  IL_CHECK(h && R > 0, "il_replay_transfer: bad argument");
+  IL_TRY(check_replay(dst, "il_replay_transfer(dst)"));
+  IL_TRY(check_replay(src, "il_replay_transfer(src)"));
+  IL_CHECK(dst->row == src->row && dst->S == src->S && dst->A == src->A, "il_replay_transfer: row layout mismatch");
+  IL_CHECK(!dst->shared || R == 1, "il_replay_transfer: a shared destination takes one writer");
+  const int n = src->size, row4 = src->row / 4;  // a pre-filled memory holds `size` valid rows (memory.py:18-23, __len__ :37-38)
+  const int64_t total = (int64_t)R * n * row4;
+  IL_LAUNCH(h, replay_transfer_rows_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, *dst, R, src->rows, n, row4);
+  IL_LAUNCH(h, replay_transfer_state_kernel, (unsigned)(dst->shared ? 1 : R), 256, 0, (cudaStream_t)stream, *dst, src->rows, n);
   return 0;
 }
 

@@ -203,6 +203,18 @@ struct TcParams {
   int l1_vec;                    // W1 rows are 16-byte multiples (K0 % 4 == 0): 16-byte staging copies
 };
 
+// packed fp32 pairs (FFMA2: two IEEE fp32 FMAs per issue slot on sm_100)
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
@@ -384,7 +396,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
     auto lo_of = [](uint32_t x) { return __float_as_uint(__uint_as_float(x) - __uint_as_float(x & 0xFFFFE000u)); };
     // FUSE: per-tile state of the computed A operand — this thread's two input rows (registers), the staging buffer parity
     // and the optional global store of the first hidden activation
-    float x0[L1_MAXK], x1[L1_MAXK];
+    unsigned long long x0[L1_MAXK / 2], x1[L1_MAXK / 2];  // packed pairs {x[2i], x[2i + 1]}
     const int fr = ptid >> 2, fc = ptid & 3;   // A chunks of this thread: rows fr and fr + 64 of the CTA's 128, 16-byte chunk fc of the k-block
     int cons_tile = gid, cons_kb = 0;
     uint32_t cons_buf = 0;
@@ -394,9 +406,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
       const float* xp = p.l1.x + (int64_t)(grp / p.l1.x_gdiv) * p.l1.x_gs + (int64_t)(m0 + fr) * p.l1.x_ld;
       const float* xq = xp + (int64_t)64 * p.l1.x_ld;
 #pragma unroll
-      for (int j = 0; j < L1_MAXK; ++j) {
-        x0[j] = j < p.l1.x_k ? __ldg(xp + j) : 0.f;
-        x1[j] = j < p.l1.x_k ? __ldg(xq + j) : 0.f;
+      for (int j = 0; j < L1_MAXK; j += 2) {
+        x0[j >> 1] = pack2(j < p.l1.x_k ? __ldg(xp + j) : 0.f, j + 1 < p.l1.x_k ? __ldg(xp + j + 1) : 0.f);
+        x1[j >> 1] = pack2(j < p.l1.x_k ? __ldg(xq + j) : 0.f, j + 1 < p.l1.x_k ? __ldg(xq + j + 1) : 0.f);
       }
     };
     if (FUSE) {
@@ -430,24 +442,35 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
         const int np = (p.l1.x_k + 3) >> 2;
         uint32_t bq[4];
         lds128(l1s + 2u * L1_W_BYTES + cons_buf * (uint32_t)L1_B_BYTES + (uint32_t)((cons_kb * 16 + fc * 4) * 4), bq);
+        // 8 accumulator pairs {even-j partial sum, odd-j partial sum} (2 rows x 4 k); per 4-column slice of the input: the 4
+        // weight chunks are loaded together, then 16 packed FMAs on independent chains
+        unsigned long long c0[4], c1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c0[q] = c1[q] = pack2(__uint_as_float(bq[q]), 0.f);
+#pragma unroll
+        for (int c4 = 0; c4 < L1_MAXK / 4; ++c4) {
+          if (c4 < np) {
+            unsigned long long w[4][2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(w[q][0]), "=l"(w[q][1]) : "r"(wb + (uint32_t)(q * 64 + ((c4 ^ fc) << 4))));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              c0[q] = fma2(x0[c4 * 2], w[q][0], c0[q]);
+              c1[q] = fma2(x1[c4 * 2], w[q][0], c1[q]);
+              c0[q] = fma2(x0[c4 * 2 + 1], w[q][1], c0[q]);
+              c1[q] = fma2(x1[c4 * 2 + 1], w[q][1], c1[q]);
+            }
+          }
+        }
         uint32_t a0[4], a1[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          float s0 = __uint_as_float(bq[q]), s1 = s0;
-#pragma unroll
-          for (int c4 = 0; c4 < L1_MAXK / 4; ++c4) {
-            if (c4 < np) {
-              uint32_t w[4];
-              lds128(wb + (uint32_t)(q * 64 + ((c4 ^ fc) << 4)), w);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                s0 = fmaf(x0[c4 * 4 + e], __uint_as_float(w[e]), s0);
-                s1 = fmaf(x1[c4 * 4 + e], __uint_as_float(w[e]), s1);
-              }
-            }
-          }
-          a0[q] = __float_as_uint(fmaxf(s0, 0.f));
-          a1[q] = __float_as_uint(fmaxf(s1, 0.f));
+          float e, o;
+          unpack2(c0[q], e, o);
+          a0[q] = __float_as_uint(fmaxf(e + o, 0.f));
+          unpack2(c1[q], e, o);
+          a1[q] = __float_as_uint(fmaxf(e + o, 0.f));
         }
         if (++cons_kb == nkb) {  // the input rows of the next tile load while this k-block is finished
           cons_kb = 0; cons_tile += n_groups; cons_buf ^= 1u;

@@ -33,18 +33,45 @@ def shard(total_replicas: int, rank: int, world: int) -> Tuple[int, int]:
   return lo, lo + base + (1 if rank < rem else 0)
 
 
+_nccl_comm = None
+
+
+def nccl_comm():
+  """This process's ncclComm_t for the library's own collectives (il_return_allreduce): created once from an ncclUniqueId
+  that rank 0 generates and torch.distributed broadcasts. None for a single process."""
+  global _nccl_comm
+  if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1): return None
+  if _nccl_comm is None:
+    rank, world = dist.get_rank(), dist.get_world_size()
+    uid = (C.c_uint8 * 128)()
+    if rank == 0: _lib.check(_lib.lib().il_nccl_unique_id(uid))
+    t = torch.tensor(list(uid), dtype=torch.uint8, device='cuda' if dist.get_backend() == 'nccl' else 'cpu')
+    dist.broadcast(t, src=0)
+    uid = (C.c_uint8 * 128)(*t.cpu().tolist())
+    comm = C.c_void_p()
+    _lib.check(_lib.lib().il_nccl_comm_create(uid, rank, world, C.byref(comm)))
+    _nccl_comm = comm
+  return _nccl_comm
+
+
 def reduce_stats(stats3: torch.Tensor) -> torch.Tensor:
   """Sum of per-rank (sum, sum of squares, count) vectors; in place. No-op for a single process."""
   if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1: dist.all_reduce(stats3, op=dist.ReduceOp.SUM)
   return stats3
 
 
+def return_stats_device(returns: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+  """(sum, sum of squares, count) of the evaluation returns over ALL ranks, left on the device: il_return_allreduce = the
+  per-rank reduction kernel + ncclAllReduce enqueued on the same stream (no host involvement)."""
+  out = torch.empty(3, device=returns.device, dtype=torch.float32) if out is None else out
+  flat = returns.reshape(-1).contiguous()
+  _lib.check(_lib.lib().il_return_allreduce(_lib.handle(), nccl_comm(), flat.data_ptr(), flat.numel(), out.data_ptr(), _lib.stream()))
+  return out
+
+
 def return_statistics(returns: torch.Tensor) -> Tuple[float, float, int]:
   """Global mean / std / count of evaluation returns over all ranks (device reduction + one all-reduce)."""
-  out = torch.empty(3, device=returns.device, dtype=torch.float32)
-  flat = returns.reshape(-1).contiguous()
-  _lib.check(_lib.lib().il_return_stats(_lib.handle(), flat.data_ptr(), flat.numel(), out.data_ptr(), _lib.stream()))
-  reduce_stats(out)
+  out = return_stats_device(returns)
   s, s2, n = (float(x) for x in out.cpu())
   mean = s / n
   return mean, max(s2 / n - mean * mean, 0.0) ** 0.5, int(n)

@@ -173,13 +173,12 @@ class ReplayMemory:
     _lib.check(_lib.lib().il_replay_wrap_absorbing(_lib.handle(), C.byref(m), self.replicas, _lib.ptr(mask), _lib.stream()))
 
   def transfer_transitions(self, memory: 'ReplayMemory'):
-    """memory.py:46-48: append every transition of `memory` (weights reset to 1 by append)."""
-    src = memory.rows[0] if memory.rows.size(0) == 1 else None
-    assert src is not None, 'transfer_transitions expects a single-store source memory'
-    for i in range(memory.size):
-      t = {k: _field_view(src, memory.off, memory.state_size, memory.action_size, k)[i] for k in FIELDS}
-      rep = lambda v: v.reshape(1, -1).expand(self.replicas, -1) if v.dim() == 1 else v.reshape(1).expand(self.replicas)
-      self.append(rep(t['step']), rep(t['states']), rep(t['actions']), rep(t['rewards']), rep(t['next_states']), rep(t['terminals']), rep(t['timeouts']))
+    """memory.py:46-48: append every transition of `memory` to every replica's ring (weights reset to 1 by append) — one
+    device pass (il_replay_transfer) instead of len(memory) appends."""
+    assert memory.rows.size(0) == 1, 'transfer_transitions expects a single-store source memory (e.g. the shared expert buffer)'
+    assert not self.shared, 'shared (expert) memories are read-only'
+    d, s = self.c_struct(), memory.c_struct()
+    _lib.check(_lib.lib().il_replay_transfer(_lib.handle(), C.byref(d), self.replicas, C.byref(s), _lib.stream()))
 
   # ---- sampling ----
   def draw_indices_host(self, n: int) -> np.ndarray:

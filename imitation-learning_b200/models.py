@@ -264,11 +264,16 @@ class GAILDiscriminator(_Module):
   def __init__(self, state_size: int, action_size: int, imitation_cfg, discount: float, replicas: int = 1, rng: Optional[ReplicaRNG] = None, device=None):
     model_cfg = imitation_cfg.discriminator
     self.discount, self.state_only = discount, bool(imitation_cfg.state_only)
-    self.reward_shaping, self.subtract_log_policy, self.reward_function = model_cfg.reward_shaping, model_cfg.subtract_log_policy, model_cfg.reward_function
-    if self.reward_shaping or self.subtract_log_policy: raise NotImplementedError('reward_shaping / subtract_log_policy discriminators are not on the accelerated path yet (SURVEY §8f)')
-    if model_cfg.depth != 1 or model_cfg.activation != 'relu': raise NotImplementedError('only the depth-1 relu discriminator (GAIL.yaml:10-13) is accelerated (SURVEY §8f)')
+    self.reward_shaping, self.subtract_log_policy, self.reward_function = bool(model_cfg.reward_shaping), bool(model_cfg.subtract_log_policy), model_cfg.reward_function
     self.state_size, self.action_size, self.replicas = state_size, action_size, replicas
     self.spectral_norm = bool(imitation_cfg.spectral_norm)
+    # the default configuration (GAIL.yaml:10-17: one relu hidden layer, no shaping, no log-policy term) runs in the fused one-CTA-per-replica
+    # kernel (csrc/gail.cu); every other configuration of models.py:157-175 runs as the replica-batched GEMM program of csrc/gail_general.cu
+    self.general = self.reward_shaping or self.subtract_log_policy or model_cfg.depth != 1 or model_cfg.activation != 'relu'
+    self._ws = None
+    if self.general:
+      self._init_general(model_cfg, rng, device)
+      return
     d, H = (state_size if self.state_only else state_size + action_size), model_cfg.hidden_size
     dims = [d, H, 1]
     self.mlp = ReplicaMLP(dims, 'relu', replicas, 1, device)
@@ -294,6 +299,101 @@ class GAILDiscriminator(_Module):
           self.v[r].copy_(torch.cat(vs))
     self.training = True
 
+  # ---- general configuration (models.py:157-162): flat [R, g | h] parameter buffer, per-net spectral-norm vectors ----------------
+  def _init_general(self, model_cfg, rng, device):
+    R, S, A = self.replicas, self.state_size, self.action_size
+    din, H, depth, act = (S if self.state_only else S + A), model_cfg.hidden_size, model_cfg.depth, model_cfg.activation
+    self.activation = act
+    self.g_dims = [din, 1] if self.reward_shaping else [din] + [H] * depth + [1]
+    self.h_dims = ([S] + [H] * depth + [1]) if self.reward_shaping else None
+    self.device = torch.device('cuda') if device is None else torch.device(device)
+    g_total = _lib.py_mlp_offsets(self.g_dims)[2]
+    h_total = _lib.py_mlp_offsets(self.h_dims)[2] if self.h_dims else 0
+    self.flat = torch.zeros(R, g_total + h_total, device=self.device)
+    self.g_mlp = ReplicaMLP(self.g_dims, act, R, 1, self.device)
+    self.g_mlp.flat, self.g_mlp.stride = self.flat, g_total + h_total
+    self.h_mlp = None
+    if self.h_dims:
+      self.h_mlp = ReplicaMLP(self.h_dims, act, R, 1, self.device)
+      self.h_mlp.flat, self.h_mlp.stride = self.flat[:, g_total:], g_total + h_total
+    self.mlp = self.g_mlp  # parameters() / generic helpers see the flat buffer through g
+    sn = self.spectral_norm
+    mk = lambda dims: (torch.zeros(R, sum(dims[1:]), device=self.device), torch.zeros(R, sum(dims[:-1]), device=self.device)) if sn else (None, None)
+    self.g_u, self.g_v = mk(self.g_dims)
+    self.h_u, self.h_v = mk(self.h_dims) if self.h_dims else (None, None)
+
+    def fcnn(dims):  # _create_fcnn (:48-69): per layer Linear() draws, orthogonal_, zero bias, then the u / v draws of spectral_norm
+      params, us, vs = [], [], []
+      for l in range(len(dims) - 1):
+        layer = torch.nn.Linear(dims[l], dims[l + 1])
+        torch.nn.init.orthogonal_(layer.weight, gain=torch.nn.init.calculate_gain(act) if l < len(dims) - 2 else 1)
+        torch.nn.init.constant_(layer.bias, 0)
+        if sn:
+          u_, v_ = _spectral_norm_init(layer.weight.detach())
+          us.append(u_); vs.append(v_)
+        params += [layer.weight.detach(), layer.bias.detach()]
+      return params, us, vs
+
+    for r in range(R):
+      with (rng.replica(r) if rng is not None else _null_ctx()):
+        if self.reward_shaping:  # :158-160: g is a plain nn.Linear (default init), then h
+          lin = torch.nn.Linear(din, 1)
+          gp, gu, gv = [lin.weight.detach(), lin.bias.detach()], [], []
+          if sn:
+            u_, v_ = _spectral_norm_init(gp[0])
+            gu, gv = [u_], [v_]
+          hp, hu, hv = fcnn(self.h_dims)
+          self.h_mlp.load_params(r, 0, hp)
+          if sn: self.h_u[r].copy_(torch.cat(hu)); self.h_v[r].copy_(torch.cat(hv))
+        else:
+          gp, gu, gv = fcnn(self.g_dims)
+        self.g_mlp.load_params(r, 0, gp)
+        if sn: self.g_u[r].copy_(torch.cat(gu)); self.g_v[r].copy_(torch.cat(gv))
+    self.training = True
+
+  def cx_struct(self) -> _lib.Gailx:
+    d = _lib.Gailx()
+    d.g = self.g_mlp.c_struct()
+    if self.h_mlp is not None: d.h = self.h_mlp.c_struct()
+    if self.spectral_norm:
+      d.g_u, d.g_v, d.g_u_stride, d.g_v_stride = self.g_u.data_ptr(), self.g_v.data_ptr(), self.g_u.stride(0), self.g_v.stride(0)
+      if self.h_mlp is not None: d.h_u, d.h_v, d.h_u_stride, d.h_v_stride = self.h_u.data_ptr(), self.h_v.data_ptr(), self.h_u.stride(0), self.h_v.stride(0)
+    d.state_only, d.reward_function, d.subtract_log_policy, d.discount = int(self.state_only), _lib.REWARD[self.reward_function], int(self.subtract_log_policy), self.discount
+    return d
+
+  def _general_state_items(self):
+    out = []
+    for name, mlp, u, v, seq in (('g', self.g_mlp, self.g_u, self.g_v, not self.reward_shaping), ('h', self.h_mlp, self.h_u, self.h_v, True)):
+      if mlp is None: continue
+      views, uo, vo = mlp.layer_views()[0], 0, 0
+      for l in range(mlp.n_layers):
+        pre = f'{name}.{2 * l}' if seq else name  # nn.Sequential indices: Linear, activation, Linear, ... (no dropout modules: models.py:160,162)
+        od, idim = mlp.dims[l + 1], mlp.dims[l]
+        if self.spectral_norm:
+          out += [(f'{pre}.bias', views[2 * l + 1]), (f'{pre}.parametrizations.weight.original', views[2 * l]), (f'{pre}.parametrizations.weight.0._u', u[:, uo:uo + od]),
+                  (f'{pre}.parametrizations.weight.0._v', v[:, vo:vo + idim])]
+        else:
+          out += [(f'{pre}.weight', views[2 * l]), (f'{pre}.bias', views[2 * l + 1])]
+        uo, vo = uo + od, vo + idim
+    return out
+
+  def _run_general(self, batch: TransitionBatch, reward_out: Optional[Tensor], want_logits: bool, log_policy: Optional[Tensor]) -> Dict[str, Tensor]:
+    R, B = self.replicas, batch.B
+    lib, d, b = _lib.lib(), self.cx_struct(), batch.c_struct()
+    need = lib.il_gailx_reward_workspace_bytes(C.byref(d), R, B)
+    if self._ws is None or self._ws.numel() < need: self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+    out = {'reward': torch.empty(R, B, device=self.device) if reward_out is None else reward_out}
+    if want_logits: out['logits'] = torch.empty(R, B, device=self.device)
+    if self.subtract_log_policy:
+      assert log_policy is not None, 'subtract_log_policy needs log_policy (make_gail_input, models.py:148)'
+      log_policy = torch.as_tensor(log_policy, dtype=torch.float32).to(self.device).reshape(R, B).contiguous()
+    _lib.check(lib.il_gailx_reward(_lib.handle(), C.byref(d), R, C.byref(b), _lib.ptr(log_policy) if self.subtract_log_policy else None, out['reward'].data_ptr(), out['reward'].stride(0),
+                                   out['reward'].stride(1), _lib.ptr(out.get('logits')), self._ws.data_ptr(), self._ws.numel(), _lib.stream()))
+    return out
+
+  def parameters(self) -> List[Tensor]:
+    return [self.flat] if self.general else [self.mlp.flat]
+
   def c_struct(self) -> _lib.Gail:
     g = _lib.Gail()
     g.g = self.mlp.c_struct()
@@ -303,6 +403,7 @@ class GAILDiscriminator(_Module):
     return g
 
   def _state_items(self):
+    if self.general: return self._general_state_items()
     v = self.mlp.layer_views()[0]
     d, H = self.mlp.dims[0], self.mlp.dims[1]
     if not self.spectral_norm:
@@ -311,16 +412,19 @@ class GAILDiscriminator(_Module):
             ('g.2.bias', v[3]), ('g.2.parametrizations.weight.original', v[2]), ('g.2.parametrizations.weight.0._u', self.u[:, H:H + 1]),
             ('g.2.parametrizations.weight.0._v', self.v[:, d:d + H])]
 
-  def _batch_of(self, state: Tensor, action: Tensor) -> TransitionBatch:
+  def _batch_of(self, state: Tensor, action: Tensor, next_state=None, terminal=None) -> TransitionBatch:
     R = self.replicas
     s, a = _as_rns(state, R, self.state_size, self.device), _as_rns(action, R, self.action_size, self.device)
-    _, row = _lib.py_row_layout(self.state_size, self.action_size)
+    off, row = _lib.py_row_layout(self.state_size, self.action_size)
     tb = TransitionBatch(torch.zeros(R, s.size(1), row, device=self.device), self.state_size, self.action_size, False)
     tb.rows[..., :self.state_size], tb.rows[..., self.state_size:self.state_size + self.action_size] = s, a
+    if next_state is not None: tb.rows[..., off['next_states']:off['next_states'] + self.state_size] = _as_rns(next_state, R, self.state_size, self.device)
+    if terminal is not None: tb.rows[..., off['terminals']] = torch.as_tensor(terminal, dtype=torch.float32).to(self.device).reshape(R, -1)
     return tb
 
-  def _run(self, batch: TransitionBatch, reward_out: Optional[Tensor] = None, want_logits: bool = False) -> Dict[str, Tensor]:
+  def _run(self, batch: TransitionBatch, reward_out: Optional[Tensor] = None, want_logits: bool = False, log_policy: Optional[Tensor] = None) -> Dict[str, Tensor]:
     if self.training and self.spectral_norm: raise RuntimeError('train-mode forward outside adversarial_imitation_update is not supported; call .eval() (train.py:147,180)')
+    if self.general: return self._run_general(batch, reward_out, want_logits, log_policy)
     R, B = self.replicas, batch.B
     g, b = self.c_struct(), batch.c_struct()
     out = {}
@@ -332,22 +436,24 @@ class GAILDiscriminator(_Module):
     return out
 
   def forward(self, state: Tensor, action: Tensor, next_state=None, terminal=None, log_policy=None) -> Tensor:  # :172-175
-    out = self._run(self._batch_of(state, action), want_logits=True)['logits']
+    out = self._run(self._batch_of(state, action, next_state, terminal), want_logits=True, log_policy=log_policy)['logits']
     return out[0] if self.replicas == 1 else out
 
   __call__ = forward
 
   def predict_reward(self, state: Tensor, action: Tensor, next_state=None, terminal=None, log_policy=None) -> Tensor:  # :177-180
-    out = self._run(self._batch_of(state, action))['reward']
+    out = self._run(self._batch_of(state, action, next_state, terminal), log_policy=log_policy)['reward']
     return out[0] if self.replicas == 1 else out
 
-  def predict_reward_batch(self, batch: TransitionBatch, write_rewards: bool = True) -> Tensor:
-    """Fast path of train.py:194: rewards of a packed batch, written straight into its reward column."""
+  def predict_reward_batch(self, batch: TransitionBatch, write_rewards: bool = True, actor: Optional['SoftActor'] = None) -> Tensor:
+    """Fast path of train.py:194: rewards of a packed batch, written straight into its reward column. `actor` supplies the
+    log-policy term of make_gail_input (models.py:148) when subtract_log_policy is set."""
+    lp = actor._run(batch.rows[..., :batch.S], given=batch.rows[..., batch.S:batch.S + batch.A], want=('log_prob', ))['log_prob'] if self.subtract_log_policy else None
     if write_rewards:
       view = batch.rows[..., batch.off['rewards']]
-      self._run(batch, reward_out=view)
+      self._run(batch, reward_out=view, log_policy=lp)
       return view
-    return self._run(batch)['reward']
+    return self._run(batch, log_policy=lp)['reward']
 
 
 class GMMILDiscriminator:

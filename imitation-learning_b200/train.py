@@ -100,8 +100,8 @@ class Trainer:
     elif self.algorithm == 'PWIL':
       self.discriminator = PWILDiscriminator(S, A, cfg.imitation, self.expert_memory, self.env.max_episode_steps, replicas=R, device=dev)
     if self.expert_memory is not None: self.expert_memory.seed = seed + 7919
-    if self.algorithm in ('GMMIL', 'PWIL') and cfg.imitation.mix_expert_data == 'prefill_memory': raise NotImplementedError('prefill_memory is not on the accelerated path yet (SURVEY §8f)')
-    if self.algorithm == 'PWIL' and cfg.imitation.mix_expert_data != 'none': raise NotImplementedError('PWIL expert-reward relabelling (train.py:136-140) is not accelerated yet')
+    if self.algorithm == 'PWIL' and cfg.imitation.mix_expert_data != 'none': self._pwil_relabel_expert()  # train.py:136-140
+    if self.algorithm in ('GMMIL', 'PWIL') and cfg.imitation.mix_expert_data == 'prefill_memory': self.memory.transfer_transitions(self.expert_memory)  # train.py:141,143
     # ---- per-step device state -------------------------------------------------------------------------------
     B = self.B = cfg.training.batch_size
     f = lambda *shape: torch.zeros(*shape, device=dev)
@@ -135,11 +135,37 @@ class Trainer:
     self.score: List[float] = []
     self.env.batch.reset(self.env.reset_noise(R), self.state)  # train.py:146
 
+  def _pwil_relabel_expert(self):
+    """train.py:136-140: the expert's own transitions get their greedy PWIL reward, walking the expert memory in order and
+    restoring the atoms at every episode end. The expert memory is shared by all replicas and every replica would compute the
+    same numbers, so one single-replica coupling state does the walk (one-off setup: one small launch per expert transition)."""
+    em, d = self.expert_memory, self.discriminator
+    one = PWILDiscriminator(self.S, self.A, self.cfg.imitation, em, self.env.max_episode_steps, replicas=1, device=self.device)
+    ends = ((em.rows[0, :, em.off['terminals']] != 0) | (em.rows[0, :, em.off['timeouts']] != 0)).cpu().numpy()  # setup-time read of the episode boundaries
+    states, actions, rewards = em.rows[0, :, em.off['states']:em.off['states'] + self.S], em.rows[0, :, em.off['actions']:em.off['actions'] + self.A], em.rows[0, :, em.off['rewards']]
+    out = torch.empty(1, device=self.device)
+    for i in range(em.size):
+      one.compute_reward_batch(states[i:i + 1], actions[i:i + 1], out=out)
+      rewards[i:i + 1].copy_(out)  # expert_memory.rewards[i] = ...
+      if ends[i]: one.reset()
+    # the reference walks the expert data with THE discriminator, so whatever atoms the last (unfinished) expert episode consumed
+    # stay consumed when training starts: every replica inherits the walk's remaining-weight vector
+    d.expert_weights.copy_(one.expert_weights.expand_as(d.expert_weights))
+
   def _replicate(self):
     """fast_init: every replica starts from replica 0's initial weights (throughput runs; replicas still diverge
     through their own env / noise streams)."""
     for mod in (self.actor, self.critic, self.discriminator):
       if mod is None: continue
+      if getattr(mod, 'general', False):  # general GAIL discriminator: one flat [R, g | h] buffer with two net views
+        g_total = mod.h_mlp.flat.storage_offset() - mod.flat.storage_offset() if mod.h_mlp is not None else 0
+        mod.flat = mod.flat.expand(self.R, -1).contiguous()
+        mod.g_mlp.flat, mod.g_mlp.replicas = mod.flat, self.R
+        if mod.h_mlp is not None: mod.h_mlp.flat, mod.h_mlp.replicas = mod.flat[:, g_total:], self.R
+        mod.replicas = self.R
+        for n in ('g_u', 'g_v', 'h_u', 'h_v'):
+          if getattr(mod, n, None) is not None: setattr(mod, n, getattr(mod, n).expand(self.R, -1).contiguous())
+        continue
       mod.mlp.flat = mod.mlp.flat.expand(self.R, -1).contiguous()
       mod.mlp.replicas = self.R
       mod.replicas = self.R
@@ -189,7 +215,7 @@ class Trainer:
       if cfg.imitation.mix_expert_data == 'mixed_batch':
         from .models import mix_expert_agent_transitions
         mix_expert_agent_transitions(self.batch, self.expert_batch)  # train.py:183
-      if self.algorithm == 'GAIL': self.discriminator.predict_reward_batch(self.batch, write_rewards=True)  # train.py:194
+      if self.algorithm == 'GAIL': self.discriminator.predict_reward_batch(self.batch, write_rewards=True, actor=self.actor)  # train.py:194
       else: self.discriminator.predict_reward_batch(self.batch, self.expert_batch, reward_out=self.batch.rows[..., self.batch.off['rewards']])  # train.py:196
     from .training import sac_update
     if cfg.imitation.bc_aux_loss:  # train.py:201

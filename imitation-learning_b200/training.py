@@ -82,6 +82,8 @@ def adversarial_imitation_update(actor: SoftActor, discriminator: GAILDiscrimina
     else: eps_mix = torch.distributions.Beta(torch.full((R, B), alpha, device=device), torch.full((R, B), alpha, device=device)).sample()
   as_dev = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.float32).to(device).reshape(R, B).contiguous()
   eps_gp, eps_mix = as_dev(eps_gp), as_dev(eps_mix)
+  if discriminator.general:
+    return _general_adversarial_update(actor, discriminator, pol, exp, discriminator_optimiser, imitation_cfg, eps_gp, eps_mix, out_losses)
   a = _lib.GailUpdateArgs()
   a.disc, a.opt, a.policy, a.expert = discriminator.c_struct(), discriminator_optimiser.c_struct(), pol.c_struct(), exp.c_struct()
   a.eps_gp, a.eps_mix, a.R, a.loss_function, a.training = _lib.ptr(eps_gp), _lib.ptr(eps_mix), R, _lib.LOSS[loss_function], int(discriminator.training)
@@ -89,6 +91,35 @@ def adversarial_imitation_update(actor: SoftActor, discriminator: GAILDiscrimina
   a.pos_class_prior, a.nonnegative_margin = float(imitation_cfg.pos_class_prior), float(imitation_cfg.nonnegative_margin)
   a.out_losses = _lib.ptr(out_losses)
   _lib.check(_lib.lib().il_gail_update(_lib.handle(), C.byref(a), _lib.stream()))
+
+
+def _general_adversarial_update(actor, disc: GAILDiscriminator, pol: TransitionBatch, exp: TransitionBatch, opt: Adam, imitation_cfg, eps_gp, eps_mix, out_losses):
+  """training.py:85-134 for the non-default discriminator configurations (reward shaping, subtract_log_policy, depth > 1, tanh / sigmoid):
+  the log-policy inputs of make_gail_input (models.py:148, evaluated under no_grad) are computed first, then one il_gailx_update call."""
+  R, B, device, lib = disc.replicas, pol.B, disc.device, _lib.lib()
+  loss_function = imitation_cfg.loss_function
+  logp = {}
+  if disc.subtract_log_policy:
+    lp = lambda tb: actor._run(tb.rows[..., :tb.S], given=tb.rows[..., tb.S:tb.S + tb.A], want=('log_prob', ))['log_prob']
+    if loss_function == 'Mixup':  # make_gail_input on the mixed state / action (training.py:107-108)
+      mix = TransitionBatch(torch.empty_like(pol.rows), pol.S, pol.A, pol.absorbing)
+      e, p_, m = exp.c_struct(), pol.c_struct(), mix.c_struct()
+      _lib.check(lib.il_gail_mix_batch(_lib.handle(), C.byref(e), C.byref(p_), eps_mix.data_ptr(), R, C.byref(m), _lib.stream()))
+      logp['mix'] = lp(mix)
+    else:
+      logp['policy'], logp['expert'] = lp(pol), lp(exp)
+  a = _lib.GailxUpdateArgs()
+  a.disc, a.opt, a.params_floats, a.policy, a.expert = disc.cx_struct(), opt.c_struct(), disc.flat.numel(), pol.c_struct(), exp.c_struct()
+  a.eps_gp, a.eps_mix = _lib.ptr(eps_gp), _lib.ptr(eps_mix)
+  a.logp_policy, a.logp_expert, a.logp_mix = _lib.ptr(logp.get('policy')), _lib.ptr(logp.get('expert')), _lib.ptr(logp.get('mix'))
+  a.R, a.loss_function, a.training = R, _lib.LOSS[loss_function], int(disc.training)
+  a.grad_penalty, a.entropy_bonus = float(imitation_cfg.grad_penalty), float(imitation_cfg.entropy_bonus)
+  a.pos_class_prior, a.nonnegative_margin = float(imitation_cfg.pos_class_prior), float(imitation_cfg.nonnegative_margin)
+  a.out_losses = _lib.ptr(out_losses)
+  need = lib.il_gailx_workspace_bytes(C.byref(a))
+  ws = _workspace(disc, 'gailx', need, device)
+  a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+  _lib.check(lib.il_gailx_update(_lib.handle(), C.byref(a), _lib.stream()))
 
 
 def behavioural_cloning_update(actor: SoftActor, expert_transition, actor_optimiser: Adam, out_loss: Optional[Tensor] = None):

@@ -81,7 +81,7 @@ const char* il_last_error(void);
 int         il_version(void);
 int         il_set_gemm_mode(il_handle* h, int mode);              /* IL_GEMM_* for the dense hidden layers */
 int64_t     il_launch_count(il_handle* h);                         /* kernels launched by this library so far */
-int         il_struct_sizes(int32_t* out9);                        /* sizeof il_mlp, il_adam, il_batch, il_replay, il_sac_args, il_gail, il_gail_update_args, il_pwil, il_env */
+int         il_struct_sizes(int32_t* out13);                       /* sizeof il_mlp, il_adam, il_batch, il_replay, il_sac_args, il_gail, il_gail_update_args, il_pwil, il_env, il_bc_args, il_eval_args, il_gailx, il_gailx_update_args */
 int         il_mlp_param_offsets(const int32_t* dims, int n_layers, int64_t* w_off, int64_t* b_off, int64_t* total);
 int         il_row_layout(int S, int A, int32_t* offsets8, int32_t* row_len); /* state, action, reward, next_state, terminal, timeout, weight, step */
 
@@ -175,6 +175,9 @@ int il_adam_step(il_handle* h, float* params, const float* grads, const il_adam*
 int il_replay_append(il_handle* h, const il_replay* mem, int R, const float* step, const float* state, const float* action,
                      const float* reward, const float* next_state, const float* terminal, const float* timeout,
                      const int32_t* active, int wrap, void* stream);
+/* transfer_transitions (memory.py:46-48): appends every row of `src` (a single-store memory, e.g. the shared expert buffer) in
+ * order to the ring of every replica of `dst` (weights reset to 1 by append, memory.py:41); used by train.py:133,141,143. */
+int il_replay_transfer(il_handle* h, const il_replay* dst, int R, const il_replay* src, void* stream);
 /* wrap_for_absorbing_states (memory.py:65-68) on the last appended row of every replica with mask != 0 (NULL = all). */
 int il_replay_wrap_absorbing(il_handle* h, const il_replay* mem, int R, const int32_t* mask, void* stream);
 /* _sample_idx x n (memory.py:51-59): uniform over valid rows, never the newest row. uniform != NULL: [R, n]
@@ -216,6 +219,45 @@ int il_gail_update(il_handle* h, const il_gail_update_args* a, void* stream);
 /* forward logits (models.py:164-175, eval mode) and predict_reward (models.py:177-180); reward/logits may be NULL. */
 int il_gail_reward(il_handle* h, const il_gail* disc, int R, const il_batch* batch, float* reward, int64_t reward_rs, int reward_ld,
                    float* logits, void* stream);
+
+/* ---- general GAILDiscriminator (models.py:152-180): reward shaping (linear g + MLP h), subtract_log_policy, any depth / activation ----
+ * g and h live in ONE flat [R, stride] parameter buffer (g at offset 0, h behind it; both il_mlp.stride == that stride), so one AdamW state
+ * covers discriminator.parameters() (train.py:84). Spectral-norm vectors: per net, u = [u_0 | u_1 | ...] (layer l: dims[l+1] floats),
+ * v = [v_0 | v_1 | ...] (layer l: dims[l] floats). */
+typedef struct il_gailx {
+  il_mlp  g;                        /* without shaping: the MLP of models.py:162; with shaping: nn.Linear (n_layers == 1), models.py:158 */
+  il_mlp  h;                        /* shaping function (models.py:160); h.n_layers == 0: no reward shaping */
+  float*  g_u; float* g_v;          /* [R, g_u_stride] / [R, g_v_stride]; NULL = no spectral norm */
+  float*  h_u; float* h_v;
+  int32_t g_u_stride, g_v_stride, h_u_stride, h_v_stride;
+  int32_t state_only;               /* imitation.state_only (models.py:156) */
+  int32_t reward_function;          /* IL_REWARD_* */
+  int32_t subtract_log_policy;      /* models.py:175 */
+  float   discount;                 /* models.py:174 */
+} il_gailx;
+typedef struct il_gailx_update_args {
+  il_gailx disc;
+  il_adam  opt;                     /* AdamW over the flat buffer at disc.g.params (params_floats = R * stride floats) */
+  int64_t  params_floats;
+  il_batch policy, expert;
+  const float* eps_gp;              /* [R, B] U(0,1) (training.py:118) */
+  const float* eps_mix;             /* [R, B] Beta(a, a) (training.py:106) */
+  const float* logp_policy;         /* [R, B] log pi(a|s) of the policy batch (make_gail_input, models.py:148); subtract_log_policy only */
+  const float* logp_expert;         /* [R, B] of the expert batch */
+  const float* logp_mix;            /* [R, B] of the Mixup batch (il_gail_mix_batch of expert and policy with eps_mix) */
+  int32_t R, loss_function, training, _pad;
+  float grad_penalty, entropy_bonus, pos_class_prior, nonnegative_margin;
+  float* out_losses;                /* [R, 2] (may be NULL) */
+  void*   workspace;                /* il_gailx_workspace_bytes */
+  int64_t workspace_bytes;
+} il_gailx_update_args;
+int64_t il_gailx_workspace_bytes(const il_gailx_update_args* a);
+int il_gailx_update(il_handle* h, const il_gailx_update_args* a, void* stream);      /* training.py:85-134 */
+int64_t il_gailx_reward_workspace_bytes(const il_gailx* disc, int R, int B);
+int il_gailx_reward(il_handle* h, const il_gailx* disc, int R, const il_batch* batch, const float* log_policy, float* reward, int64_t reward_rs, int reward_ld,
+                    float* logits, void* workspace, int64_t workspace_bytes, void* stream);   /* models.py:164-180, eval mode */
+/* _mix_vars (training.py:79-81) on every field of the packed rows: out = eps * expert + (1 - eps) * policy */
+int il_gail_mix_batch(il_handle* h, const il_batch* expert, const il_batch* policy, const float* eps, int R, const il_batch* out, void* stream);
 
 /* ---- GMMILDiscriminator (models.py:183-201) ------------------------------------------------------------- */
 /* bandwidths (models.py:193-195): gamma[r, 0:2] = 1 / (weighted median + 1e-8). workspace: il_gmmil_workspace_bytes. */
@@ -272,6 +314,38 @@ int il_eval_accumulate(il_handle* h, int n_envs, const float* reward, const int3
                        int32_t* n_unfinished, void* stream);
 /* per-rank statistics vector for the NCCL reduction: out[0:3] = sum, sum of squares, count. */
 int il_return_stats(il_handle* h, const float* returns, int64_t n, float* out3, void* stream);
+
+/* evaluate_agent (evaluation.py:11-35) as one device program: R x episodes greedy episodes (get_greedy_action, models.py:101-102)
+ * advance in lock-step inside a CUDA graph WHILE node whose condition is set on the device, so the host launches once and is not
+ * involved until every episode has ended (finished episodes are frozen). The caller resets the environments first (il_env_reset
+ * into `state`). Not capturable itself (it launches its own graph). */
+typedef struct il_eval_args {
+  il_mlp   actor;                   /* R nets */
+  il_env   env;                     /* R * episodes evaluation environments (x, t hold their state) */
+  int32_t  R, episodes;
+  int32_t  max_steps;               /* safety bound on loop iterations (>= env.max_episode_steps) */
+  int32_t  traj_T;                  /* capacity (steps) of the trajectory buffers */
+  float*   state;                   /* [R * episodes, S] in: initial states (il_env_reset); scratch afterwards */
+  float*   returns;                 /* [R * episodes] out: sum of rewards per episode (evaluation.py:28) */
+  float*   traj_states;             /* optional [R * episodes, traj_T, S]   (return_trajectories, evaluation.py:22,33) */
+  float*   traj_actions;            /* optional [R * episodes, traj_T, A] */
+  float*   traj_rewards;            /* optional [R * episodes, traj_T] */
+  int32_t* traj_len;                /* optional [R * episodes] steps recorded per episode */
+  int64_t* out_counters;            /* optional [2]: loop iterations executed, environment steps executed */
+  void*    workspace;               /* il_eval_workspace_bytes */
+  int64_t  workspace_bytes;
+} il_eval_args;
+int64_t il_eval_workspace_bytes(const il_eval_args* a);
+int il_eval_rollout(il_handle* h, const il_eval_args* a, void* stream);
+
+/* train.py:213-219 across the seed-sharded ranks: out3 = (sum, sum of squares, count) of this rank's returns, then
+ * ncclAllReduce(sum) over `nccl_comm` (an ncclComm_t; NULL = single process) enqueued on the same stream — no host involvement.
+ * il_nccl_* create that communicator from a 128-byte ncclUniqueId the caller distributes (e.g. a torch.distributed broadcast);
+ * NCCL is bound at run time (libnccl.so.2, the copy the host framework already loaded). */
+int il_nccl_unique_id(uint8_t* out128);                                   /* HOST pointer */
+int il_nccl_comm_create(const uint8_t* id128, int rank, int world, void** comm);  /* HOST pointers */
+int il_nccl_comm_destroy(void* comm);
+int il_return_allreduce(il_handle* h, void* nccl_comm, const float* returns, int64_t n, float* out3, void* stream);
 
 #ifdef __cplusplus
 }

@@ -39,13 +39,13 @@ CASES: Dict[str, dict] = {
   'gail_tuned25': dict(kind='gail', S=12, A=3, H=128, B=256, steps=2, seed=302, spectral_norm=True, grad_penalty=0.3203035416081548, entropy_bonus=0.015492475591599941, loss='BCE',
                        lr=7.299440972507e-05, wd=6.3524082861840725, reward='GAIL'),
   'gmmil_ant': dict(kind='gmmil', S=112, A=8, B=300, seed=43),
-  # SURVEY §8f row 3 variants (oracle pinned; CUDA path is next-round work): shaping f = g(s,a) + (1-t)(gamma h(s') - h(s)) with a
+  # SURVEY §8f row 3 variants (csrc/gail_general.cu): shaping f = g(s,a) + (1-t)(gamma h(s') - h(s)) with a
   # linear g (models.py:157-160), subtract_log_policy (:175), deeper / tanh / sigmoid / state-only discriminators
-  'gailx_shaping': dict(kind='gailx', cuda=False, S=12, A=3, H=32, depth=1, activation='relu', B=48, steps=2, seed=36, spectral_norm=True, grad_penalty=1.0, entropy_bonus=0.05, loss='BCE',
+  'gailx_shaping': dict(kind='gailx', S=12, A=3, H=32, depth=1, activation='relu', B=48, steps=2, seed=36, spectral_norm=True, grad_penalty=1.0, entropy_bonus=0.05, loss='BCE',
                         lr=1e-3, wd=0.1, reward='AIRL', reward_shaping=True, subtract_log_policy=True, state_only=False),
-  'gailx_depth2_tanh': dict(kind='gailx', cuda=False, S=12, A=3, H=32, depth=2, activation='tanh', B=48, steps=2, seed=37, spectral_norm=True, grad_penalty=1.0, entropy_bonus=0.0, loss='BCE',
+  'gailx_depth2_tanh': dict(kind='gailx', S=12, A=3, H=32, depth=2, activation='tanh', B=48, steps=2, seed=37, spectral_norm=True, grad_penalty=1.0, entropy_bonus=0.0, loss='BCE',
                             lr=1e-3, wd=0.1, reward='GAIL', reward_shaping=False, subtract_log_policy=False, state_only=False),
-  'gailx_state_only_sigmoid': dict(kind='gailx', cuda=False, S=18, A=6, H=32, depth=2, activation='sigmoid', B=48, steps=2, seed=38, spectral_norm=False, grad_penalty=0.0, entropy_bonus=0.1, loss='Mixup',
+  'gailx_state_only_sigmoid': dict(kind='gailx', S=18, A=6, H=32, depth=2, activation='sigmoid', B=48, steps=2, seed=38, spectral_norm=False, grad_penalty=0.0, entropy_bonus=0.1, loss='Mixup',
                                    lr=1e-3, wd=0.0, reward='FAIRL', reward_shaping=True, subtract_log_policy=False, state_only=True),
   # expert-data ingest (environments.py:63-125) on a D4RL-shaped raw buffer — host logic, no CUDA
   'ingest_absorbing_sub4': dict(kind='ingest', cuda=False, obs=11, A=3, N=900, trajectories=4, subsample=4, absorbing=True, seed=71),
@@ -56,7 +56,7 @@ CASES: Dict[str, dict] = {
   'eval_halfcheetah': dict(kind='eval', cuda=False, env='halfcheetah', H=32, episodes=3, max_steps=50, seed=82),
   # a7 / a8 / a16 around expert data: ReplayMemory(transitions=...) prefill (memory.py:18-23), transfer_transitions (:46-48), the
   # "never the last row" sampling rule of a pre-filled memory (:22-23, 55) and mix_expert_agent_transitions (models.py:287-290)
-  'prefill_mix': dict(kind='mix', cuda=False, S=12, A=3, Ne=40, size=64, extra=9, B=16, seed=91),
+  'prefill_mix': dict(kind='mix', S=12, A=3, Ne=40, size=64, extra=9, B=16, seed=91),
   'gmmil_hopper': dict(kind='gmmil', S=12, A=3, B=64, seed=41),
   'gmmil_halfcheetah': dict(kind='gmmil', S=18, A=6, B=256, seed=42),
   'pwil_small': dict(kind='pwil', S=12, A=3, N=150, T=40, steps=100, seed=51),

@@ -136,6 +136,49 @@ def run_cuda(name, inps):
       if c['spectral_norm']:
         d = S + A
         outs[r]['u_0'], outs[r]['u_1'], outs[r]['v_0'], outs[r]['v_1'] = _np(disc.u[r, :H]), _np(disc.u[r, H:H + 1]), _np(disc.v[r, :d]), _np(disc.v[r, d:d + H])
+  elif k == 'gailx':  # reward shaping / subtract_log_policy / depth 2 / tanh / sigmoid / state-only (models.py:157-175) on the general CUDA path
+    S, A, H = c['S'], c['A'], c['H']
+    icfg = Cfg(state_only=c['state_only'], spectral_norm=c['spectral_norm'], loss_function=c['loss'], grad_penalty=c['grad_penalty'], mixup_alpha=1, entropy_bonus=c['entropy_bonus'],
+               pos_class_prior=0.7, nonnegative_margin=float('inf'),
+               discriminator=Cfg(hidden_size=H, depth=c['depth'], activation=c['activation'], input_dropout=0.5, dropout=0.75, reward_shaping=c['reward_shaping'],
+                                 subtract_log_policy=c['subtract_log_policy'], reward_function=c['reward']))
+    disc = il_b200.GAILDiscriminator(S, A, icfg, 0.97, replicas=R)
+    assert disc.general
+    nz = lambda x: x / np.maximum(np.linalg.norm(x), 1e-12)
+    nets = [('g', disc.g_mlp, 'g_u', 'g_v')] + ([('h', disc.h_mlp, 'h_u', 'h_v')] if disc.h_mlp is not None else [])
+    for name, mlp, un, vn in nets:
+      _load_mlp(mlp, inps, name, 0, 2 * mlp.n_layers)
+      if c['spectral_norm']:
+        for r, inp in enumerate(inps):
+          getattr(disc, un)[r].copy_(_t(np.concatenate([nz(inp[f'{name}u_{l}']) for l in range(mlp.n_layers)]).astype(np.float32)))
+          getattr(disc, vn)[r].copy_(_t(np.concatenate([nz(inp[f'{name}v_{l}']) for l in range(mlp.n_layers)]).astype(np.float32)))
+    actor = None
+    if c['subtract_log_policy']:
+      actor = il_b200.SoftActor(S, A, Cfg(hidden_size=32, depth=2, activation='relu'), replicas=R)
+      _load_mlp(actor.mlp, inps, 'actor')
+    opt = il_b200.AdamW(disc.parameters(), lr=c['lr'], weight_decay=c['wd'])
+    disc.eval()
+    for s in range(c['steps']):
+      pol, exp = _batch(inps, f'p{s}_', S, A), _batch(inps, f'e{s}_', S, A)
+      disc.train()
+      il_b200.adversarial_imitation_update(actor, disc, pol, exp, opt, icfg, eps_gp=_stack(inps, f's{s}_eps_gp'), eps_mix=_stack(inps, f's{s}_eps_mix'))
+      disc.eval()
+      lp = actor._run(pol.rows[..., :S], given=pol.rows[..., S:S + A], want=('log_prob', ))['log_prob'] if actor is not None else None
+      res = disc._run(pol, want_logits=True, log_policy=lp)
+      for r in range(R): outs[r][f's{s}_reward'], outs[r][f's{s}_logits'] = _np(res['reward'][r]), _np(res['logits'][r])
+    m_all, v_all = opt.exp_avg, opt.exp_avg_sq
+    for r in range(R):
+      for name, mlp, un, vn in nets:
+        off = 0 if name == 'g' else disc.h_mlp.flat.storage_offset() - disc.flat.storage_offset()
+        _export(mlp, r, 0, name, outs[r])
+        _export(mlp, r, 0, f'adam_{name}_m', outs[r], m_all[:, off:])
+        _export(mlp, r, 0, f'adam_{name}_v', outs[r], v_all[:, off:])
+        if c['spectral_norm']:
+          uo = vo = 0
+          for l in range(mlp.n_layers):
+            od, idim = mlp.dims[l + 1], mlp.dims[l]
+            outs[r][f'{name}u_{l}'], outs[r][f'{name}v_{l}'] = _np(getattr(disc, un)[r, uo:uo + od]), _np(getattr(disc, vn)[r, vo:vo + idim])
+            uo, vo = uo + od, vo + idim
   elif k == 'gmmil':
     S, A = c['S'], c['A']
     d = il_b200.GMMILDiscriminator(S, A, Cfg(state_only=False), replicas=R)
@@ -157,6 +200,27 @@ def run_cuda(name, inps):
       if (i + 1) % c['T'] == 0: d.reset()
     rw = torch.stack(rewards, dim=1)
     for r in range(R): outs[r]['rewards'] = _np(rw[r])
+  elif k == 'mix':  # memory.py:18-23 prefill, :46-48 transfer_transitions, :51-59 index rule, models.py:287-290 mix — R == 1 (the reference's numpy stream)
+    assert R == 1
+    S, A, inp = c['S'], c['A'], inps[0]
+    tr = {key: _t(inp[f'e_{key}']) for key in ('states', 'actions', 'rewards', 'next_states', 'terminals', 'timeouts', 'weights')}
+    tr['num_trajectories'] = 3
+    em = il_b200.ReplayMemory(c['Ne'], S, A, True, transitions=tr, shared=True)
+    am = il_b200.ReplayMemory(c['size'], S, A, True)
+    am.transfer_transitions(em)
+    for i in range(c['extra']):
+      am.append(float(100 + i), _t(inp['x_states'][i:i + 1]), _t(inp['x_actions'][i:i + 1]), float(inp['x_rewards'][i]), _t(inp['x_next_states'][i:i + 1]), float(bool(inp['x_terminals'][i])), 0.0)
+    state = np.random.get_state()
+    np.random.seed(int(inp['np_seed'][0]))
+    try:
+      ia, ie = am.draw_indices_host(c['B']), em.draw_indices_host(c['B'])
+    finally:
+      np.random.set_state(state)
+    ta, te = am.gather(torch.from_numpy(ia)), em.gather(torch.from_numpy(ie))
+    il_b200.mix_expert_agent_transitions(ta, te)
+    outs[0]['idx_agent'], outs[0]['idx_expert'] = ia[0].astype(np.int64), ie[0].astype(np.int64)
+    for key in ta.keys(): outs[0][f'mixed_{key}'] = _np(ta[key])
+    outs[0]['meta'] = np.int64([int(am._idx[0]), int(am._full[0]), int(am._num_trajectories[0]), int(em._idx[0]), int(em._full[0]), int(em._num_trajectories[0])])
   elif k == 'replay':
     S, A = c['S'], c['A']
     mem = il_b200.ReplayMemory(c['size'], S, A, True, replicas=R)

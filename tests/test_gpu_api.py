@@ -53,11 +53,26 @@ def test_evaluate_agent_matches_oracle():
   actor = il_b200.SoftActor(12, 3, MODEL, replicas=R)
   rs = np.random.RandomState(3)
   u = rs.uniform(size=(R * E, env.obs)).astype(np.float32)
-  got = evaluate_agent(actor, env, E, reset_noise=torch.from_numpy(u), check_every=10)
+  stats = {}
+  got, traj = evaluate_agent(actor, env, E, return_trajectories=True, reset_noise=torch.from_numpy(u), out_stats=stats)
+  total_steps = 0
   for r in range(R):
     twin = port.SyntheticEnv('hopper', True, max_episode_steps=80)
     ref = port.evaluate_agent(actor.mlp.export_params(r, 0), twin, E, [torch.from_numpy(u[r * E + e]) for e in range(E)])
     np.testing.assert_allclose(got[r].cpu().numpy(), np.float32(ref), rtol=2e-3, atol=2e-3)
+    for e in range(E):  # evaluation.py:30-33: per-episode states / actions / rewards / terminals; the rewards add up to the return
+      t = traj[r][e]
+      L = t['rewards'].numel()
+      total_steps += L
+      assert t['states'].shape == (L, 12) and t['actions'].shape == (L, 3) and t['terminals'].shape == (L, )
+      assert float(t['terminals'].sum()) == 1.0 and float(t['terminals'][-1]) == 1.0
+      np.testing.assert_allclose(float(t['rewards'].sum()), float(got[r, e]), rtol=1e-4, atol=1e-4)
+      np.testing.assert_allclose(t['states'][0, :11].numpy(), (u[r * E + e] * 2 - 1) * 0.1, rtol=1e-6, atol=1e-7)  # environments.py:29-33 reset state
+  # the device loop ran exactly as long as the longest episode and counted every environment step
+  assert stats['env_steps'] == total_steps and stats['iterations'] == max(t['rewards'].numel() for tr in traj for t in tr)
+  # second evaluation on the same buffers (cached device graph) without trajectories gives the same returns
+  again = evaluate_agent(actor, env, E, reset_noise=torch.from_numpy(u))
+  np.testing.assert_array_equal(again.cpu().numpy(), got.cpu().numpy())
   # R == 1 returns a list of floats like the reference (evaluation.py:35)
   env1 = D4RLEnv('hopper', True, replicas=1, max_episode_steps=20)
   actor1 = il_b200.SoftActor(12, 3, MODEL, replicas=1)
@@ -240,3 +255,27 @@ def test_separate_wrap_call_equals_fused_wrap_and_transfer():
                                                                 terminals=a.terminals[:a.idx], timeouts=a.timeouts[:a.idx], weights=a.weights[:a.idx] * 0.5, num_trajectories=3))
   c.transfer_transitions(src)
   assert c.idx == a.idx and torch.equal(c.states[:a.idx], a.states[:a.idx]) and bool((c.weights[:a.idx] == 1).all())
+
+
+def test_evaluate_agent_many_episodes_uses_the_general_mlp_path():
+  """More than 32 episodes per replica: the loop body runs the per-layer MLP program instead of the fused small-batch kernel."""
+  import il_b200
+  from il_b200.environments import D4RLEnv
+  from il_b200.evaluation import evaluate_agent
+  R, E = 2, 40
+  env = D4RLEnv('halfcheetah', True, replicas=R, max_episode_steps=25)
+  actor = il_b200.SoftActor(18, 6, MODEL, replicas=R)
+  u = np.random.RandomState(5).uniform(size=(R * E, env.obs)).astype(np.float32)
+  big = evaluate_agent(actor, env, E, reset_noise=torch.from_numpy(u))
+  env2 = D4RLEnv('halfcheetah', True, replicas=R, max_episode_steps=25)
+  small = torch.stack([evaluate_agent(actor, env2, 20, reset_noise=torch.from_numpy(u.reshape(R, E, -1)[:, h * 20:(h + 1) * 20].reshape(R * 20, -1).copy())) for h in range(2)], dim=1).reshape(R, E)
+  np.testing.assert_allclose(big.cpu().numpy(), small.cpu().numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_return_allreduce_single_process_matches_torch():
+  from il_b200 import distributed
+  r = torch.randn(7, 30, device='cuda') * 10
+  s = distributed.return_stats_device(r).cpu()
+  np.testing.assert_allclose(s.numpy(), [float(r.sum()), float((r * r).sum()), 210.0], rtol=1e-5)
+  mean, std, n = distributed.return_statistics(r)
+  assert n == 210 and abs(mean - float(r.mean())) < 1e-3 and abs(std - float(r.std(unbiased=False))) < 1e-2

@@ -22,14 +22,14 @@ class _Injected:
   def sac_eps(self, B, A): return self._pop('eps_next'), self._pop('eps_new')
 
 
-def _run(algorithm, env_name, steps, start, B, H, extra=()):
+def _run(algorithm, env_name, steps, start, B, H, extra=(), graphs=False, gemm_mode='fp32', imitation=None):
   import il_b200
   from il_b200.config import load_config
   from il_b200.train import Trainer
   from oracle import loop as oloop, port
   R = 2
   cfg = load_config([f'algorithm={algorithm}', f'env={env_name}', f'steps={steps}', f'training.start={start}', f'training.batch_size={B}', 'imitation.trajectories=2',
-                     f'reinforcement.actor.hidden_size={H}', f'reinforcement.critic.hidden_size={H}', 'cuda_graphs=false', f'replicas={R}', 'seed=3', *extra])
+                     f'reinforcement.actor.hidden_size={H}', f'reinforcement.critic.hidden_size={H}', f'cuda_graphs={str(graphs).lower()}', f'gemm_mode={gemm_mode}', f'replicas={R}', 'seed=3', *extra])
   tr = Trainer(cfg, replicas=R)
   tr.inject = True
   rs = np.random.RandomState(123)
@@ -38,12 +38,23 @@ def _run(algorithm, env_name, steps, start, B, H, extra=()):
   loops = []
   for r in range(R):
     init = dict(actor=tr.actor.mlp.export_params(r, 0), twin=[tr.critic.mlp.export_params(r, 0), tr.critic.mlp.export_params(r, 1)])
-    if algorithm == 'GAIL':
+    if algorithm == 'GAIL' and not tr.discriminator.general:
       d, Hd = S + A, tr.discriminator.mlp.dims[1]
       init['g'] = tr.discriminator.mlp.export_params(r, 0)
       init['sn'] = [(tr.discriminator.u[r, :Hd].cpu().clone(), tr.discriminator.v[r, :d].cpu().clone()), (tr.discriminator.u[r, Hd:Hd + 1].cpu().clone(), tr.discriminator.v[r, d:d + Hd].cpu().clone())]
     lp = oloop.OracleLoop(algorithm, env_name, seed=3 + r, batch_size=B, start=start, memory_size=cfg.memory.size, hidden_size=H, trajectories=2, expert_raw=expert_raw, init=init,
-                          mix_expert_data=cfg.imitation.mix_expert_data)
+                          mix_expert_data=cfg.imitation.mix_expert_data, imitation=imitation)
+    if algorithm == 'GAIL' and tr.discriminator.general:  # general discriminator (g / h nets): start the oracle from the product's initial weights and spectral-norm vectors
+      dd = tr.discriminator
+      for name, mlp, u, v in (('g', dd.g_mlp, dd.g_u, dd.g_v), ('h', dd.h_mlp, dd.h_u, dd.h_v)):
+        if mlp is None: continue
+        for P_, src in zip(getattr(lp.disc, name), mlp.export_params(r, 0)): P_.data.copy_(src)
+        if dd.spectral_norm:
+          sn, uo, vo = getattr(lp.disc, name + '_sn'), 0, 0
+          for l in range(mlp.n_layers):
+            od, idim = mlp.dims[l + 1], mlp.dims[l]
+            sn[l] = (u[r, uo:uo + od].cpu().clone(), v[r, vo:vo + idim].cpu().clone())
+            uo, vo = uo + od, vo + idim
     loops.append(lp)
   if algorithm != 'SAC':  # same expert buffer on both sides
     np.testing.assert_allclose(tr.expert_memory.states.cpu().numpy(), loops[0].expert_memory.data['states'].numpy(), rtol=1e-4, atol=1e-5)
@@ -93,10 +104,41 @@ def _run(algorithm, env_name, steps, start, B, H, extra=()):
 
 
 @pytest.mark.parametrize('algorithm,env_name,extra', [('GAIL', 'hopper', ()), ('SAC', 'hopper', ()), ('GMMIL', 'halfcheetah', ()), ('PWIL', 'hopper', ()),
-                                                      ('GAIL', 'walker2d', ('imitation.mix_expert_data=mixed_batch', ))])
+                                                      ('GAIL', 'walker2d', ('imitation.mix_expert_data=mixed_batch', )),
+                                                      # train.py:133,136-143: expert rows pre-filled into every replica's ring (the ring of 60 rows wraps during the
+                                                      # transfer), PWIL's greedy relabelling of the expert's own transitions
+                                                      ('GMMIL', 'halfcheetah', ('imitation.mix_expert_data=prefill_memory', )),
+                                                      ('PWIL', 'hopper', ('imitation.mix_expert_data=prefill_memory', )),
+                                                      ('PWIL', 'hopper', ('imitation.mix_expert_data=mixed_batch', ))])
 def test_loop_matches_oracle(algorithm, env_name, extra):
   err = _run(algorithm, env_name, steps=60, start=30, B=32, H=64, extra=extra)
   print(algorithm, env_name, err)
+  assert err['state'] < 2e-3, err
+  assert err.get('q', 0) < 5e-3, err
+  assert err.get('reward', 0) < 5e-3, err
+  assert err['actor'] < 5e-4, err
+
+
+def test_loop_matches_oracle_at_the_benchmarked_configuration():
+  """The configuration bench.py times: 256-wide actor / critic, batch 256, dense layers on the 3xTF32 tcgen05
+  engine (incl. the first layer fused into its producers), the whole iteration replayed as a CUDA graph — 62 steps, 32 of them
+  updates, 2 replicas, every noise draw and index injected on both sides."""
+  err = _run('GAIL', 'hopper', steps=62, start=30, B=256, H=256, graphs=True, gemm_mode='tf32x3')
+  print('bench config', err)
+  assert err['state'] < 2e-3, err
+  assert err.get('q', 0) < 5e-3, err
+  assert err.get('reward', 0) < 5e-3, err
+  assert err['actor'] < 5e-4, err
+
+
+@pytest.mark.parametrize('extra,imitation', [
+    (('imitation.discriminator.reward_shaping=true', 'imitation.discriminator.subtract_log_policy=true'), dict(reward_shaping=True, subtract_log_policy=True)),
+    (('imitation.discriminator.depth=2', 'imitation.discriminator.activation=tanh', 'imitation.discriminator.hidden_size=32'), dict(depth=2, activation='tanh', hidden_size=32))])
+def test_loop_with_general_discriminator_matches_oracle(extra, imitation):
+  """SURVEY §8f row 3 inside the loop: reward shaping + subtract_log_policy (linear g, MLP h, log-policy from the live actor) and a depth-2
+  tanh discriminator (second-order terms of the gradient penalty), csrc/gail_general.cu vs the oracle loop (pinned to the reference's train())."""
+  err = _run('GAIL', 'hopper', steps=50, start=30, B=32, H=64, extra=extra, imitation=imitation)
+  print('general discriminator', imitation, err)
   assert err['state'] < 2e-3, err
   assert err.get('q', 0) < 5e-3, err
   assert err.get('reward', 0) < 5e-3, err
