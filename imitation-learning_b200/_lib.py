@@ -98,6 +98,7 @@ SIGNATURES = {
   'il_version': (C.c_int, []),
   'il_set_gemm_mode': (C.c_int, [vp, C.c_int]),
   'il_launch_count': (i64, [vp]),
+  'il_set_option': (C.c_int, [vp, C.c_char_p, C.c_int]),
   'il_struct_sizes': (C.c_int, [P(i32)]),
   'il_mlp_param_offsets': (C.c_int, [P(i32), C.c_int, P(i64), P(i64), P(i64)]),
   'il_row_layout': (C.c_int, [C.c_int, C.c_int, P(i32), P(i32)]),
@@ -125,6 +126,7 @@ SIGNATURES = {
   'il_replay_sample_indices': (C.c_int, [vp, P(Replay), C.c_int, C.c_int, vp, vp, u64, u64, vp, vp]),
   'il_replay_gather': (C.c_int, [vp, P(Replay), C.c_int, vp, P(Batch), vp]),
   'il_mix_expert_rows': (C.c_int, [vp, P(Batch), P(Batch), C.c_int, vp]),
+  'il_adril_relabel': (C.c_int, [vp, P(Batch), P(Batch), C.c_int, C.c_int, C.c_int, vp, vp, f32, vp, C.c_int, C.c_int, vp]),
   'il_gail_workspace_bytes': (i64, [P(GailUpdateArgs)]),
   'il_gail_update': (C.c_int, [vp, P(GailUpdateArgs), vp]),
   'il_gail_reward': (C.c_int, [vp, P(Gail), C.c_int, P(Batch), vp, i64, C.c_int, vp, vp]),
@@ -202,6 +204,10 @@ def handle(device: Optional[int] = None) -> int:
     mode = os.environ.get('IL_GEMM_MODE')
     if mode: check(lib().il_set_gemm_mode(h, GEMM_MODE[mode]))
   return h
+
+
+def set_option(name: str, value: int):
+  check(lib().il_set_option(handle(), name.encode(), int(value)))
 
 
 def stream() -> int:

@@ -443,6 +443,471 @@ __global__ void __launch_bounds__(THREADS) gail_update_kernel(const GailUpdParam
   }
 }
 
+
+// ---- register-tiled variant of the update (d <= 32, H in {32, 64, 128}) -------------------------------------------------------------
+// Same mathematics and phase order as gail_update_kernel; the three GEMM-shaped inner loops per pass run on 4 x 4 register tiles
+// with 128-bit shared-memory operand loads (the first kernel issues two shared loads per FMA and is bound by the shared-memory pipe:
+// 0.77 ms at R = 1024 = 3.9 TFLOP/s). Chunk of RB rows resident in shared memory; 2 CTAs per SM.
+struct TSmem {
+  float *W1, *G1, *W1e, *W1eT, *G1k, *b1, *w2, *w2e, *G2, *gb1, *G2k, *gb1k, *u1, *v1, *v2, *tvec, *slots, *X, *Z, *GX, *F, *DF, *CO, *red, *scal, *part;
+};
+struct TDims { int S, A, d, DP, H, B, row, RB, LDZ, HD; };
+__host__ __device__ inline int64_t tiled_carve(const TDims& g, float* base, TSmem* s) {
+  int64_t o = 0;
+  auto take = [&](int n) { float* p = base ? base + o : nullptr; o += (n + 3) / 4 * 4; return p; };
+  TSmem t;
+  t.W1 = take(g.HD); t.G1 = take(g.HD); t.W1e = take(g.H * g.DP); t.W1eT = take(g.DP * g.H); t.G1k = take(g.H * g.DP);
+  t.b1 = take(g.H); t.w2 = take(g.H); t.w2e = take(g.H); t.G2 = take(g.H); t.gb1 = take(g.H); t.G2k = take(g.H); t.gb1k = take(g.H);
+  t.u1 = take(g.H); t.v1 = take(g.d); t.v2 = take(g.H); t.tvec = take(g.H > g.d ? g.H : g.d);
+  t.slots = take(3 * gail_slot_floats(g.H, g.d));
+  t.X = take(g.RB * g.DP); t.Z = take(g.RB * g.LDZ); t.GX = take(g.RB * g.DP);
+  t.F = take(g.RB); t.DF = take(g.RB); t.CO = take(g.RB);
+  t.red = take(32); t.scal = take(32); t.part = take(4 * THREADS);
+  if (s) *s = t;
+  return o * 4;
+}
+struct GailTiledParams {
+  il_gail_update_args a;
+  TDims g;
+  int64_t off_w1, off_b1, off_w2, off_b2;
+};
+
+// Loads rows [b0, b0 + nb) into X [RB][DP] (zero padded columns / rows); CO = sample weight, DF = mixing epsilon.
+__device__ void tiled_load_rows(const TDims& g, const float* pol, const float* exp_, const float* eps, int kind, int b0, int nb, float* X, float* CO, float* DF) {
+  const RowLayout L = row_layout(g.S, g.A);
+  for (int idx = threadIdx.x; idx < g.RB * g.DP; idx += blockDim.x) {
+    const int b = idx / g.DP, j = idx % g.DP;
+    float v = 0.f;
+    if (b < nb && j < g.d) {
+      const int64_t ro = (int64_t)(b0 + b) * g.row + j;
+      if (kind == PASS_POLICY) v = pol[ro];
+      else if (kind == PASS_EXPERT) v = exp_[ro];
+      else {
+        const float e = eps[b0 + b];
+        v = __fadd_rn(__fmul_rn(e, exp_[ro]), __fmul_rn(__fsub_rn(1.f, e), pol[ro]));
+      }
+    }
+    X[idx] = v;
+  }
+  for (int b = threadIdx.x; b < g.RB; b += blockDim.x) {
+    float w = 0.f, e = 0.f;
+    if (b < nb) {
+      const int64_t wo = (int64_t)(b0 + b) * g.row + L.weight;
+      if (kind == PASS_POLICY) w = pol[wo];
+      else if (kind == PASS_EXPERT) w = exp_[wo];
+      else {
+        e = eps[b0 + b];
+        w = __fadd_rn(__fmul_rn(e, exp_[wo]), __fmul_rn(__fsub_rn(1.f, e), pol[wo]));
+      }
+    }
+    CO[b] = w;
+    DF[b] = e;
+  }
+}
+
+// acc[4 b][4 h] = bias[h] + sum_j IN[b][j] * WT[j][h] on 4 x 4 register tiles, handed to `epi(tb, th, acc)`; lanes run over the h-tiles
+// (operand rows broadcast). Tile t = tid + m * 256 keeps th = t % (H / 4) fixed per thread (256 is a multiple of H / 4).
+template <typename Epi>
+__device__ __forceinline__ void tiled_rows_times_wt(const TDims& g, const float* IN, const float* WT, const float* bias, Epi epi) {
+  const int nth = g.H >> 2, ntb = g.RB >> 2;
+  for (int t = threadIdx.x; t < nth * ntb; t += blockDim.x) {
+    const int th = t % nth, tb = t / nth;
+    float acc[4][4];
+    const float4 bv = bias ? *reinterpret_cast<const float4*>(bias + 4 * th) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[i][0] = bv.x; acc[i][1] = bv.y; acc[i][2] = bv.z; acc[i][3] = bv.w; }
+    const float* xr = IN + (4 * tb) * g.DP;
+    for (int j4 = 0; j4 < g.DP; j4 += 4) {
+      float4 x[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = *reinterpret_cast<const float4*>(xr + i * g.DP + j4);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const float4 w = *reinterpret_cast<const float4*>(WT + (j4 + jj) * g.H + 4 * th);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float xv = jj == 0 ? x[i].x : (jj == 1 ? x[i].y : (jj == 2 ? x[i].z : x[i].w));
+          acc[i][0] = fmaf(xv, w.x, acc[i][0]); acc[i][1] = fmaf(xv, w.y, acc[i][1]); acc[i][2] = fmaf(xv, w.z, acc[i][2]); acc[i][3] = fmaf(xv, w.w, acc[i][3]);
+        }
+      }
+    }
+    epi(tb, th, acc);
+  }
+}
+// hidden = relu(W1e x + b1) stored to Z [RB][LDZ]
+__device__ __forceinline__ void tiled_hidden(const TDims& g, const float* X, const float* W1eT, const float* b1, float* Z) {
+  tiled_rows_times_wt(g, X, W1eT, b1, [&](int tb, int th, float (&acc)[4][4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(Z + (4 * tb + i) * g.LDZ + 4 * th) = make_float4(fmaxf(acc[i][0], 0.f), fmaxf(acc[i][1], 0.f), fmaxf(acc[i][2], 0.f), fmaxf(acc[i][3], 0.f));
+  });
+}
+
+// acc[4 h][4 j] += sum over this thread's rows of  DZ(b, 4 th + k) * IN[b][4 tj + c]   (weight-gradient shape [H][DP], K = rows split 4 ways
+// over lane groups: lane = th_low + 8 * ks). DZ(b, h) is produced by `dz` from Z / per-row coefficients.
+// Slot q of a thread covers tile (warp * 8 + lane % 8) + 64 q; ks = (lane / 8) is the row group.
+struct TileMap { int th, tj, active; };
+__device__ __forceinline__ TileMap tiled_wgrad_map(const TDims& g, int q) {
+  TileMap m;
+  const int nth = g.H >> 2, ntj = g.DP >> 2;
+  const int tile = (threadIdx.x >> 5) * 8 + (threadIdx.x & 7) + 64 * q;
+  m.active = tile < nth * ntj;
+  const int tc = m.active ? tile : 0;
+  m.th = tc % nth; m.tj = tc / nth;
+  return m;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(THREADS, 2) gail_update_tiled_kernel(const GailTiledParams p) {
+  extern __shared__ __align__(16) float sm[];
+  const TDims g = p.g;
+  TSmem s;
+  tiled_carve(g, sm, &s);
+  const il_gail_update_args& a = p.a;
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const int H = g.H, d = g.d, B = g.B, DP = g.DP, LDZ = g.LDZ;
+  float* prm = a.disc.g.params + (int64_t)r * a.disc.g.stride;
+  const bool sn = a.disc.u != nullptr;
+  const float* pol = a.policy.rows + (int64_t)r * a.policy.replica_stride;
+  const float* exp_ = a.expert.rows + (int64_t)r * a.expert.replica_stride;
+  const float* eps_gp = a.eps_gp ? a.eps_gp + (int64_t)r * B : nullptr;
+  const float* eps_mix = a.eps_mix ? a.eps_mix + (int64_t)r * B : nullptr;
+  const float invB = 1.f / (float)B;
+
+  for (int i = tid; i < H * d; i += THREADS) { s.W1[i] = prm[p.off_w1 + i]; s.G1[i] = 0.f; }
+  for (int h = tid; h < H; h += THREADS) {
+    s.b1[h] = prm[p.off_b1 + h]; s.w2[h] = prm[p.off_w2 + h]; s.G2[h] = 0.f; s.gb1[h] = 0.f;
+    if (sn) { s.u1[h] = a.disc.u[(int64_t)r * a.disc.u_stride + h]; s.v2[h] = a.disc.v[(int64_t)r * a.disc.v_stride + d + h]; }
+  }
+  if (sn) for (int j = tid; j < d; j += THREADS) s.v1[j] = a.disc.v[(int64_t)r * a.disc.v_stride + j];
+  const float b2 = prm[p.off_b2];
+  float u2 = sn ? a.disc.u[(int64_t)r * a.disc.u_stride + H] : 1.f;
+  __syncthreads();
+
+  int kinds[3], n_pass = 0;
+  const float* pass_eps[3] = {nullptr, nullptr, nullptr};
+  int gp_pass = -1;
+  if (a.loss_function == IL_LOSS_MIXUP) { kinds[n_pass] = PASS_MIX; pass_eps[n_pass++] = eps_mix; }
+  else { kinds[n_pass++] = PASS_POLICY; kinds[n_pass++] = PASS_EXPERT; }
+  if (a.grad_penalty > 0.f) { gp_pass = n_pass; kinds[n_pass] = PASS_MIX; pass_eps[n_pass++] = eps_gp; }
+
+  // ---- phase 1: power iterations (identical to gail_update_kernel) -------------------------------------------------------------
+  const int SF = gail_slot_floats(H, d);
+  for (int k = 0; k < n_pass; ++k) {
+    float* slot = s.slots + k * SF;
+    float sig1 = 1.f, sig2 = 1.f;
+    if (sn) {
+      sig1 = spectral_sigma(s.W1, s.u1, s.v1, s.tvec, s.red, H, d, a.training != 0);
+      float t = 0.f;
+      if (a.training) {
+        for (int h = tid; h < H; h += THREADS) t = fmaf(s.w2[h], s.v2[h], t);
+        t = bsum(t, s.red);
+        u2 = t / fmaxf(fabsf(t), 1e-12f);
+        for (int h = tid; h < H; h += THREADS) s.tvec[h] = s.w2[h] * u2;
+        __syncthreads();
+        const float dn = fmaxf(sqrtf(sq_norm(s.tvec, H, s.red)), 1e-12f);
+        for (int h = tid; h < H; h += THREADS) s.v2[h] = s.tvec[h] / dn;
+        __syncthreads();
+      }
+      t = 0.f;
+      for (int h = tid; h < H; h += THREADS) t = fmaf(s.w2[h], s.v2[h], t);
+      sig2 = u2 * bsum(t, s.red);
+    }
+    for (int h = tid; h < H; h += THREADS) { slot[h] = s.u1[h]; slot[H + d + h] = s.v2[h]; }
+    for (int j = tid; j < d; j += THREADS) slot[H + j] = s.v1[j];
+    if (tid == 0) { slot[2 * H + d] = sig1; slot[2 * H + d + 1] = sig2; slot[2 * H + d + 2] = u2; }
+    __syncthreads();
+  }
+
+  auto set_effective = [&](const float* slot) {  // W1e [H][DP] and its transpose [DP][H], zero padded; w2e
+    const float sig1 = slot[2 * H + d], sig2 = slot[2 * H + d + 1];
+    for (int i = tid; i < H * DP; i += THREADS) {
+      const int h = i / DP, j = i % DP;
+      const float v = j < d ? s.W1[h * d + j] / sig1 : 0.f;
+      s.W1e[i] = v;
+      s.W1eT[j * H + h] = v;
+    }
+    for (int h = tid; h < H; h += THREADS) s.w2e[h] = s.w2[h] / sig2;
+  };
+  auto logits = [&](int nb, float* FO) {  // FO[b] = w2e . Z[b] + b2, one warp per row
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int b = warp; b < nb; b += THREADS / 32) {
+      float f = 0.f;
+      for (int h = lane; h < H; h += 32) f = fmaf(s.w2e[h], s.Z[b * LDZ + h], f);
+      f = warp_sum(f);
+      if (lane == 0) FO[b] = f + b2;
+    }
+  };
+
+  // ---- phase 2 (PUGAIL): batch scalar of the clamp ---------------------------------------------------------------------------------
+  float pu_gate = 1.f, loss_bce = 0.f, loss_gp = 0.f;
+  if (a.loss_function == IL_LOSS_PUGAIL) {
+    float sums[2] = {0.f, 0.f};
+    for (int k = 0; k < 2; ++k) {
+      set_effective(s.slots + k * SF);
+      __syncthreads();
+      float part = 0.f;
+      for (int b0 = 0; b0 < B; b0 += g.RB) {
+        const int nb = min(g.RB, B - b0);
+        tiled_load_rows(g, pol, exp_, nullptr, kinds[k], b0, nb, s.X, s.CO, s.DF);
+        __syncthreads();
+        tiled_hidden(g, s.X, s.W1eT, s.b1, s.Z);
+        __syncthreads();
+        logits(nb, s.F);
+        __syncthreads();
+        for (int b = tid; b < nb; b += THREADS) part += s.CO[b] * softplusf(s.F[b]);
+        __syncthreads();
+      }
+      sums[k] = bsum(part, s.red);
+    }
+    pu_gate = (a.pos_class_prior * (sums[1] * invB) - sums[0] * invB) >= -a.nonnegative_margin ? 1.f : 0.f;
+  }
+
+  // ---- phase 3: forward + backward per pass ---------------------------------------------------------------------------------------
+  TileMap wm[NT];
+#pragma unroll
+  for (int q = 0; q < NT; ++q) wm[q] = tiled_wgrad_map(g, q);
+  const int wks = (tid >> 3) & 3;  // row group of this lane in the weight-gradient tiles
+  const int parts = THREADS / H, hh = tid % H, part = tid / H;  // column-sum helpers: hidden unit hh, row slice `part`
+  float gb2 = 0.f;
+  for (int k = 0; k < n_pass; ++k) {
+    const float* slot = s.slots + k * SF;
+    const float sig1 = slot[2 * H + d], sig2 = slot[2 * H + d + 1], u2k = slot[2 * H + d + 2];
+    const int kind = kinds[k];
+    const bool is_gp = (k == gp_pass);
+    set_effective(slot);
+    for (int h = tid; h < H; h += THREADS) { s.G2k[h] = 0.f; s.gb1k[h] = 0.f; }
+    float wacc[NT][4][4];  // this thread's tiles of dL/dW1e, summed over its rows of every chunk
+#pragma unroll
+    for (int q = 0; q < NT; ++q)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) wacc[q][i][0] = wacc[q][i][1] = wacc[q][i][2] = wacc[q][i][3] = 0.f;
+    float gb2k = 0.f, loss_part = 0.f;
+    __syncthreads();
+    float4 w2t[NT];
+#pragma unroll
+    for (int q = 0; q < NT; ++q) w2t[q] = *reinterpret_cast<const float4*>(s.w2e + 4 * wm[q].th);
+    // wacc[q] += sum over this lane's rows of  (coef_b * 1[hidden > 0] * w2e)[b, 4 th + i] * IN[b][4 tj + c]
+    auto wgrad = [&](const float* IN, int nb) {
+#pragma unroll
+      for (int q = 0; q < NT; ++q) {
+        if (!wm[q].active) continue;
+        for (int b = wks; b < nb; b += 4) {
+          const float4 z = *reinterpret_cast<const float4*>(s.Z + b * LDZ + 4 * wm[q].th);
+          const float4 x = *reinterpret_cast<const float4*>(IN + b * DP + 4 * wm[q].tj);
+          const float cf = s.DF[b];
+          const float dz[4] = {z.x > 0.f ? cf * w2t[q].x : 0.f, z.y > 0.f ? cf * w2t[q].y : 0.f, z.z > 0.f ? cf * w2t[q].z : 0.f, z.w > 0.f ? cf * w2t[q].w : 0.f};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            wacc[q][i][0] = fmaf(dz[i], x.x, wacc[q][i][0]); wacc[q][i][1] = fmaf(dz[i], x.y, wacc[q][i][1]);
+            wacc[q][i][2] = fmaf(dz[i], x.z, wacc[q][i][2]); wacc[q][i][3] = fmaf(dz[i], x.w, wacc[q][i][3]);
+          }
+        }
+      }
+    };
+    for (int b0 = 0; b0 < B; b0 += g.RB) {
+      const int nb = min(g.RB, B - b0);
+      tiled_load_rows(g, pol, exp_, pass_eps[k], kind, b0, nb, s.X, s.CO, s.DF);
+      __syncthreads();
+      tiled_hidden(g, s.X, s.W1eT, s.b1, s.Z);  // hidden = relu(W1e x + b1)
+      __syncthreads();
+      if (!is_gp) {
+        logits(nb, s.F);
+        __syncthreads();
+        for (int b = tid; b < g.RB; b += THREADS) {
+          float df = 0.f;
+          if (b < nb) {
+            const float f = s.F[b], w = s.CO[b], sg = sigmoidf(f);
+            if (a.loss_function == IL_LOSS_MIXUP) {
+              const float e = s.DF[b];
+              df = w * (sg - e) * invB;
+              loss_part += e * w * softplusf(-f) + (1.f - e) * w * softplusf(f);
+            } else if (a.loss_function == IL_LOSS_BCE) {
+              df = kind == PASS_EXPERT ? w * (sg - 1.f) * invB : w * sg * invB;
+              loss_part += kind == PASS_EXPERT ? w * softplusf(-f) : w * softplusf(f);
+            } else {
+              const float pr = a.pos_class_prior;
+              df = kind == PASS_EXPERT ? pr * w * (sg - 1.f) * invB + pu_gate * pr * w * sg * invB : -pu_gate * w * sg * invB;
+              loss_part += kind == PASS_EXPERT ? pr * w * softplusf(-f) + pu_gate * pr * w * softplusf(f) : -pu_gate * w * softplusf(f);
+            }
+            if (a.entropy_bonus > 0.f) df += a.entropy_bonus * w * f * sg * (1.f - sg) * invB;
+            gb2k += df;
+          }
+          s.DF[b] = df;  // padded rows: 0
+        }
+        __syncthreads();
+        // dL/dw2e[h] += sum_b df_b hidden[b,h];  dL/db1[h] += sum_b dz[b,h], dz = df_b w2e[h] 1[hidden > 0]
+        {
+          float acc2 = 0.f, accb = 0.f;
+          if (part < parts) {
+            const float w2h = s.w2e[hh];
+            const int per = (nb + parts - 1) / parts, b_lo = part * per, b_hi = min(nb, b_lo + per);
+            for (int b = b_lo; b < b_hi; ++b) {
+              const float hv = s.Z[b * LDZ + hh], df = s.DF[b];
+              acc2 = fmaf(df, hv, acc2);
+              accb += hv > 0.f ? df * w2h : 0.f;
+            }
+          }
+          s.part[tid] = acc2;
+          s.part[THREADS + tid] = accb;
+          __syncthreads();
+          for (int h = tid; h < H; h += THREADS) {
+            float a2 = 0.f, ab = 0.f;
+            for (int q = 0; q < parts; ++q) { a2 += s.part[q * H + h]; ab += s.part[THREADS + q * H + h]; }
+            s.G2k[h] += a2;
+            s.gb1k[h] += ab;
+          }
+        }
+        wgrad(s.X, nb);  // dL/dW1e[h, j] += sum_b dz[b,h] x[b,j]   (dz formed on the fly from the hidden tile)
+        __syncthreads();
+      } else {
+        // gradient penalty: g_x[b][j] = sum_h q[b][h] W1e[h][j], q = 1[hidden > 0] w2e[h]; 4 x 4 tiles, h split over 4 lane groups
+        {
+          const int ntj = DP >> 2, ntiles = (g.RB >> 2) * ntj, l8 = tid & 7, ks = (tid >> 3) & 3;
+          for (int base = (tid >> 5) * 8; base < ntiles; base += (THREADS / 32) * 8) {  // warp-uniform trip count (full-mask shuffles inside)
+            const bool valid = base + l8 < ntiles;
+            const int tile = valid ? base + l8 : 0, tj = tile % ntj, tb = tile / ntj;
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+            for (int h = ks; h < H; h += 4) {
+              const float4 w = *reinterpret_cast<const float4*>(s.W1e + h * DP + 4 * tj);
+              const float w2h = s.w2e[h];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float q = s.Z[(4 * tb + i) * LDZ + h] > 0.f ? w2h : 0.f;
+                acc[i][0] = fmaf(q, w.x, acc[i][0]); acc[i][1] = fmaf(q, w.y, acc[i][1]); acc[i][2] = fmaf(q, w.z, acc[i][2]); acc[i][3] = fmaf(q, w.w, acc[i][3]);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                float v = acc[i][c];
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                acc[i][c] = v;
+              }
+            if (valid && ks == 0) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(s.GX + (4 * tb + i) * DP + 4 * tj) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            }
+          }
+        }
+        __syncthreads();
+        for (int b = tid; b < g.RB; b += THREADS) {
+          float coef = 0.f;
+          if (b < nb) {
+            float pen = 0.f;
+            for (int j = 0; j < d; ++j) pen = fmaf(s.GX[b * DP + j], s.GX[b * DP + j], pen);
+            const float wmix = s.CO[b];
+            loss_part += a.grad_penalty * wmix * pen;
+            coef = 2.f * a.grad_penalty * wmix * invB;
+          }
+          s.DF[b] = coef;
+        }
+        __syncthreads();
+        // dL/dw2e[h] += sum_b coef_b m[b,h] (W1e g_b)[h]: the product is formed tile by tile and reduced in registers (th is fixed per thread)
+        {
+          float a2[4] = {0.f, 0.f, 0.f, 0.f};
+          tiled_rows_times_wt(g, s.GX, s.W1eT, nullptr, [&](int tb, int th, float (&acc)[4][4]) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 z = *reinterpret_cast<const float4*>(s.Z + (4 * tb + i) * LDZ + 4 * th);
+              const float cf = s.DF[4 * tb + i];  // 0 on padded rows
+              a2[0] = fmaf(z.x > 0.f ? cf : 0.f, acc[i][0], a2[0]); a2[1] = fmaf(z.y > 0.f ? cf : 0.f, acc[i][1], a2[1]);
+              a2[2] = fmaf(z.z > 0.f ? cf : 0.f, acc[i][2], a2[2]); a2[3] = fmaf(z.w > 0.f ? cf : 0.f, acc[i][3], a2[3]);
+            }
+          });
+          *reinterpret_cast<float4*>(s.part + 4 * tid) = make_float4(a2[0], a2[1], a2[2], a2[3]);
+          __syncthreads();
+          const int nth = H >> 2;
+          for (int h = tid; h < H; h += THREADS) {
+            float t2 = 0.f;
+            for (int q = h >> 2; q < THREADS; q += nth) t2 += s.part[4 * q + (h & 3)];  // threads whose tile column block is h / 4
+            s.G2k[h] += t2;
+          }
+          __syncthreads();
+        }
+        wgrad(s.GX, nb);  // dL/dW1e[h, j] += sum_b coef_b (m[b,h] w2e[h]) g_b[j]
+        __syncthreads();
+      }
+    }
+    // gather the weight-gradient tiles: sum over the 4 row groups, then G1k [H][DP] in shared memory
+#pragma unroll
+    for (int q = 0; q < NT; ++q) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float v = wacc[q][i][c];
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          wacc[q][i][c] = v;
+        }
+      if (wm[q].active && wks == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(s.G1k + (4 * wm[q].th + i) * DP + 4 * wm[q].tj) = make_float4(wacc[q][i][0], wacc[q][i][1], wacc[q][i][2], wacc[q][i][3]);
+      }
+    }
+    __syncthreads();
+    // ---- spectral-norm backward: dL/dW = (G - <G, W_eff> u v^T) / sigma, accumulated over the passes
+    float inner1 = 0.f, inner2 = 0.f;
+    if (sn) {
+      for (int e = tid; e < H * d; e += THREADS) inner1 = fmaf(s.G1k[(e / d) * DP + e % d], s.W1e[(e / d) * DP + e % d], inner1);
+      inner1 = bsum(inner1, s.red);
+      for (int h = tid; h < H; h += THREADS) inner2 = fmaf(s.G2k[h], s.w2e[h], inner2);
+      inner2 = bsum(inner2, s.red);
+    }
+    for (int e = tid; e < H * d; e += THREADS) {
+      const int h = e / d, j = e % d;
+      const float gk = s.G1k[h * DP + j];
+      s.G1[e] += sn ? (gk - inner1 * slot[h] * slot[H + j]) / sig1 : gk;
+    }
+    for (int h = tid; h < H; h += THREADS) {
+      s.G2[h] += sn ? (s.G2k[h] - inner2 * u2k * slot[H + d + h]) / sig2 : s.G2k[h];
+      s.gb1[h] += s.gb1k[h];
+    }
+    gb2k = bsum(gb2k, s.red);
+    gb2 += gb2k;
+    loss_part = bsum(loss_part, s.red);
+    if (is_gp) loss_gp = loss_part * invB; else loss_bce += loss_part * invB;
+    __syncthreads();
+  }
+  if (tid == 0 && a.out_losses) { a.out_losses[r * 2 + 0] = loss_bce; a.out_losses[r * 2 + 1] = loss_gp; }
+
+  // ---- AdamW (train.py:84; torch _single_tensor_adam) -----------------------------------------------------------
+  if (tid == 0) {
+    const double t = (double)*a.opt.step;
+    s.scal[0] = (float)(a.opt.lr / (1.0 - pow(a.opt.beta1, t)));
+    s.scal[1] = (float)sqrt(1.0 - pow(a.opt.beta2, t));
+  }
+  __syncthreads();
+  const float step_size = s.scal[0], bc2_sqrt = s.scal[1];
+  const float decay = (float)(1.0 - a.opt.lr * a.opt.weight_decay), w1c = (float)(1.0 - a.opt.beta1), w2c = (float)(1.0 - a.opt.beta2), beta2 = (float)a.opt.beta2,
+              eps = (float)a.opt.eps;
+  const bool has_wd = a.opt.weight_decay != 0.0;
+  float* am = a.opt.m + (int64_t)r * a.disc.g.stride;
+  float* avv = a.opt.v + (int64_t)r * a.disc.g.stride;
+  auto adam = [&](int64_t off, float grad) {
+    float pi = prm[off], mi = am[off], vi = avv[off];
+    if (has_wd) pi = __fmul_rn(pi, decay);
+    mi = __fadd_rn(mi, __fmul_rn(w1c, __fsub_rn(grad, mi)));
+    vi = __fadd_rn(__fmul_rn(vi, beta2), __fmul_rn(__fmul_rn(w2c, grad), grad));
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);
+    pi = __fadd_rn(pi, __fmul_rn(-step_size, __fdiv_rn(mi, denom)));
+    prm[off] = pi; am[off] = mi; avv[off] = vi;
+  };
+  for (int i = tid; i < H * d; i += THREADS) adam(p.off_w1 + i, s.G1[i]);
+  for (int h = tid; h < H; h += THREADS) { adam(p.off_b1 + h, s.gb1[h]); adam(p.off_w2 + h, s.G2[h]); }
+  if (tid == 0) adam(p.off_b2, gb2);
+  if (sn) {
+    for (int h = tid; h < H; h += THREADS) { a.disc.u[(int64_t)r * a.disc.u_stride + h] = s.u1[h]; a.disc.v[(int64_t)r * a.disc.v_stride + d + h] = s.v2[h]; }
+    for (int j = tid; j < d; j += THREADS) a.disc.v[(int64_t)r * a.disc.v_stride + j] = s.v1[j];
+    if (tid == 0) a.disc.u[(int64_t)r * a.disc.u_stride + H] = u2;
+  }
+}
+
 __global__ void __launch_bounds__(THREADS) gail_reward_kernel(const GailRewParams p) {
   extern __shared__ __align__(16) float sm[];
   const GailDims g = p.g;
@@ -535,6 +1000,25 @@ extern "C" int il_gail_update(il_handle* h, const il_gail_update_args* a, void* 
   p.off_w1 = off[0]; p.off_b1 = off[1]; p.off_w2 = off[2]; p.off_b2 = off[3];
   cudaStream_t st = (cudaStream_t)stream;
   IL_LAUNCH(h, gail_tick_kernel, 1, 1, 0, st, a->opt.step);
+  const int tiled_tiles = (p.g.H / 4) * ((p.g.d + 3) / 4);
+  if (h->gail_tiled && p.g.d <= 32 && (p.g.H == 32 || p.g.H == 64 || p.g.H == 128) && a->policy.B % 4 == 0 && tiled_tiles <= 256) {
+    GailTiledParams tp;
+    tp.a = *a;
+    TDims& t = tp.g;
+    t.S = p.g.S; t.A = p.g.A; t.d = p.g.d; t.DP = (p.g.d + 3) / 4 * 4; t.H = p.g.H; t.B = p.g.B; t.row = p.g.row; t.LDZ = p.g.H + 4; t.HD = (p.g.H * p.g.d + 3) / 4 * 4;
+    t.RB = a->policy.B < 128 ? (a->policy.B + 3) / 4 * 4 : 128;
+    tp.off_w1 = off[0]; tp.off_b1 = off[1]; tp.off_w2 = off[2]; tp.off_b2 = off[3];
+    int64_t tsm = tiled_carve(t, nullptr, nullptr);
+    while (tsm > 110 * 1024 && t.RB > 32) {  // wider nets: shorter row chunks keep two CTAs per SM
+      t.RB /= 2;
+      tsm = tiled_carve(t, nullptr, nullptr);
+    }
+    IL_CHECK(tsm <= 110 * 1024, "il_gail_update: tiled kernel shared memory %lld", (long long)tsm);
+    if (tiled_tiles <= 64) IL_LAUNCH(h, gail_update_tiled_kernel<1>, a->R, THREADS, (size_t)tsm, st, tp);
+    else if (tiled_tiles <= 128) IL_LAUNCH(h, gail_update_tiled_kernel<2>, a->R, THREADS, (size_t)tsm, st, tp);
+    else IL_LAUNCH(h, gail_update_tiled_kernel<4>, a->R, THREADS, (size_t)tsm, st, tp);
+    return 0;
+  }
   const int ne = (p.g.H * p.g.d + THREADS - 1) / THREADS;
 #define GAIL_LAUNCH(NE) IL_LAUNCH(h, gail_update_kernel<NE>, a->R, THREADS, (size_t)smem, st, p)
   if (ne <= 4) GAIL_LAUNCH(4);
@@ -565,5 +1049,8 @@ int gail_init() {
   IL_CUDA(cudaFuncSetAttribute(gail_update_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   IL_CUDA(cudaFuncSetAttribute(gail_update_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   IL_CUDA(cudaFuncSetAttribute(gail_reward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  IL_CUDA(cudaFuncSetAttribute(gail_update_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  IL_CUDA(cudaFuncSetAttribute(gail_update_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  IL_CUDA(cudaFuncSetAttribute(gail_update_tiled_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   return 0;
 }

@@ -165,6 +165,37 @@ __global__ void replay_transfer_state_kernel(il_replay dst, const float* __restr
   }
 }
 
+// RewardRelabeller.resample_and_relabel (models.py:297-318), AdRIL (update_freq > 0) / SQIL (update_freq == 0). One thread per float4 of a row.
+//   balanced: the whole batch is the expert batch on "expert" calls (flag[0] != 0) and the policy batch otherwise; the flag alternates per call.
+//   unbalanced: the first B / 2 rows become expert rows (mix_expert_agent_transitions).
+//   rewards: expert rows 1 / num_expert_trajectories (AdRIL) or 1 (SQIL); policy rows -1[round(step) > round(row step)] / max(num_trajectories, 1) or 0.
+__global__ void adril_relabel_kernel(float* __restrict__ rows, int64_t rs, const float* __restrict__ ex, int64_t ex_rs, int R, int B, int row4, int off_reward, int off_step,
+                                     int balanced, int update_freq, const int32_t* __restrict__ flag, const float* __restrict__ step_f, float step_offset,
+                                     const int32_t* __restrict__ num_traj, int traj_shared, int num_expert_traj) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)R * B * row4) return;
+  const int q = (int)(t % row4);
+  const int64_t rb = t / row4;
+  const int r = (int)(rb / B), b = (int)(rb % B);
+  const bool expert_row = balanced ? (flag[0] != 0) : (b < B / 2);
+  float4* dst = reinterpret_cast<float4*>(rows + (int64_t)r * rs + (int64_t)b * row4 * 4) + q;
+  float4 v = expert_row ? __ldg(reinterpret_cast<const float4*>(ex + (int64_t)r * ex_rs + (int64_t)b * row4 * 4) + q) : *dst;
+  if (off_reward / 4 == q) {
+    float rew;
+    if (expert_row) rew = update_freq > 0 ? 1.f / (float)num_expert_traj : 1.f;
+    else if (update_freq > 0) {
+      const float* rp = expert_row ? nullptr : rows + (int64_t)r * rs + (int64_t)b * row4 * 4;
+      const float round_num = ceilf((step_f[r] + step_offset) / (float)update_freq);        // ceil(step / update_freq), models.py:313
+      const float row_round = ceilf(rp[off_step] / (float)update_freq);                       // torch.ceil(transitions['step'] / update_freq)
+      const int nt = num_traj[traj_shared ? 0 : r];
+      rew = -1.f * (round_num > row_round ? 1.f : 0.f) / (float)(nt > 1 ? nt : 1);
+    } else rew = 0.f;
+    reinterpret_cast<float*>(&v)[off_reward % 4] = rew;
+  }
+  if (expert_row || off_reward / 4 == q) *dst = v;
+}
+__global__ void flag_toggle_kernel(int32_t* flag) { flag[0] = flag[0] ? 0 : 1; }
+
 int check_replay(const il_replay* m, const char* what) {
   IL_CHECK(m && m->rows && m->idx && m->full && m->num_trajectories, "%s: null replay field", what);
   IL_CHECK(m->size > 0 && m->S > 0 && m->A > 0, "%s: size=%d S=%d A=%d", what, m->size, m->S, m->A);
@@ -230,6 +261,23 @@ extern "C" int il_replay_gather(il_handle* h, const il_replay* mem, int R, const
   const int64_t total = (int64_t)R * out->B * row4;
   IL_LAUNCH(h, replay_gather_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, mem->rows, mem->replica_stride, mem->size, row4, idx, out->rows,
             out->replica_stride, R, out->B);
+  return 0;
+}
+
+extern "C" int il_adril_relabel(il_handle* h, const il_batch* batch, const il_batch* expert, int R, int balanced, int update_freq, int32_t* sample_expert_flag,
+                                const float* step_f, float step_offset, const int32_t* num_trajectories, int trajectories_shared, int num_expert_trajectories, void* stream) {
+  IL_CHECK(h && R > 0, "il_adril_relabel: bad argument");
+  IL_TRY(check_batch(batch, "il_adril_relabel(batch)"));
+  IL_TRY(check_batch(expert, "il_adril_relabel(expert)"));
+  IL_CHECK(batch->row == expert->row && expert->B >= (balanced ? batch->B : batch->B / 2), "il_adril_relabel: shape mismatch");
+  IL_CHECK(!balanced || sample_expert_flag, "il_adril_relabel: balanced sampling needs the alternation flag");
+  IL_CHECK(update_freq == 0 || (step_f && num_trajectories && num_expert_trajectories > 0), "il_adril_relabel: AdRIL relabelling needs step / trajectory counters");
+  const RowLayout L = row_layout(batch->S, batch->A);
+  const int row4 = batch->row / 4;
+  const int64_t total = (int64_t)R * batch->B * row4;
+  IL_LAUNCH(h, adril_relabel_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, batch->rows, batch->replica_stride, expert->rows, expert->replica_stride, R, batch->B, row4,
+            L.reward, L.step, balanced, update_freq, sample_expert_flag, step_f, step_offset, num_trajectories, trajectories_shared, num_expert_trajectories);
+  if (balanced) IL_LAUNCH(h, flag_toggle_kernel, 1, 1, 0, (cudaStream_t)stream, sample_expert_flag);
   return 0;
 }
 

@@ -550,3 +550,25 @@ def mix_expert_agent_transitions(transitions: TransitionBatch, expert_transition
   """:287-290 — first B // 2 rows of every field replaced by expert rows."""
   b, e = transitions.c_struct(), expert_transitions.c_struct()
   _lib.check(_lib.lib().il_mix_expert_rows(_lib.handle(), C.byref(b), C.byref(e), transitions.R, _lib.stream()))
+
+
+class RewardRelabeller:
+  """:293-318 — AdRIL (update_freq > 0) / SQIL (update_freq == 0): builds the training batch from expert and policy data and labels the
+  rewards; one kernel, with the balanced-sampling alternation flag kept on the device so the call can live inside a captured CUDA graph."""
+
+  def __init__(self, update_freq: int, balanced: bool, device=None):
+    self.update_freq, self.balanced = int(update_freq), bool(balanced)
+    self.device = torch.device('cuda') if device is None else torch.device(device)
+    self._flag = torch.ones(1, dtype=torch.int32, device=self.device)  # sample_expert = True (:295)
+
+  @property
+  def sample_expert(self) -> bool: return bool(self._flag.item())
+
+  def resample_and_relabel(self, transitions: TransitionBatch, expert_transitions: TransitionBatch, step, num_trajectories, num_expert_trajectories: int, step_offset: float = 0.0):
+    """`step`: the loop step (int, or a device float tensor [R] + `step_offset`); `num_trajectories`: int or the device counters [R] of the replay memory."""
+    R, dev = transitions.R, self.device
+    step_t = step if torch.is_tensor(step) else torch.full((R, ), float(step), device=dev)
+    nt = num_trajectories if torch.is_tensor(num_trajectories) else torch.full((R, ), int(num_trajectories), dtype=torch.int32, device=dev)
+    b, e = transitions.c_struct(), expert_transitions.c_struct()
+    _lib.check(_lib.lib().il_adril_relabel(_lib.handle(), C.byref(b), C.byref(e), R, int(self.balanced), self.update_freq, self._flag.data_ptr(), step_t.data_ptr(), float(step_offset),
+                                           nt.data_ptr(), int(nt.numel() == 1), int(num_expert_trajectories), _lib.stream()))

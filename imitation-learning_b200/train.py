@@ -22,11 +22,11 @@ from .config import Config, load_config
 from .environments import D4RLEnv, ENVS
 from .evaluation import evaluate_agent
 from .memory import ReplayMemory, TransitionBatch
-from .models import GAILDiscriminator, GMMILDiscriminator, PWILDiscriminator, SoftActor, TwinCritic, _RNG, create_target_network
+from .models import GAILDiscriminator, GMMILDiscriminator, PWILDiscriminator, RewardRelabeller, SoftActor, TwinCritic, _RNG, create_target_network
 from .net import ReplicaRNG
 from .optim import Adam, AdamW
 
-ACCELERATED = ['BC', 'SAC', 'GAIL', 'GMMIL', 'PWIL']
+ACCELERATED = ['AdRIL', 'BC', 'SAC', 'GAIL', 'GMMIL', 'PWIL']
 
 
 def check_config(cfg: Config):
@@ -38,6 +38,9 @@ def check_config(cfg: Config):
   assert cfg.imitation.trajectories >= 0
   assert cfg.imitation.subsample >= 1
   assert cfg.imitation.mix_expert_data in ['none', 'mixed_batch', 'prefill_memory']
+  if cfg.algorithm == 'AdRIL':  # train.py:35-37
+    assert cfg.imitation.mix_expert_data == 'mixed_batch'
+    assert cfg.imitation.update_freq >= 0
   if cfg.algorithm == 'GAIL':
     assert cfg.imitation.mix_expert_data != 'prefill_memory'
     assert cfg.imitation.discriminator.reward_function in ['AIRL', 'FAIRL', 'GAIL']
@@ -95,6 +98,8 @@ class Trainer:
     if self.algorithm == 'GAIL':
       self.discriminator_optimiser = AdamW(self.discriminator.parameters(), lr=cfg.imitation.learning_rate, weight_decay=cfg.imitation.weight_decay)
       self.discriminator.eval()  # train.py:147
+    elif self.algorithm == 'AdRIL':
+      self.discriminator = RewardRelabeller(cfg.imitation.update_freq, cfg.imitation.balanced, device=dev)  # train.py:72
     elif self.algorithm == 'GMMIL':
       self.discriminator = GMMILDiscriminator(S, A, cfg.imitation, replicas=R, device=dev)
     elif self.algorithm == 'PWIL':
@@ -217,6 +222,8 @@ class Trainer:
         mix_expert_agent_transitions(self.batch, self.expert_batch)  # train.py:183
       if self.algorithm == 'GAIL': self.discriminator.predict_reward_batch(self.batch, write_rewards=True, actor=self.actor)  # train.py:194
       else: self.discriminator.predict_reward_batch(self.batch, self.expert_batch, reward_out=self.batch.rows[..., self.batch.off['rewards']])  # train.py:196
+    if self.algorithm == 'AdRIL':  # train.py:188-189; `step` of the reference = step_f - 1 here (the rollout has already advanced the counter)
+      self.discriminator.resample_and_relabel(self.batch, self.expert_batch, self.step_f, self.memory._num_trajectories, self.expert_memory.num_trajectories, step_offset=-1.0)
     from .training import sac_update
     if cfg.imitation.bc_aux_loss:  # train.py:201
       from .training import behavioural_cloning_update

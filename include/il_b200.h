@@ -81,6 +81,9 @@ const char* il_last_error(void);
 int         il_version(void);
 int         il_set_gemm_mode(il_handle* h, int mode);              /* IL_GEMM_* for the dense hidden layers */
 int64_t     il_launch_count(il_handle* h);                         /* kernels launched by this library so far */
+/* Kernel-selection toggles for A/B measurements and tests (defaults from the IL_* environment variables at il_create):
+ * "tc_fuse_l1" (first MLP layer inside the tcgen05 producers), "gail_tiled", "tc_pairs", "thin_hoist". */
+int         il_set_option(il_handle* h, const char* name, int value);
 int         il_struct_sizes(int32_t* out13);                       /* sizeof il_mlp, il_adam, il_batch, il_replay, il_sac_args, il_gail, il_gail_update_args, il_pwil, il_env, il_bc_args, il_eval_args, il_gailx, il_gailx_update_args */
 int         il_mlp_param_offsets(const int32_t* dims, int n_layers, int64_t* w_off, int64_t* b_off, int64_t* total);
 int         il_row_layout(int S, int A, int32_t* offsets8, int32_t* row_len); /* state, action, reward, next_state, terminal, timeout, weight, step */
@@ -188,6 +191,12 @@ int il_replay_sample_indices(il_handle* h, const il_replay* mem, int R, int n, i
 int il_replay_gather(il_handle* h, const il_replay* mem, int R, const int32_t* idx, const il_batch* out, void* stream);
 /* mix_expert_agent_transitions (models.py:287-290): first B/2 rows <- expert rows (all fields). */
 int il_mix_expert_rows(il_handle* h, const il_batch* batch, const il_batch* expert, int R, void* stream);
+
+/* RewardRelabeller.resample_and_relabel (models.py:297-318): AdRIL (update_freq > 0) / SQIL (update_freq == 0) batch construction and reward
+ * labels. balanced != 0: the batch becomes the expert batch on calls where *sample_expert_flag != 0 and stays the policy batch otherwise; the
+ * flag (device scalar, initially 1) is toggled by the call. Otherwise the first B / 2 rows become expert rows. step = step_f[r] + step_offset. */
+int il_adril_relabel(il_handle* h, const il_batch* batch, const il_batch* expert, int R, int balanced, int update_freq, int32_t* sample_expert_flag,
+                     const float* step_f, float step_offset, const int32_t* num_trajectories, int trajectories_shared, int num_expert_trajectories, void* stream);
 
 /* ---- GAILDiscriminator (models.py:152-180), depth-1 `g` network, optional spectral norm ------------------- */
 typedef struct il_gail {

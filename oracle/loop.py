@@ -43,12 +43,13 @@ class OracleLoop:
     gail = algorithm == 'GAIL'
     self.algorithm, self.B, self.start, self.absorbing, self.mix = algorithm, batch_size, start, absorbing, mix_expert_data
     self.bc_aux_loss = bc_aux_loss  # train.py:201
-    self.discount = (0.97 if gail else 0.99) if discount is None else discount  # GAIL.yaml:5 / train_config.yaml:36
-    self.polyak = (0.99 if gail else 0.995) if polyak is None else polyak  # GAIL.yaml:7 / train_config.yaml:38
+    adril = algorithm == 'AdRIL'
+    self.discount = (0.97 if gail else (0.98 if adril else 0.99)) if discount is None else discount  # GAIL.yaml:5 / AdRIL.yaml:5 / train_config.yaml:36
+    self.polyak = (0.99 if gail else (0.98 if adril else 0.995)) if polyak is None else polyak  # GAIL.yaml:7 / AdRIL.yaml:6 / train_config.yaml:38
     tt = (-0.5 if gail else -1.0) if target_temperature is None else target_temperature  # GAIL.yaml:6 / train_config.yaml:37
     self.im = dict(hidden_size=64, learning_rate=3e-5, weight_decay=10.0, grad_penalty=1.0, spectral_norm=True, entropy_bonus=0.0, loss_function='BCE', reward_function='AIRL',
                    mixup_alpha=1.0, pos_class_prior=0.7, nonnegative_margin=float('inf'), reward_scale=5.0, reward_bandwidth_scale=5.0,
-                   depth=1, activation='relu', reward_shaping=False, subtract_log_policy=False, state_only=False)  # GAIL.yaml:8-27, PWIL.yaml:4-6, train_config.yaml:45
+                   depth=1, activation='relu', reward_shaping=False, subtract_log_policy=False, state_only=False, update_freq=1250, balanced=True)  # GAIL.yaml:8-27, PWIL.yaml:4-6, AdRIL.yaml:9-10, train_config.yaml:45
     self.im.update(imitation or {})
     np.random.seed(seed)
     torch.manual_seed(seed)  # train.py:51-52
@@ -99,6 +100,9 @@ class OracleLoop:
       self.disc = port.GailDiscriminator(g, sn if im['spectral_norm'] else None, self.discount, activation=im['activation'], reward_function=im['reward_function'],
                                          state_only=im['state_only'], subtract_log_policy=im['subtract_log_policy'], h=h, h_sn=h_sn if im['spectral_norm'] else None)
       self.disc_opt = torch.optim.AdamW(self.disc.parameters(), lr=self.im['learning_rate'], weight_decay=self.im['weight_decay'])  # train.py:84
+    elif algorithm == 'AdRIL':
+      assert mix_expert_data == 'mixed_batch'  # train.py:36
+      self.disc = port.RewardRelabeller(self.im['update_freq'], self.im['balanced'])  # train.py:72
     elif algorithm == 'GMMIL':
       self.disc = port.GmmilDiscriminator()
     elif algorithm == 'PWIL':
@@ -163,6 +167,9 @@ class OracleLoop:
             rewards = self.disc.predict_reward(transitions['states'], transitions['actions'], transitions['next_states'], transitions['terminals'], lp)
           else: rewards = self.disc.predict_reward(transitions['states'], transitions['actions'], expert['states'], expert['actions'], transitions['weights'], expert['weights'])
         transitions['rewards'] = rewards.clone()
+      if self.algorithm == 'AdRIL':  # train.py:188-189 (mix_expert_agent_transitions of :183 is skipped for AdRIL)
+        with torch.inference_mode():
+          self.disc.resample_and_relabel(transitions, expert, step, self.memory.num_trajectories, self.expert_memory.num_trajectories)
       if self.bc_aux_loss: port.behavioural_cloning_update(agent.actor, agent.opt_actor, expert)  # train.py:201 (the SAC actor optimiser)
       e1, e2 = self.noise.sac_eps(B, self.A)
       self.last['sac'] = port.sac_update(agent, transitions, e1, e2, self.discount, self.entropy_target, self.polyak)  # train.py:203

@@ -327,6 +327,35 @@ def gail_update(disc: GailDiscriminator, optimiser, policy: Dict[str, Tensor], e
 
 
 # ----------------------------------------------------------------------------------------------------------
+# AdRIL / SQIL reward relabelling (models.py:293-318)
+# ----------------------------------------------------------------------------------------------------------
+class RewardRelabeller:
+  def __init__(self, update_freq: int, balanced: bool):
+    self.update_freq, self.balanced, self.sample_expert = update_freq, balanced, True  # models.py:294-295
+
+  def resample_and_relabel(self, transitions: Dict[str, Tensor], expert_transitions: Dict[str, Tensor], step: int, num_trajectories: int, num_expert_trajectories: int):
+    """models.py:297-318; rewrites `transitions` in place."""
+    batch_size = transitions['rewards'].size(0)
+    if self.balanced:  # :300-308: alternate whole batches of expert / policy data
+      if self.sample_expert:
+        for key in transitions.keys(): transitions[key] = expert_transitions[key]
+        expert_idxs, policy_idxs = range(batch_size), []
+      else:
+        expert_idxs, policy_idxs = [], range(batch_size)
+      self.sample_expert = not self.sample_expert
+    else:  # :309-311
+      mix_expert_agent_transitions(transitions, expert_transitions)
+      expert_idxs, policy_idxs = range(batch_size // 2), range(batch_size // 2, batch_size)
+    if self.update_freq > 0:  # AdRIL, :313-316
+      transitions['rewards'][expert_idxs] = 1 / num_expert_trajectories
+      round_num = math.ceil(step / self.update_freq)
+      transitions['rewards'][policy_idxs] = -1 * (round_num > torch.ceil(transitions['step'][policy_idxs] / self.update_freq)).to(dtype=torch.float32) / max(num_trajectories, 1)
+    else:  # SQIL, :317-318
+      transitions['rewards'][expert_idxs] = 1
+      transitions['rewards'][policy_idxs] = 0
+
+
+# ----------------------------------------------------------------------------------------------------------
 # GMMIL reward (models.py:183-201 with helpers :25-44)
 # ----------------------------------------------------------------------------------------------------------
 def squared_distance_mean(x: Tensor, y: Tensor) -> Tensor:

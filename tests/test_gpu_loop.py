@@ -143,3 +143,17 @@ def test_loop_with_general_discriminator_matches_oracle(extra, imitation):
   assert err.get('q', 0) < 5e-3, err
   assert err.get('reward', 0) < 5e-3, err
   assert err['actor'] < 5e-4, err
+
+
+@pytest.mark.parametrize('extra,imitation', [(('imitation.update_freq=20', ), dict(update_freq=20, balanced=True)),
+                                             (('imitation.update_freq=15', 'imitation.balanced=false'), dict(update_freq=15, balanced=False)),
+                                             (('imitation.update_freq=0', ), dict(update_freq=0, balanced=True))])
+def test_loop_adril_sqil_matches_oracle(extra, imitation):
+  """RewardRelabeller (models.py:293-318) inside the loop — balanced alternation with the flag on the device, AdRIL round
+  arithmetic on the stored `step` column and the per-replica trajectory counters, SQIL labels."""
+  err = _run('AdRIL', 'hopper', steps=70, start=30, B=32, H=64, extra=extra, imitation=imitation)
+  print('AdRIL', imitation, err)
+  assert err['state'] < 2e-3, err
+  assert err.get('q', 0) < 5e-3, err
+  assert err.get('reward', 0) < 1e-6, err
+  assert err['actor'] < 5e-4, err

@@ -85,6 +85,7 @@ def test_config_defaults_and_overrides():
   assert tuned.training.batch_size == 1024 and tuned.imitation.loss_function == 'Mixup'
   with pytest.raises(FileNotFoundError): config.load_config(['algorithm=NOPE'])
   with pytest.raises(NotImplementedError): config.load_config(['algorithm=RED'])
+  assert config.load_config(['algorithm=AdRIL']).imitation.update_freq == 1250
   with pytest.raises(AttributeError): _ = cfg.training.no_such_key
 
 

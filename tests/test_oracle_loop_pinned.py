@@ -46,6 +46,10 @@ CONFIGS = [
    dict(imitation=dict(depth=2, activation='tanh', hidden_size=16, reward_function='GAIL'))),
   ('GAIL', 'hopper', ('imitation.state_only=true', 'imitation.grad_penalty=0', 'imitation.discriminator.activation=sigmoid', 'imitation.discriminator.reward_shaping=true'),
    dict(imitation=dict(state_only=True, grad_penalty=0.0, activation='sigmoid', reward_shaping=True))),
+  # AdRIL (balanced alternation, rounds of 20 steps so several round boundaries fall inside the run), unbalanced AdRIL, SQIL (update_freq 0)
+  ('AdRIL', 'hopper', ('imitation.update_freq=20', ), dict(mix_expert_data='mixed_batch', imitation=dict(update_freq=20, balanced=True))),
+  ('AdRIL', 'walker2d', ('imitation.update_freq=15', 'imitation.balanced=false'), dict(mix_expert_data='mixed_batch', imitation=dict(update_freq=15, balanced=False))),
+  ('AdRIL', 'hopper', ('imitation.update_freq=0', ), dict(mix_expert_data='mixed_batch', imitation=dict(update_freq=0, balanced=True))),
   ('SAC', 'hopper', (), {}),
   ('SAC', 'ant', ('training.weight_decay=0.01', ), dict(weight_decay=0.01)),
   ('GMMIL', 'halfcheetah', (), {}),
