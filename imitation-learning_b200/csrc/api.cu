@@ -6,6 +6,7 @@ thread_local char g_il_error[512] = "";
 int gail_init();
 int gmmil_pwil_init();
 int gemm_init();
+int mlp_init();
 
 extern "C" const char* il_last_error(void) { return g_il_error; }
 extern "C" int il_version(void) { return 100; }
@@ -24,6 +25,7 @@ extern "C" int il_create(int device, il_handle** out) {
   IL_TRY(gmmil_pwil_init());
   IL_TRY(tc_gemm_init());
   IL_TRY(gemm_init());
+  IL_TRY(mlp_init());
   il_handle* h = new il_handle();
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
@@ -32,6 +34,14 @@ extern "C" int il_create(int device, il_handle** out) {
     const char* e = getenv("IL_TC_PAIRS");
     h->tc_pairs = (e && e[0] == '0') ? 0 : 1;
     h->tc_pair_groups = 0;
+    const char* hf = getenv("IL_HEAD_FUSED");
+    h->head_fused = (hf && hf[0] == '0') ? 0 : 1;
+    const char* ds = getenv("IL_DEBUG_SYNC");
+    h->debug_sync = (ds && ds[0] == '1') ? 1 : 0;
+    // AdamW with TMA staging (cp.async.bulk tiles through shared memory): bit-identical to the plain kernel, 7.309 -> 7.285 ms / step in an
+    // A/B inside one gpurun call (profiles/README.md) -> on by default for the large flat buffers
+    const char* at = getenv("IL_ADAM_TMA");
+    h->adam_tma = (at && at[0] == '0') ? 0 : 1;
     const char* gt = getenv("IL_GAIL_TILED");
     h->gail_tiled = (gt && gt[0] == '0') ? 0 : 1;
     // first MLP layer computed inside the producers of the tcgen05 launch: measured 7.64 vs 7.59 ms / step against the separate
@@ -70,6 +80,8 @@ extern "C" int il_set_option(il_handle* h, const char* name, int value) {
   IL_CHECK(h && name, "il_set_option: null argument");
   if (!strcmp(name, "tc_fuse_l1")) h->tc_fuse_l1 = value;
   else if (!strcmp(name, "gail_tiled")) h->gail_tiled = value;
+  else if (!strcmp(name, "adam_tma")) h->adam_tma = value;
+  else if (!strcmp(name, "head_fused")) h->head_fused = value;
   else if (!strcmp(name, "tc_pairs")) { h->tc_pairs = value; h->tc_pair_groups = 0; }
   else if (!strcmp(name, "thin_hoist")) h->thin_hoist = value;
   else IL_FAIL("il_set_option: unknown option '%s'", name);

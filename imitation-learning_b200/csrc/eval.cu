@@ -11,6 +11,11 @@
 #include "env.cuh"
 #include "mlp.cuh"
 
+// Up to 8 episodes per replica the whole actor runs in one weight-streaming kernel; above that (the reference's 30 evaluation episodes,
+// conf/train_config.yaml:23) the per-layer grouped GEMM program is used: the single-kernel path is bound by its shared-memory operand
+// loads (measured 0.93 ms per loop iteration at R = 1024 x 30 episodes; numbers for both in profiles/README.md).
+constexpr int EVAL_SMALL_MAX = 8;
+
 struct EvalCounters {  // device-resident loop state
   int32_t running;      // episodes still running after the current iteration (accumulated by the blocks of the step kernel)
   int32_t ticket;       // blocks that have finished the current iteration
@@ -176,7 +181,7 @@ static int eval_build_impl(il_handle* h, EvalGraph* eg, const il_eval_args* a, f
   int rc = 0;
   {  // evaluation.py:21: greedy action for every episode (frozen ones ignore theirs)
     const MatView X{a->state, (int64_t)E * S, 1, S};
-    if (E <= 32) {
+    if (E <= EVAL_SMALL_MAX) {
       rc = mlp_small_forward(h, &a->actor, R, E, X, action, st, act);
     } else {
       MlpActs acts;
@@ -212,7 +217,7 @@ extern "C" int64_t il_eval_workspace_bytes(const il_eval_args* a) {
   const int act = a->env.act;
   // action [n, act] | finished [n] | counters | (episodes > 32: per-layer activations + head of the general MLP path)
   int64_t b = il_align_up(n * act * 4, 256) + il_align_up(n * 4, 256) + 256;
-  if (a->episodes > 32) b += mlp_acts_bytes(&a->actor, a->R, a->episodes) + il_align_up(n * a->actor.dims[a->actor.n_layers] * 4, 256);
+  if (a->episodes > EVAL_SMALL_MAX) b += mlp_acts_bytes(&a->actor, a->R, a->episodes) + il_align_up(n * a->actor.dims[a->actor.n_layers] * 4, 256);
   return b;
 }
 

@@ -15,6 +15,19 @@
 
 namespace {
 
+// IL_DEBUG_SYNC=1: synchronise after every stage of the program and name the stage that failed (diagnostics only; not capturable)
+#define GX_STAGE(h, st, ...)                                                                          \
+  do {                                                                                                \
+    if ((h)->debug_sync) {                                                                            \
+      cudaError_t _e = cudaStreamSynchronize(st);                                                     \
+      if (_e != cudaSuccess) {                                                                        \
+        char _where[160];                                                                             \
+        snprintf(_where, sizeof(_where), __VA_ARGS__);                                                \
+        IL_FAIL("gailx stage '%s' failed: %s", _where, cudaGetErrorString(_e));                       \
+      }                                                                                               \
+    }                                                                                                 \
+  } while (0)
+
 constexpr int GX_MAX_EVALS = 9;
 
 __device__ __forceinline__ float act_grad2_from_output(float y, int act) {  // second derivative of the activation through its output
@@ -47,28 +60,31 @@ __global__ void __launch_bounds__(256) sn_access_kernel(const SnAccessParams p) 
   __shared__ float red[32];
   extern __shared__ float sm[];  // tvec [max(out, in)]
   const int r = blockIdx.x, tid = threadIdx.x, L = p.net.n_layers;
-  const MlpOffsets o = mlp_offsets(p.net.dims, L);
-  const SnLayout sl = sn_layout(p.net.dims, L);
+  int u_total = 0, v_total = 0;
+  for (int l = 0; l < L; ++l) { u_total += p.net.dims[l + 1]; v_total += p.net.dims[l]; }
   const float* prm = p.net.params + (int64_t)r * p.net.stride;
   float* eff = p.eff.params + (int64_t)r * p.eff.stride;
   float* snap = p.snap + (int64_t)r * p.snap_stride;
+  int off = 0, uo = 0, vo = 0;  // running offsets of layer l: parameters (mlp_offsets rule), u, v
   for (int l = 0; l < L; ++l) {
     const int od = p.net.dims[l + 1], in = p.net.dims[l];
-    const float* W = prm + o.w[l];
+    const int w_off = off, b_off = (off + od * in + 3) / 4 * 4;
+    off = (b_off + od + 3) / 4 * 4;
+    const float* W = prm + w_off;
     float sigma = 1.f;
     if (p.u) {
-      float* u = p.u + (int64_t)r * p.u_stride + sl.uo[l];
-      float* v = p.v + (int64_t)r * p.v_stride + sl.vo[l];
+      float* u = p.u + (int64_t)r * p.u_stride + uo;
+      float* v = p.v + (int64_t)r * p.v_stride + vo;
       __syncthreads();
       if (p.training) {  // u <- normalize(W v), v <- normalize(W^T u)  (eps 1e-12)
-        for (int i = tid; i < od; i += 256) { float s = 0.f; for (int j = 0; j < in; ++j) s = fmaf(W[(int64_t)i * in + j], v[j], s); sm[i] = s; }
+        for (int i = tid; i < od; i += 256) { float s = 0.f; for (int j = 0; j < in; ++j) s = fmaf(W[i * in + j], v[j], s); sm[i] = s; }
         __syncthreads();
         float nn = 0.f;
         for (int i = tid; i < od; i += 256) nn = fmaf(sm[i], sm[i], nn);
         nn = fmaxf(sqrtf(block_sum(nn, red)), 1e-12f);
         for (int i = tid; i < od; i += 256) u[i] = sm[i] / nn;
         __syncthreads();
-        for (int j = tid; j < in; j += 256) { float s = 0.f; for (int i = 0; i < od; ++i) s = fmaf(W[(int64_t)i * in + j], u[i], s); sm[j] = s; }
+        for (int j = tid; j < in; j += 256) { float s = 0.f; for (int i = 0; i < od; ++i) s = fmaf(W[i * in + j], u[i], s); sm[j] = s; }
         __syncthreads();
         nn = 0.f;
         for (int j = tid; j < in; j += 256) nn = fmaf(sm[j], sm[j], nn);
@@ -77,14 +93,15 @@ __global__ void __launch_bounds__(256) sn_access_kernel(const SnAccessParams p) 
         __syncthreads();
       }
       float s = 0.f;  // sigma = u . (W v)
-      for (int i = tid; i < od; i += 256) { float t = 0.f; for (int j = 0; j < in; ++j) t = fmaf(W[(int64_t)i * in + j], v[j], t); s = fmaf(u[i], t, s); }
+      for (int i = tid; i < od; i += 256) { float t = 0.f; for (int j = 0; j < in; ++j) t = fmaf(W[i * in + j], v[j], t); s = fmaf(u[i], t, s); }
       sigma = block_sum(s, red);
-      for (int i = tid; i < od; i += 256) snap[sl.uo[l] + i] = u[i];
-      for (int j = tid; j < in; j += 256) snap[sl.u_total + sl.vo[l] + j] = v[j];
+      for (int i = tid; i < od; i += 256) snap[uo + i] = u[i];
+      for (int j = tid; j < in; j += 256) snap[u_total + vo + j] = v[j];
     }
-    if (tid == 0) snap[sl.u_total + sl.v_total + l] = sigma;
-    for (int i = tid; i < od * in; i += 256) eff[o.w[l] + i] = W[i] / sigma;
-    for (int i = tid; i < od; i += 256) eff[o.b[l] + i] = prm[o.b[l] + i];
+    if (tid == 0) snap[u_total + v_total + l] = sigma;
+    for (int i = tid; i < od * in; i += 256) eff[w_off + i] = W[i] / sigma;
+    for (int i = tid; i < od; i += 256) eff[b_off + i] = prm[b_off + i];
+    uo += od; vo += in;
   }
 }
 
@@ -100,23 +117,27 @@ struct SnProjectParams {
 __global__ void __launch_bounds__(256) sn_project_kernel(const SnProjectParams p) {
   __shared__ float red[32];
   const int r = blockIdx.x, tid = threadIdx.x, L = p.eff.n_layers;
-  const MlpOffsets o = mlp_offsets(p.eff.dims, L);
-  const SnLayout sl = sn_layout(p.eff.dims, L);
+  int u_total = 0, v_total = 0;
+  for (int l = 0; l < L; ++l) { u_total += p.eff.dims[l + 1]; v_total += p.eff.dims[l]; }
   const float* eff = p.eff.params + (int64_t)r * p.eff.stride;
   const float* G = p.g_eff + (int64_t)r * p.eff.stride;
   const float* snap = p.snap + (int64_t)r * p.snap_stride;
   float* out = p.g_out + (int64_t)r * p.out_stride;
+  int off = 0, uo = 0, vo = 0;
   for (int l = 0; l < L; ++l) {
     const int od = p.eff.dims[l + 1], in = p.eff.dims[l];
+    const int w_off = off, b_off = (off + od * in + 3) / 4 * 4;
+    off = (b_off + od + 3) / 4 * 4;
     if (p.has_sn) {
       float s = 0.f;
-      for (int i = tid; i < od * in; i += 256) s = fmaf(G[o.w[l] + i], eff[o.w[l] + i], s);
-      const float inner = block_sum(s, red), sigma = snap[sl.u_total + sl.v_total + l];
-      for (int i = tid; i < od * in; i += 256) out[o.w[l] + i] += (G[o.w[l] + i] - inner * snap[sl.uo[l] + i / in] * snap[sl.u_total + sl.vo[l] + i % in]) / sigma;
+      for (int i = tid; i < od * in; i += 256) s = fmaf(G[w_off + i], eff[w_off + i], s);
+      const float inner = block_sum(s, red), sigma = snap[u_total + v_total + l];
+      for (int i = tid; i < od * in; i += 256) out[w_off + i] += (G[w_off + i] - inner * snap[uo + i / in] * snap[u_total + vo + i % in]) / sigma;
     } else {
-      for (int i = tid; i < od * in; i += 256) out[o.w[l] + i] += G[o.w[l] + i];
+      for (int i = tid; i < od * in; i += 256) out[w_off + i] += G[w_off + i];
     }
-    for (int i = tid; i < od; i += 256) out[o.b[l] + i] += G[o.b[l] + i];
+    for (int i = tid; i < od; i += 256) out[b_off + i] += G[b_off + i];
+    uo += od; vo += in;
   }
 }
 
@@ -359,6 +380,8 @@ int eval_access(il_handle* h, NetEval& e, int R, int training, cudaStream_t st) 
 }
 int eval_forward(il_handle* h, NetEval& e, int R, int B, cudaStream_t st) { return mlp_forward(h, &e.eff, R, B, e.X, e.acts, e.out, (int64_t)B, 1, st); }
 int eval_project(il_handle* h, NetEval& e, int R, int64_t out_stride, cudaStream_t st) {
+  IL_CHECK(e.eff.params && e.g_eff && e.snap && e.g_out, "gailx: internal: projecting an evaluation without gradient storage (eff=%p g_eff=%p snap=%p out=%p)", (void*)e.eff.params,
+           (void*)e.g_eff, (void*)e.snap, (void*)e.g_out);
   SnProjectParams p;
   p.eff = e.eff; p.g_eff = e.g_eff; p.snap = e.snap; p.snap_stride = e.snap_stride; p.has_sn = e.u != nullptr; p.g_out = e.g_out; p.out_stride = out_stride;
   IL_LAUNCH(h, sn_project_kernel, R, 256, 0, st, p);
@@ -581,8 +604,10 @@ extern "C" int il_gailx_update(il_handle* h, const il_gailx_update_args* a, void
       e.X = MatView{pass_rows[k] + col0, pass_rs[k], 1, row};
       e.g_out = L.g_flat + (j == 0 ? 0 : h_off);
       IL_TRY(eval_access(h, e, R, a->training, st));
+      GX_STAGE(h, st, "access pass %d net %d", k, j);
       if (is_gp && j == 1) continue;  // h(s') of the GP pass: the access (power iteration) happens, its value and gradient are never used
       IL_TRY(eval_forward(h, e, R, B, st));
+      GX_STAGE(h, st, "forward pass %d net %d", k, j);
     }
   }
   // ---- loss, d loss / d outputs -------------------------------------------------------------------------------------------------
@@ -600,12 +625,15 @@ extern "C" int il_gailx_update(il_handle* h, const il_gailx_update_args* a, void
     v.kind = mixup ? 2 : k;
   }
   IL_LAUNCH(h, gailx_loss_kernel, R, 256, 0, st, lp);
+  GX_STAGE(h, st, "loss");
   // ---- backward of the loss passes, projected through each access ----------------------------------------------------------------
   for (int k = 0; k < n_loss_pass; ++k)
     for (int j = 0; j < per_pass; ++j) {
       NetEval& e = L.ev[k * per_pass + j];
       IL_TRY(mlp_backward(h, &e.eff, R, B, e.X, e.acts, MatView{e.dout, (int64_t)B, 1, 1}, e.g_eff, e.eff.stride, nullptr, 0, 0, 0, 0, L.tmpA, L.tmpB, st));
+      GX_STAGE(h, st, "backward pass %d net %d", k, j);
       IL_TRY(eval_project(h, e, R, pstride, st));
+      GX_STAGE(h, st, "project pass %d net %d (eff %p g_eff %p out %p ws %p + %lld)", k, j, (void*)e.eff.params, (void*)e.g_eff, (void*)e.g_out, a->workspace, (long long)a->workspace_bytes);
     }
   // ---- gradient penalty ------------------------------------------------------------------------------------------------------------
   if (gp) {
@@ -618,12 +646,17 @@ extern "C" int il_gailx_update(il_handle* h, const il_gailx_update_args* a, void
     IL_TRY(gp_input_gradient(h, e[0], one, L.gb, L.gin, ld, 0, R, B, st));
     if (shaping) IL_TRY(gp_input_gradient(h, e[2], kh, L.gb, L.gin, ld, 1, R, B, st));
     IL_LAUNCH(h, gp_penalty_kernel, R, 256, 0, st, L.gin, ld, ld, pass_rows[n_loss_pass], pass_rs[n_loss_pass], row, RL.weight, a->grad_penalty, a->out_losses, B);
+    GX_STAGE(h, st, "gp input gradients + penalty");
     if (shaping) {
       IL_TRY(gp_double_backward(h, e[2], kh, L.gb, L.gin, ld, R, B, st));
+      GX_STAGE(h, st, "gp double backward h");
       IL_TRY(eval_project(h, e[2], R, pstride, st));
+      GX_STAGE(h, st, "gp project h");
     }
     IL_TRY(gp_double_backward(h, e[0], one, L.gb, L.gin, ld, R, B, st));
+    GX_STAGE(h, st, "gp double backward g");
     IL_TRY(eval_project(h, e[0], R, pstride, st));
+    GX_STAGE(h, st, "gp project g");
   }
   // ---- AdamW over the flat parameter buffer (train.py:84) ------------------------------------------------------------------------
   return launch_adam(h, d.g.params, L.g_flat, &a->opt, a->params_floats, st);

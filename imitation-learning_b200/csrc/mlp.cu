@@ -3,6 +3,17 @@
 
 #include <math.h>
 
+constexpr int HB_MAXN = 8;
+struct HeadBwdArgs {
+  const float* dout; int64_t dout_gs; int dout_gdiv, ld_dout;   // [n, Nh]
+  const float* w; int64_t w_gs;                                 // W_L [Nh, H] row-major
+  const float* y; int64_t y_gs;                                 // Y [n, H]
+  float* dz; int64_t dz_gs;                                     // out [n, H]
+  float* dw; float* db; float* db_prev; int64_t g_gs;           // gradient slices (group stride g_gs): dW_L [Nh, H], db_L [Nh], db_{L-1} [H]
+  int n, H, Nh;
+};
+int launch_head_backward(il_handle* h, const HeadBwdArgs& a, int G, cudaStream_t stream);
+
 int mlp_validate(const il_mlp* m, const char* what) {
   IL_CHECK(m != nullptr && m->params != nullptr, "%s: null mlp", what);
   IL_CHECK(m->n_layers >= 1 && m->n_layers <= IL_MAX_LAYERS, "%s: n_layers %d out of range", what, m->n_layers);
@@ -80,20 +91,42 @@ int mlp_forward(il_handle* h, const il_mlp* m, int G, int n, MatView X, const Ml
   return 0;
 }
 
+static bool head_backward_eligible(const il_mlp* m, int n, int64_t grad_stride) {
+  const int L = m->n_layers, H = m->dims[L - 1], Nh = m->dims[L];
+  return m->activation == IL_ACT_RELU && Nh <= HB_MAXN && H % 4 == 0 && n <= 1024 && grad_stride % 4 == 0 && m->stride % 4 == 0;
+}
+
 int mlp_backward(il_handle* h, const il_mlp* m, int G, int n, MatView X, const MlpActs& acts, MatView dOut, float* grads, int64_t grad_stride,
                  float* dX, int64_t dx_gs, int ld_dx, int dx_col0, int dx_cols, float* tmpA, float* tmpB, cudaStream_t stream) {
   const MlpOffsets o = mlp_offsets(m->dims, m->n_layers);
   const int L = m->n_layers;
   MatView dZ = dOut;  // gradient w.r.t. the pre-activation output of layer l
   float* next_tmp = tmpA;
+  bool bias_done = false;  // db of the current layer already produced by the fused head kernel
   for (int l = L - 1; l >= 0; --l) {
     MatView Xin = l == 0 ? X : MatView{acts.hid[l - 1], (int64_t)n * m->dims[l], 1, m->dims[l]};
+    if (l == L - 1 && l > 0 && grads && h->head_fused && head_backward_eligible(m, n, grad_stride)) {
+      // head: dZ_{L-2}, dW_L, db_L and db_{L-1} in one pass over the last hidden activation
+      HeadBwdArgs a{};
+      a.dout = dZ.ptr; a.dout_gs = dZ.gs; a.dout_gdiv = dZ.gdiv; a.ld_dout = dZ.ld;
+      a.w = m->params + o.w[l]; a.w_gs = m->stride;
+      a.y = acts.hid[l - 1]; a.y_gs = (int64_t)n * m->dims[l];
+      a.dz = next_tmp; a.dz_gs = (int64_t)n * m->dims[l];
+      a.dw = grads + o.w[l]; a.db = grads + o.b[l]; a.db_prev = grads + o.b[l - 1]; a.g_gs = grad_stride;
+      a.n = n; a.H = m->dims[l]; a.Nh = m->dims[l + 1];
+      IL_TRY(launch_head_backward(h, a, G, stream));
+      dZ = MatView{next_tmp, (int64_t)n * m->dims[l], 1, m->dims[l]};
+      next_tmp = next_tmp == tmpA ? tmpB : tmpA;
+      bias_done = true;
+      continue;
+    }
     if (grads) {  // dW_l[o, i] = sum_b dZ[b, o] * Xin[b, i];  db_l[o] = sum_b dZ[b, o]
       GemmArgs a{};
       a.A = dZ.ptr; a.a_gs = dZ.gs; a.a_gdiv = dZ.gdiv; a.lda = dZ.ld; a.a_kmajor = 0;
       a.B = Xin.ptr; a.b_gs = Xin.gs; a.b_gdiv = Xin.gdiv; a.ldb = Xin.ld; a.b_kmajor = 0;
       a.C = grads + o.w[l]; a.c_gs = grad_stride; a.ldc = m->dims[l]; a.act = -1;
-      a.colsum = grads + o.b[l]; a.colsum_gs = grad_stride;
+      if (!bias_done) { a.colsum = grads + o.b[l]; a.colsum_gs = grad_stride; }
+      bias_done = false;
       a.M = m->dims[l + 1]; a.N = m->dims[l]; a.K = n; a.G = G;
       IL_TRY(launch_gemm(h, a, stream));
     }
@@ -295,6 +328,184 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// Same update with TMA staging: persistent CTAs stream 8 KB tiles of every operand into shared memory with 1-D bulk copies
+// (cp.async.bulk ... mbarrier::complete_tx, issued by one thread), update in place, and write the results back with bulk stores —
+// the LSU only sees shared-memory traffic, global traffic is 128-byte-line bulk transfers on the copy engine path. Double buffered.
+constexpr int ADAM_TILE = 2048;                 // floats per operand per stage
+constexpr int ADAM_STREAMS = 5;                 // p, g, m, v, target
+constexpr int ADAM_TMA_SMEM = 2 * ADAM_STREAMS * ADAM_TILE * 4 + 64;
+__global__ void __launch_bounds__(256) adam_tma_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, const int64_t* __restrict__ step,
+                                                       double lr, double beta1_d, double beta2_d, double eps_d, double wd, int64_t n, float* __restrict__ target, float tau, float one_minus_tau) {
+  extern __shared__ __align__(128) uint8_t adam_smem[];
+  float* buf = reinterpret_cast<float*>(adam_smem);                                  // [stage][stream][ADAM_TILE]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(adam_smem + 2 * ADAM_STREAMS * ADAM_TILE * 4);
+  __shared__ float s_step_size, s_bc2_sqrt;
+  const int tid = threadIdx.x;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars), smem0 = (uint32_t)__cvta_generic_to_shared(buf);
+  if (tid == 0) {
+    const double t = (double)*step;
+    s_step_size = (float)(lr / (1.0 - pow(beta1_d, t)));
+    s_bc2_sqrt = (float)sqrt(1.0 - pow(beta2_d, t));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const float decay = (float)(1.0 - lr * wd), w1 = (float)(1.0 - beta1_d), w2 = (float)(1.0 - beta2_d), beta2 = (float)beta2_d, eps = (float)eps_d;
+  const bool has_wd = wd != 0.0;
+  auto upd = [&](float& pi, float& mi, float& vi, float gi) {
+    if (has_wd) pi = __fmul_rn(pi, decay);
+    mi = __fadd_rn(mi, __fmul_rn(w1, __fsub_rn(gi, mi)));
+    vi = __fadd_rn(__fmul_rn(vi, beta2), __fmul_rn(__fmul_rn(w2, gi), gi));
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);
+    pi = __fadd_rn(pi, __fmul_rn(-step_size, __fdiv_rn(mi, denom)));
+  };
+  const int64_t n_tiles = (n + ADAM_TILE - 1) / ADAM_TILE;
+  const int n_streams = target ? 5 : 4;
+  auto tile_floats = [&](int64_t tile) { const int64_t left = n - tile * ADAM_TILE; return (int)(left < ADAM_TILE ? left : ADAM_TILE); };
+  auto issue_loads = [&](int64_t tile, int stage) {  // thread 0 only
+    const uint32_t bytes = (uint32_t)tile_floats(tile) * 4u, bar = bar0 + 8u * stage;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * (uint32_t)n_streams) : "memory");
+    const float* src[5] = {p, g, m, v, target};
+    for (int q = 0; q < n_streams; ++q)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem0 + (uint32_t)((stage * ADAM_STREAMS + q) * ADAM_TILE * 4)),
+                   "l"(src[q] + tile * ADAM_TILE), "r"(bytes), "r"(bar) : "memory");
+  };
+  int64_t tile = blockIdx.x;
+  if (tid == 0 && tile < n_tiles) issue_loads(tile, 0);
+  for (int k = 0; tile < n_tiles; ++k, tile += gridDim.x) {
+    const int stage = k & 1;
+    if (tid == 0 && tile + gridDim.x < n_tiles) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stores that last read the other stage have left shared memory
+      issue_loads(tile + gridDim.x, stage ^ 1);
+    }
+    {  // wait for this stage's bytes
+      const uint32_t bar = bar0 + 8u * stage, parity = (uint32_t)((k >> 1) & 1);
+      asm volatile(
+          "{\n\t.reg .pred q;\n\t"
+          "ADAM_WAIT:\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n\t"
+          "@q bra ADAM_DONE;\n\t"
+          "bra ADAM_WAIT;\n\t"
+          "ADAM_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+    }
+    const int nf4 = tile_floats(tile) >> 2;
+    float4* sp = reinterpret_cast<float4*>(buf + (stage * ADAM_STREAMS + 0) * ADAM_TILE);
+    const float4* sg = reinterpret_cast<const float4*>(buf + (stage * ADAM_STREAMS + 1) * ADAM_TILE);
+    float4* smm = reinterpret_cast<float4*>(buf + (stage * ADAM_STREAMS + 2) * ADAM_TILE);
+    float4* sv = reinterpret_cast<float4*>(buf + (stage * ADAM_STREAMS + 3) * ADAM_TILE);
+    float4* stg = reinterpret_cast<float4*>(buf + (stage * ADAM_STREAMS + 4) * ADAM_TILE);
+    for (int i = tid; i < nf4; i += 256) {
+      float4 pv = sp[i], mv = smm[i], vv = sv[i];
+      const float4 gv = sg[i];
+      upd(pv.x, mv.x, vv.x, gv.x); upd(pv.y, mv.y, vv.y, gv.y); upd(pv.z, mv.z, vv.z, gv.z); upd(pv.w, mv.w, vv.w, gv.w);
+      sp[i] = pv; smm[i] = mv; sv[i] = vv;
+      if (target) {  // fused update_target_network (models.py:81)
+        float4 tv = stg[i];
+        tv.x = __fadd_rn(__fmul_rn(tv.x, tau), __fmul_rn(one_minus_tau, pv.x)); tv.y = __fadd_rn(__fmul_rn(tv.y, tau), __fmul_rn(one_minus_tau, pv.y));
+        tv.z = __fadd_rn(__fmul_rn(tv.z, tau), __fmul_rn(one_minus_tau, pv.z)); tv.w = __fadd_rn(__fmul_rn(tv.w, tau), __fmul_rn(one_minus_tau, pv.w));
+        stg[i] = tv;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk-copy engine
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)tile_floats(tile) * 4u;
+      float* dst[5] = {p, nullptr, m, v, target};
+      for (int q = 0; q < n_streams; ++q) {
+        if (!dst[q]) continue;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst[q] + tile * ADAM_TILE), "r"(smem0 + (uint32_t)((stage * ADAM_STREAMS + q) * ADAM_TILE * 4)), "r"(bytes)
+                     : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before the CTA (and its shared memory) goes away
+}
+
+
+// ---- fused backward of the linear head + last hidden activation (one pass over the hidden output) -----------------------------------
+// For the last layer out = Y W_L^T + b_L (N_h <= 8 units) with Y = relu(Z) [n, H]:
+//   dZ[b, o]   = (sum_j dOut[b, j] W_L[j, o]) * 1[Y[b, o] > 0]        (was: K-thin GEMM with mask epilogue, reads Y, writes dZ)
+//   dW_L[j, o] = sum_b dOut[b, j] Y[b, o],  db_L[j] = sum_b dOut[b, j]  (was: streaming TN kernel, reads Y again)
+//   db_{L-1}[o] = sum_b dZ[b, o]                                        (was: column-sum kernel, reads dZ again)
+// One CTA per (net, 256 hidden columns) streams Y once and writes dZ once; thread = 4 columns x every 4th row, W_L columns in registers,
+// cross-row-group reduction through shared memory in a fixed order (deterministic).
+__global__ void __launch_bounds__(256, 2) head_backward_kernel(const HeadBwdArgs p) {
+  extern __shared__ __align__(16) float hb_sm[];   // dOut [n][HB_MAXN] (zero padded), then the reduction scratch [4][HB_MAXN * 4 + 4][64]
+  const int g = blockIdx.y, n0 = blockIdx.x * 256, tid = threadIdx.x, tc = tid & 63, tr = tid >> 6, col = n0 + tc * 4;
+  float* dos = hb_sm;
+  float* red = hb_sm + p.n * HB_MAXN;
+  const float* dout = p.dout + (int64_t)(g / p.dout_gdiv) * p.dout_gs;
+  for (int i = tid; i < p.n * HB_MAXN; i += 256) {
+    const int b = i / HB_MAXN, j = i % HB_MAXN;
+    dos[i] = j < p.Nh ? __ldg(dout + (int64_t)b * p.ld_dout + j) : 0.f;
+  }
+  const bool active = col < p.H;
+  float4 w[HB_MAXN];
+#pragma unroll
+  for (int j = 0; j < HB_MAXN; ++j) w[j] = (active && j < p.Nh) ? __ldg(reinterpret_cast<const float4*>(p.w + (int64_t)g * p.w_gs + (int64_t)j * p.H + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  float4 dw[HB_MAXN], cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < HB_MAXN; ++j) dw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+    const float* Y = p.y + (int64_t)g * p.y_gs + col;
+    float* DZ = p.dz + (int64_t)g * p.dz_gs + col;
+    for (int b0 = tr; b0 < p.n; b0 += 16) {  // 4 rows (b0, b0 + 4, b0 + 8, b0 + 12) in flight
+      float4 yv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int b = b0 + 4 * u;
+        yv[u] = b < p.n ? __ldg(reinterpret_cast<const float4*>(Y + (int64_t)b * p.H)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int b = b0 + 4 * u;
+        if (b >= p.n) continue;
+        const float4 d0 = *reinterpret_cast<const float4*>(dos + b * HB_MAXN), d1 = *reinterpret_cast<const float4*>(dos + b * HB_MAXN + 4);
+        const float dj[HB_MAXN] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < HB_MAXN; ++j) {
+          z.x = fmaf(dj[j], w[j].x, z.x); z.y = fmaf(dj[j], w[j].y, z.y); z.z = fmaf(dj[j], w[j].z, z.z); z.w = fmaf(dj[j], w[j].w, z.w);
+          dw[j].x = fmaf(dj[j], yv[u].x, dw[j].x); dw[j].y = fmaf(dj[j], yv[u].y, dw[j].y); dw[j].z = fmaf(dj[j], yv[u].z, dw[j].z); dw[j].w = fmaf(dj[j], yv[u].w, dw[j].w);
+        }
+        z.x = yv[u].x > 0.f ? z.x : 0.f; z.y = yv[u].y > 0.f ? z.y : 0.f; z.z = yv[u].z > 0.f ? z.z : 0.f; z.w = yv[u].w > 0.f ? z.w : 0.f;
+        cs.x += z.x; cs.y += z.y; cs.z += z.z; cs.w += z.w;
+        *reinterpret_cast<float4*>(DZ + (int64_t)b * p.H) = z;
+      }
+    }
+  }
+  // reduce the 4 row groups: red[tr][slot][tc] (slot = j for dW_L rows, HB_MAXN for the column sum), float4 per entry
+  float4* r4 = reinterpret_cast<float4*>(red);
+#pragma unroll
+  for (int j = 0; j < HB_MAXN; ++j) r4[(tr * (HB_MAXN + 1) + j) * 64 + tc] = dw[j];
+  r4[(tr * (HB_MAXN + 1) + HB_MAXN) * 64 + tc] = cs;
+  __syncthreads();
+  if (tr == 0 && active) {
+#pragma unroll
+    for (int j = 0; j <= HB_MAXN; ++j) {
+      if (j < p.Nh || j == HB_MAXN) {
+        float4 a = r4[(0 * (HB_MAXN + 1) + j) * 64 + tc];
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+          const float4 t = r4[(q * (HB_MAXN + 1) + j) * 64 + tc];
+          a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
+        float* dst = j == HB_MAXN ? p.db_prev + (int64_t)g * p.g_gs + col : p.dw + (int64_t)g * p.g_gs + (int64_t)j * p.H + col;
+        *reinterpret_cast<float4*>(dst) = a;
+      }
+    }
+  }
+  if (blockIdx.x == 0 && tid < p.Nh) {  // db_L[j] = sum_b dOut[b, j]
+    float sacc = 0.f;
+    for (int b = 0; b < p.n; ++b) sacc += dos[b * HB_MAXN + tid];
+    p.db[(int64_t)g * p.g_gs + tid] = sacc;
+  }
+}
+
 __global__ void tick_kernel(int64_t* s0, int64_t* s1, int64_t* s2) {
   if (s0) *s0 += 1;
   if (s1) *s1 += 1;
@@ -345,8 +556,25 @@ int launch_adam(il_handle* h, float* params, const float* grads, const il_adam* 
   IL_CHECK(opt->m && opt->v && opt->step, "adam: null state");
   IL_CHECK(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(opt->m) | reinterpret_cast<uintptr_t>(opt->v) |
              reinterpret_cast<uintptr_t>(polyak_target)) & 15) == 0, "adam: buffers must be 16-byte aligned");
+  if (h->adam_tma && n % 4 == 0 && n >= (int64_t)ADAM_TILE * h->sm_count * 2) {  // large flat buffers: TMA-staged streaming variant
+    IL_LAUNCH(h, adam_tma_kernel, h->sm_count * 2, 256, ADAM_TMA_SMEM, stream, params, grads, opt->m, opt->v, opt->step, opt->lr, opt->beta1, opt->beta2, opt->eps, opt->weight_decay, n,
+              polyak_target, polyak_factor, (float)(1.0 - (double)polyak_factor));
+    return 0;
+  }
   IL_LAUNCH(h, adam_kernel, ew_blocks(n / 4 + 1, 256, h->sm_count), 256, 0, stream, params, grads, opt->m, opt->v, opt->step, opt->lr, opt->beta1, opt->beta2, opt->eps,
             opt->weight_decay, n, polyak_target, polyak_factor, (float)(1.0 - (double)polyak_factor));
+  return 0;
+}
+
+int launch_head_backward(il_handle* h, const HeadBwdArgs& a, int G, cudaStream_t stream) {
+  const size_t smem = ((size_t)a.n * HB_MAXN + 4 * (HB_MAXN + 1) * 64 * 4) * sizeof(float);
+  IL_LAUNCH(h, head_backward_kernel, dim3((a.H + 255) / 256, G), 256, smem, stream, a);
+  return 0;
+}
+
+int mlp_init() {
+  IL_CUDA(cudaFuncSetAttribute(adam_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ADAM_TMA_SMEM));
+  IL_CUDA(cudaFuncSetAttribute(head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1024 * HB_MAXN + 4 * (HB_MAXN + 1) * 64 * 4) * 4));
   return 0;
 }
 
