@@ -34,6 +34,10 @@ extern "C" int il_create(int device, il_handle** out) {
     const char* e = getenv("IL_TC_PAIRS");
     h->tc_pairs = (e && e[0] == '0') ? 0 : 1;
     h->tc_pair_groups = 0;
+    const char* wt = getenv("IL_WIDE_TN");
+    h->wide_tn = (wt && wt[0] == '0') ? 0 : 1;
+    const char* ff = getenv("IL_FIRST_LAYER_FAST");
+    h->first_layer_fast = (ff && ff[0] == '0') ? 0 : 1;
     const char* hf = getenv("IL_HEAD_FUSED");
     h->head_fused = (hf && hf[0] == '0') ? 0 : 1;
     const char* ds = getenv("IL_DEBUG_SYNC");
@@ -82,6 +86,8 @@ extern "C" int il_set_option(il_handle* h, const char* name, int value) {
   else if (!strcmp(name, "gail_tiled")) h->gail_tiled = value;
   else if (!strcmp(name, "adam_tma")) h->adam_tma = value;
   else if (!strcmp(name, "head_fused")) h->head_fused = value;
+  else if (!strcmp(name, "first_layer_fast")) h->first_layer_fast = value;
+  else if (!strcmp(name, "wide_tn")) h->wide_tn = value;
   else if (!strcmp(name, "tc_pairs")) { h->tc_pairs = value; h->tc_pair_groups = 0; }
   else if (!strcmp(name, "thin_hoist")) h->thin_hoist = value;
   else IL_FAIL("il_set_option: unknown option '%s'", name);

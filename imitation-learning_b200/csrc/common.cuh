@@ -21,6 +21,8 @@ struct il_handle {
   int tc_pair_groups;                   // co-resident 2-CTA clusters of the tcgen05 pair kernel (0 = not queried yet)
   int thin_hoist;                       // K-thin kernel: hoisted mask loads for the masked (dX) variant (IL_THIN_HOIST=0/1)
   int tc_pairs;                         // tcgen05 engine: use CTA pairs (cta_group::2) when rows are a multiple of 256 (IL_TC_PAIRS=0 disables)
+  int wide_tn;                          // first-layer weight gradient: 128-bit row-group kernel (IL_WIDE_TN=0 keeps the column-streaming kernel)
+  int first_layer_fast;                 // first MLP layer: specialised FFMA2 kernel for K <= 16 (IL_FIRST_LAYER_FAST=0 keeps the generic K-thin kernel)
   int head_fused;                       // MLP backward: fused head kernel (dZ, dW_L, db_L, db_{L-1} in one pass; IL_HEAD_FUSED=0 disables)
   int debug_sync;                       // IL_DEBUG_SYNC=1: multi-kernel programs synchronise after every stage and name the one that failed
   int adam_tma;                         // AdamW: TMA-staged (cp.async.bulk) streaming kernel for large flat buffers (IL_ADAM_TMA=1 enables)

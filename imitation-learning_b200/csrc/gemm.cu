@@ -333,6 +333,92 @@ __global__ void __launch_bounds__(256, HOIST_MASK ? 2 : 3) gemm_thin_k_kernel(co
   }
 }
 
+
+// First MLP layer, specialised: C = relu(A W^T + b) with K <= 16 input columns (state or state + action), N a multiple of 256, M a multiple
+// of 32. The generic K-thin kernel above is instruction-issue bound on this shape (ncu: 154 M warp instructions for 67 M FMAs); here the
+// contraction runs on packed FFMA2 over k-pairs ({a_k, a_k+1} x {w_k, w_k+1} accumulate the even / odd partial sums, added at the end), the
+// activation is compile-time and there are no bounds checks in the inner loops: ~3x fewer issued instructions, so the kernel is bound by
+// its 128-bit output stores instead.
+constexpr int FL_K = 16, FL_ROWS = 32, FL_ITERS = 4, FL_COLS = 256;
+__device__ __forceinline__ unsigned long long fl_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__global__ void __launch_bounds__(256, 2) first_layer_relu_kernel(const GemmArgs p) {
+  __shared__ __align__(16) float Ws[(FL_K / 2) * FL_COLS * 2];  // [k pair][n][2]
+  __shared__ __align__(16) float As[FL_ROWS][FL_K];
+  const int tid = threadIdx.x, g = blockIdx.z, n0 = blockIdx.x * FL_COLS, K = p.K;
+  const float* __restrict__ A = p.A + (int64_t)(g / p.a_gdiv) * p.a_gs;
+  const float* __restrict__ W = p.B + (int64_t)(g / p.b_gdiv) * p.b_gs;
+  for (int idx = tid; idx < FL_K * FL_COLS; idx += 256) {
+    const int k = idx / FL_COLS, n = idx % FL_COLS;
+    Ws[(k >> 1) * (FL_COLS * 2) + n * 2 + (k & 1)] = k < K ? __ldg(W + (int64_t)(n0 + n) * p.ldb + k) : 0.f;
+  }
+  const int n = (tid & 63) * 4, tr = tid >> 6;
+  float* __restrict__ C = p.C + (int64_t)g * p.c_gs + n0 + n;
+  const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + (int64_t)g * p.bias_gs + n0 + n));
+  float a_next[2];
+  auto fetch_a = [&](int m0) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int idx = tid + q * 256, r = idx / FL_K, k = idx % FL_K;
+      a_next[q] = k < K ? __ldg(A + (int64_t)(m0 + r) * p.lda + k) : 0.f;
+    }
+  };
+  const int mbase = blockIdx.y * FL_ITERS * FL_ROWS;
+  fetch_a(mbase);
+  for (int it = 0; it < FL_ITERS; ++it) {
+    const int m0 = mbase + it * FL_ROWS;
+    if (m0 >= p.M) break;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 2; ++q) { const int idx = tid + q * 256; As[idx / FL_K][idx % FL_K] = a_next[q]; }
+    __syncthreads();
+    if (it + 1 < FL_ITERS && m0 + FL_ROWS < p.M) fetch_a(m0 + FL_ROWS);
+    unsigned long long acc[8][4];  // {even-k partial, odd-k partial} per (row, column)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0ull;
+#pragma unroll
+    for (int kq = 0; kq < FL_K / 4; ++kq) {  // 4 k's = 2 pairs per step
+      unsigned long long w[2][4];
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const ulonglong2 lo = *reinterpret_cast<const ulonglong2*>(&Ws[(kq * 2 + h2) * (FL_COLS * 2) + n * 2]);
+        const ulonglong2 hi = *reinterpret_cast<const ulonglong2*>(&Ws[(kq * 2 + h2) * (FL_COLS * 2) + n * 2 + 4]);
+        w[h2][0] = lo.x; w[h2][1] = lo.y; w[h2][2] = hi.x; w[h2][3] = hi.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&As[tr + 4 * i][kq * 4]);  // {a_k, a_k+1}, {a_k+2, a_k+3}: warp-uniform address
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          acc[i][c] = fl_fma2(a.x, w[0][c], acc[i][c]);
+          acc[i][c] = fl_fma2(a.y, w[1][c], acc[i][c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float e, o;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(e), "=f"(o) : "l"(acc[i][c]));
+        v[c] = e + o;
+      }
+      const float4 out = make_float4(fmaxf(v[0] + bv.x, 0.f), fmaxf(v[1] + bv.y, 0.f), fmaxf(v[2] + bv.z, 0.f), fmaxf(v[3] + bv.w, 0.f));
+      *reinterpret_cast<float4*>(C + (int64_t)(m0 + tr + 4 * i) * p.ldc) = out;
+    }
+  }
+}
+
+bool first_layer_eligible(const GemmArgs& a) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  return a.a_kmajor && a.b_kmajor && a.K <= FL_K && a.N % FL_COLS == 0 && a.M % FL_ROWS == 0 && a.act == IL_ACT_RELU && a.bias && !a.mask && !a.colsum && !a.accumulate &&
+         al16(a.C) && a.ldc % 4 == 0 && a.c_gs % 4 == 0 && al16(a.bias) && a.bias_gs % 4 == 0;
+}
+
 bool thin_k_eligible(const GemmArgs& a) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (a.K > TK_MAXK || !a.a_kmajor || a.N < 64 || a.N % 4 || a.colsum || a.accumulate) return false;
@@ -422,6 +508,144 @@ __global__ void __launch_bounds__(256) gemm_stream_tn_kernel(const GemmArgs p) {
   }
 }
 
+
+// First-layer weight gradient, specialised: C[m][j] = sum_k A[k][m] * B[k][j] (+ colsum[m] = sum_k A[k][m]) with A = dZ [K = batch rows, M = hidden
+// columns] wide and B = X [K, N <= 16 input columns] narrow. One CTA per (net, 256 hidden columns): 64 column-threads (a 128-bit slice of every
+// dZ row each) x 4 row groups, 4 rows in flight per thread, the narrow operand broadcast from shared memory; the row groups are combined through
+// shared memory in a fixed order. (The streaming kernel above walks one column per thread with 8 scalar loads in flight: 2.1 TB/s.)
+constexpr int WT_MAXN = 16;
+__global__ void __launch_bounds__(256, 2) wide_tn_kernel(const GemmArgs p) {
+  extern __shared__ __align__(16) float wt_sm[];  // X [K][WT_MAXN] zero padded, then the reduction scratch [4][WT_MAXN + 1][64] float4
+  const int g = blockIdx.y, tid = threadIdx.x, tc = tid & 63, tr = tid >> 6, col = blockIdx.x * 256 + tc * 4, K = p.K, N = p.N;
+  float* xs = wt_sm;
+  float4* red = reinterpret_cast<float4*>(wt_sm + K * WT_MAXN);
+  const float* __restrict__ A = p.A + (int64_t)(g / p.a_gdiv) * p.a_gs;
+  const float* __restrict__ B = p.B + (int64_t)(g / p.b_gdiv) * p.b_gs;
+  for (int i = tid; i < K * WT_MAXN; i += 256) {
+    const int k = i / WT_MAXN, j = i % WT_MAXN;
+    xs[i] = j < N ? __ldg(B + (int64_t)k * p.ldb + j) : 0.f;
+  }
+  __syncthreads();
+  const bool active = col < p.M;
+  float4 acc[WT_MAXN], cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < WT_MAXN; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+    const float* ap = A + col;
+    for (int k0 = tr; k0 < K; k0 += 16) {
+      float4 d[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + 4 * u;
+        d[u] = k < K ? __ldg(reinterpret_cast<const float4*>(ap + (int64_t)k * p.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + 4 * u;
+        if (k >= K) continue;
+        cs.x += d[u].x; cs.y += d[u].y; cs.z += d[u].z; cs.w += d[u].w;
+#pragma unroll
+        for (int q = 0; q < WT_MAXN / 4; ++q) {
+          if (q * 4 < N) {
+            const float4 xv = *reinterpret_cast<const float4*>(xs + k * WT_MAXN + 4 * q);
+            const float xj[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float4& a = acc[q * 4 + e];
+              a.x = fmaf(d[u].x, xj[e], a.x); a.y = fmaf(d[u].y, xj[e], a.y); a.z = fmaf(d[u].z, xj[e], a.z); a.w = fmaf(d[u].w, xj[e], a.w);
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < WT_MAXN; ++j) red[(tr * (WT_MAXN + 1) + j) * 64 + tc] = acc[j];
+  red[(tr * (WT_MAXN + 1) + WT_MAXN) * 64 + tc] = cs;
+  __syncthreads();
+  if (tr == 0 && active) {
+    float* __restrict__ C = p.C + (int64_t)g * p.c_gs;
+#pragma unroll
+    for (int j = 0; j <= WT_MAXN; ++j) {
+      if (j < N || j == WT_MAXN) {
+        float4 a = red[(0 * (WT_MAXN + 1) + j) * 64 + tc];
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+          const float4 t = red[(q * (WT_MAXN + 1) + j) * 64 + tc];
+          a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
+        if (j == WT_MAXN) {
+          if (p.colsum) *reinterpret_cast<float4*>(p.colsum + (int64_t)g * p.colsum_gs + col) = a;
+        } else {
+          C[(int64_t)(col + 0) * p.ldc + j] = a.x; C[(int64_t)(col + 1) * p.ldc + j] = a.y; C[(int64_t)(col + 2) * p.ldc + j] = a.z; C[(int64_t)(col + 3) * p.ldc + j] = a.w;
+        }
+      }
+    }
+  }
+}
+bool wide_tn_eligible(const GemmArgs& a) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  return !a.a_kmajor && !a.b_kmajor && a.N <= WT_MAXN && a.M >= 64 && a.M % 4 == 0 && a.K <= 1024 && !a.bias && a.act < 0 && !a.mask && !a.accumulate && al16(a.A) && a.lda % 4 == 0 &&
+         a.a_gs % 4 == 0 && (!a.colsum || (al16(a.colsum) && a.colsum_gs % 4 == 0));
+}
+
+
+// First-layer input gradient, specialised: C[m][j] = sum_k A[m][k] * B[k][j] with A = dZ [M = batch rows, K = hidden width, K-major] and a narrow
+// B = a column slice of W_1 [K, N <= 8] (the action columns, training.py:36-41). One warp per row: the lanes own 4-wide slices of k (128-bit
+// coalesced loads of the row), their slice of B lives in registers for the whole CTA, 4 rows in flight, butterfly reduction per row.
+constexpr int RD_MAXN = 8, RD_MAXKV = 4;  // N <= 8 output columns, K <= 512 (K / 128 float4 per lane)
+template <int RD_MAXKV, int RD_MAXN>
+__global__ void __launch_bounds__(256) row_dot_kernel(const GemmArgs p) {
+  const int g = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, N = p.N, kv = p.K / 128;
+  const float* __restrict__ A = p.A + (int64_t)(g / p.a_gdiv) * p.a_gs;
+  const float* __restrict__ B = p.B + (int64_t)(g / p.b_gdiv) * p.b_gs;
+  float w[RD_MAXKV][4][RD_MAXN];  // this lane's k values x output columns
+#pragma unroll
+  for (int v = 0; v < RD_MAXKV; ++v)
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int j = 0; j < RD_MAXN; ++j) w[v][e][j] = (v < kv && j < N) ? __ldg(B + (int64_t)(v * 128 + lane * 4 + e) * p.ldb + j) : 0.f;
+  float* __restrict__ C = p.C + (int64_t)g * p.c_gs;
+  const int rows_per_cta = 64, m_end = min(p.M, (int)(blockIdx.x + 1) * rows_per_cta);
+  for (int m0 = blockIdx.x * rows_per_cta + warp; m0 < m_end; m0 += 32) {  // rows m0, m0 + 8, m0 + 16, m0 + 24 in flight
+    float4 a[4][RD_MAXKV];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < RD_MAXKV; ++v) {
+        const int m = m0 + 8 * u;
+        a[u][v] = (v < kv && m < m_end) ? __ldg(reinterpret_cast<const float4*>(A + (int64_t)m * p.lda + v * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int m = m0 + 8 * u;
+      float acc[RD_MAXN];
+#pragma unroll
+      for (int j = 0; j < RD_MAXN; ++j) {
+        float t = 0.f;
+#pragma unroll
+        for (int v = 0; v < RD_MAXKV; ++v) t = fmaf(a[u][v].x, w[v][0][j], fmaf(a[u][v].y, w[v][1][j], fmaf(a[u][v].z, w[v][2][j], fmaf(a[u][v].w, w[v][3][j], t))));
+        acc[j] = t;
+      }
+#pragma unroll
+      for (int j = 0; j < RD_MAXN; ++j)
+        if (j < N) acc[j] = warp_sum(acc[j]);
+      if (m < m_end && lane < N) {
+        float v = acc[0];
+#pragma unroll
+        for (int j = 1; j < RD_MAXN; ++j) v = lane == j ? acc[j] : v;
+        C[(int64_t)m * p.ldc + lane] = v;
+      }
+    }
+  }
+}
+bool row_dot_eligible(const GemmArgs& a) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  return a.a_kmajor && !a.b_kmajor && a.N <= RD_MAXN && a.K % 128 == 0 && a.K <= 128 * RD_MAXKV && a.M >= 32 && !a.bias && a.act < 0 && !a.mask && !a.accumulate && !a.colsum &&
+         al16(a.A) && a.lda % 4 == 0 && a.a_gs % 4 == 0;
+}
+
 template <int BM, int BN, int TM, int TN>
 int launch_cfg(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   constexpr int BK = 16;
@@ -445,6 +669,7 @@ static bool gemm_uses_tc(const il_handle* h, const GemmArgs& a) {
 }
 
 int gemm_init() {
+  IL_CUDA(cudaFuncSetAttribute(wide_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1024 * WT_MAXN + 4 * (WT_MAXN + 1) * 64 * 4) * 4));
   IL_CUDA(cudaFuncSetAttribute(gemm_stream_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   IL_CUDA(cudaFuncSetAttribute(gemm_stream_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   return 0;
@@ -479,6 +704,18 @@ int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   IL_CHECK(!(a.colsum && a.a_kmajor), "gemm: colsum needs the [K, M] operand layout");
   IL_CHECK(!(a.accumulate && a.act >= 0), "gemm: accumulate with activation is not supported");
   const bool plain = !a.bias && a.act < 0 && !a.mask && !a.accumulate;
+  if (h->wide_tn && row_dot_eligible(a)) {
+    const dim3 grid((a.M + 63) / 64, a.G);
+    if (a.K <= 256 && a.N <= 4) IL_LAUNCH(h, (row_dot_kernel<2, 4>), grid, 256, 0, stream, a);
+    else if (a.K <= 256) IL_LAUNCH(h, (row_dot_kernel<2, 8>), grid, 256, 0, stream, a);
+    else IL_LAUNCH(h, (row_dot_kernel<4, 8>), grid, 256, 0, stream, a);
+    return 0;
+  }
+  if (h->wide_tn && a.K >= 64 && wide_tn_eligible(a)) {
+    const size_t smem = ((size_t)a.K * WT_MAXN + 4 * (WT_MAXN + 1) * 64 * 4) * sizeof(float);
+    IL_LAUNCH(h, wide_tn_kernel, dim3((a.M + 255) / 256, a.G), 256, smem, stream, a);
+    return 0;
+  }
   if (plain && !a.a_kmajor && !a.b_kmajor && a.K >= 64 && a.K * ST_MAXS * 4 <= 64 * 1024 && ((a.M <= ST_MAXS && a.N >= 64) || (a.N <= ST_MAXS && a.M >= 64))) {
     const bool wide_a = a.N <= ST_MAXS && a.M >= 64;
     const int W = wide_a ? a.M : a.N;
@@ -486,6 +723,11 @@ int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
     const size_t smem = (size_t)a.K * ST_MAXS * 4;
     if (wide_a) IL_LAUNCH(h, gemm_stream_tn_kernel<true>, grid, 256, smem, stream, a);
     else IL_LAUNCH(h, gemm_stream_tn_kernel<false>, grid, 256, smem, stream, a);
+    return 0;
+  }
+  if (h->first_layer_fast && a.M > 16 && first_layer_eligible(a)) {
+    dim3 grid(a.N / FL_COLS, (a.M + FL_ROWS * FL_ITERS - 1) / (FL_ROWS * FL_ITERS), a.G);
+    IL_LAUNCH(h, first_layer_relu_kernel, grid, 256, 0, stream, a);
     return 0;
   }
   if (a.M > 16 && thin_k_eligible(a)) {
