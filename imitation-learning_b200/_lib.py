@@ -72,6 +72,15 @@ class GailxUpdateArgs(C.Structure):
               ('entropy_bonus', C.c_float), ('pos_class_prior', C.c_float), ('nonnegative_margin', C.c_float), ('out_losses', vp), ('workspace', vp), ('workspace_bytes', C.c_int64)]
 
 
+class Red(C.Structure):
+  _fields_ = [('predictor', Mlp), ('target', Mlp), ('sigma', vp), ('state_only', C.c_int32), ('_pad', C.c_int32)]
+
+
+class RedUpdateArgs(C.Structure):
+  _fields_ = [('disc', Red), ('opt', Adam), ('batch', Batch), ('R', C.c_int32), ('_pad', C.c_int32), ('mask_in', vp), ('mask_hid', vp * MAX_LAYERS), ('out_loss', vp), ('workspace', vp),
+              ('workspace_bytes', C.c_int64)]
+
+
 class Pwil(C.Structure):
   _fields_ = [('atoms', vp), ('scale', vp), ('offset', vp), ('weights', vp), ('N', C.c_int32), ('d', C.c_int32), ('S', C.c_int32), ('A', C.c_int32), ('state_only', C.c_int32),
               ('time_horizon', C.c_int32), ('reward_scale', C.c_float), ('reward_bandwidth', C.c_float)]
@@ -120,6 +129,15 @@ SIGNATURES = {
   'il_bc_workspace_bytes': (i64, [P(BcArgs)]),
   'il_bc_update': (C.c_int, [vp, P(BcArgs), vp]),
   'il_adam_step': (C.c_int, [vp, vp, vp, P(Adam), i64, vp]),
+  'il_fill_dropout_mask': (C.c_int, [vp, vp, i64, f32, u64, u64, vp, vp]),
+  'il_actor_dropout_workspace_bytes': (i64, [P(Mlp), C.c_int, C.c_int]),
+  'il_actor_log_prob_dropout': (C.c_int, [vp, P(Mlp), C.c_int, C.c_int, C.c_int, vp, i64, C.c_int, vp, vp, P(vp), vp, vp, i64, vp]),
+  'il_bc_update_dropout': (C.c_int, [vp, P(BcArgs), vp, P(vp), vp]),
+  'il_dril_reward': (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, i64, C.c_int, vp, vp]),
+  'il_red_workspace_bytes': (i64, [P(Red), C.c_int, C.c_int]),
+  'il_red_update': (C.c_int, [vp, P(RedUpdateArgs), vp]),
+  'il_red_sigma': (C.c_int, [vp, P(Red), C.c_int, P(Batch), vp, P(vp), vp, i64, vp]),
+  'il_red_reward': (C.c_int, [vp, P(Red), C.c_int, P(Batch), vp, i64, C.c_int, vp, i64, vp]),
   'il_replay_append': (C.c_int, [vp, P(Replay), C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]),
   'il_replay_wrap_absorbing': (C.c_int, [vp, P(Replay), C.c_int, vp, vp]),
   'il_replay_transfer': (C.c_int, [vp, P(Replay), C.c_int, P(Replay), vp]),
@@ -216,6 +234,13 @@ def stream() -> int:
 
 def launch_count() -> int:
   return int(lib().il_launch_count(handle()))
+
+
+def mask_array(masks):
+  """ctypes array of MAX_LAYERS device pointers (NULL-padded) for the per-hidden-layer dropout masks."""
+  arr = (vp * MAX_LAYERS)()
+  for i, t in enumerate(masks or []): arr[i] = None if t is None else t.data_ptr()
+  return arr
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:

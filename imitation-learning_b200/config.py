@@ -65,8 +65,6 @@ def load_config(overrides: Optional[List[str]] = None, conf_dir: str = CONF_DIR)
     if groups[g] in (None, 'null', ''): continue
     path = os.path.join(conf_dir, g, f'{groups[g]}.yaml')
     if not os.path.exists(path):
-      if g == 'algorithm' and groups[g] in ('DRIL', 'RED'):  # train.py:28 accepts them; this build does not accelerate them
-        raise NotImplementedError(f'algorithm={groups[g]} is outside the accelerated hot path (BASELINE.json north_star; SURVEY §8f row 4); supported: AdRIL, BC, GAIL, GMMIL, PWIL, SAC')
       raise FileNotFoundError(f'no {g} config {groups[g]!r} under {conf_dir}')
     with open(path) as f: _merge(cfg, yaml.safe_load(f) or {})
   for k, v in rest:

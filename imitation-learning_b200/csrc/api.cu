@@ -108,6 +108,8 @@ extern "C" int il_struct_sizes(int32_t* out) {
   out[10] = (int32_t)sizeof(il_eval_args);
   out[11] = (int32_t)sizeof(il_gailx);
   out[12] = (int32_t)sizeof(il_gailx_update_args);
+  out[13] = (int32_t)sizeof(il_red);
+  out[14] = (int32_t)sizeof(il_red_update_args);
   return 0;
 }
 

@@ -234,6 +234,30 @@ __global__ void __launch_bounds__(256) mlp_small_forward_kernel(const SmallFwdAr
     const float* xin = bufs[l & 1];
     float* xout = bufs[(l + 1) & 1];
     const bool vec = (in % 4 == 0) && (p.m.stride % 4 == 0);
+    if (NR == 1 && vec) {
+      // single row (the training rollout, train.py:152): the kernel is a pure weight stream, so every warp keeps FOUR weight rows in flight
+      // (4 output units per iteration, 128-bit loads) and reduces them together — the one-row-at-a-time loop was latency-bound at 1.7 TB/s
+      for (int o0 = warp * 4; o0 < od; o0 += 32) {
+        float a4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = lane * 4; k < in; k += 128) {
+          const float4 x4 = *reinterpret_cast<const float4*>(xin + k);
+          float4 w4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) w4[u] = o0 + u < od ? __ldg(reinterpret_cast<const float4*>(W + (int64_t)(o0 + u) * in + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) a4[u] = fmaf(w4[u].x, x4.x, fmaf(w4[u].y, x4.y, fmaf(w4[u].z, x4.z, fmaf(w4[u].w, x4.w, a4[u]))));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a4[u] = warp_sum(a4[u]);
+        if (lane < 4 && o0 + lane < od) {
+          float v = (lane == 0 ? a4[0] : lane == 1 ? a4[1] : lane == 2 ? a4[2] : a4[3]) + __ldg(bias + o0 + lane);
+          if (l < L - 1) v = act_apply(v, p.m.activation);
+          xout[o0 + lane] = v;
+        }
+      }
+      __syncthreads();
+      continue;
+    }
     for (int o = warp; o < od; o += 8) {
       float acc[NR];
 #pragma unroll

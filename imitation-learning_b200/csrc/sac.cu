@@ -304,6 +304,18 @@ BcWs bc_layout(const il_bc_args* a, char* base) {
 }
 }  // namespace
 
+// launchers shared with the dropout-policy variant (dropout_nets.cu)
+int bc_head_backward_launch(il_handle* h, const float* head, const il_batch* batch, float* dhead, float* row_loss, int R, cudaStream_t st) {
+  const RowLayout L = row_layout(batch->S, batch->A);
+  IL_LAUNCH(h, bc_head_backward_kernel, (unsigned)(((int64_t)R * batch->B + 127) / 128), 128, 0, st, head, batch->rows, batch->replica_stride, L.len, L.action, L.weight, dhead, row_loss, R,
+            batch->B, batch->A);
+  return 0;
+}
+int bc_row_mean_launch(il_handle* h, const float* row_loss, float* out_loss, int R, int B, cudaStream_t st) {
+  IL_LAUNCH(h, row_mean_kernel, R, 256, 0, st, row_loss, out_loss, B);
+  return 0;
+}
+
 extern "C" int64_t il_bc_workspace_bytes(const il_bc_args* a) { return a ? bc_layout(a, nullptr).bytes : -1; }
 
 extern "C" int il_bc_update(il_handle* h, const il_bc_args* a, void* stream) {

@@ -137,8 +137,12 @@ class TanhNormalPolicy:
 class SoftActor(_Module):
   """:84-102. `actor(state)` returns a TanhNormalPolicy; state is [n, S] (R == 1) or [R, n, S]."""
 
+  ENSEMBLE = 5  # :105
+
   def __init__(self, state_size: int, action_size: int, model_cfg, replicas: int = 1, rng: Optional[ReplicaRNG] = None, device=None):
-    assert _cfg_get(model_cfg, 'input_dropout', 0) == 0 and _cfg_get(model_cfg, 'dropout', 0) == 0, 'dropout actors (DRIL) are outside the accelerated path'
+    # :88 — a policy with dropout is DRIL's "discriminator" (train.py:74); its density / BC update run on the dropout MLP program (csrc/dropout_nets.cu)
+    self.input_dropout, self.dropout = float(_cfg_get(model_cfg, 'input_dropout', 0) or 0), float(_cfg_get(model_cfg, 'dropout', 0) or 0)
+    self.training, self.q, self._drop_ws, self._drop_rng = True, None, None, None
     self.state_size, self.action_size, self.replicas = state_size, action_size, replicas
     self.log_std_dev_min, self.log_std_dev_max = -20, 2  # :87 (the kernel hard-codes the same clamp)
     dims = [state_size] + [model_cfg.hidden_size] * model_cfg.depth + [2 * action_size]
@@ -154,7 +158,8 @@ class SoftActor(_Module):
 
   def _state_items(self):
     v = self.mlp.layer_views()[0]
-    return [(f'actor.{2 * l}.{n}', v[2 * l + i]) for l in range(self.mlp.n_layers) for i, n in enumerate(('weight', 'bias'))]
+    base, step = (1 if self.input_dropout > 0 else 0), (3 if self.dropout > 0 else 2)  # nn.Sequential indices: [Dropout], Linear, [Dropout], activation, ... (:51-61)
+    return [(f'actor.{base + step * l}.{n}', v[2 * l + i]) for l in range(self.mlp.n_layers) for i, n in enumerate(('weight', 'bias'))]
 
   def _run(self, state: Tensor, eps: Optional[Tensor] = None, given: Optional[Tensor] = None, want=('action', )) -> Dict[str, Tensor]:
     R, A = self.replicas, self.action_size
@@ -171,12 +176,69 @@ class SoftActor(_Module):
                                            _lib.stream()))
     return out
 
+  @property
+  def has_dropout(self) -> bool: return self.input_dropout > 0 or self.dropout > 0
+
   def forward(self, state: Tensor) -> TanhNormalPolicy:
+    if self.has_dropout and self.training: raise NotImplementedError('sampling from a dropout policy in train mode is not used by the reference (DRIL only evaluates log_prob, models.py:104-120)')
     return TanhNormalPolicy(self, _as_rns(state, self.replicas, self.state_size, self.device))
 
   __call__ = forward
 
-  def log_prob(self, state: Tensor, action: Tensor) -> Tensor:  # :97-99
+  # ---- dropout policy (DRIL) ----------------------------------------------------------------------------------------------------
+  def draw_masks(self, n: int) -> List[Optional[Tensor]]:
+    """[input mask [R, n, S] or None, one [R, n, H] mask per hidden layer or None]: Bernoulli(1 - p) / (1 - p) draws on the device (Philox), the analogue
+    of nn.Dropout's draws from torch's global stream."""
+    if self._drop_rng is None: self._drop_rng = _RNG(default_rng.seed + 977, self.device)
+    rng, R, lib = self._drop_rng, self.replicas, _lib.lib()
+    def draw(width, p):
+      if p <= 0: return None
+      out = torch.empty(R, n, width, device=self.device)
+      ctr = rng._ctr(self.device)
+      _lib.check(lib.il_fill_dropout_mask(_lib.handle(), out.data_ptr(), out.numel(), p, rng.seed, 31, ctr.data_ptr(), _lib.stream()))
+      _lib.check(lib.il_counter_add(_lib.handle(), ctr.data_ptr(), (out.numel() + 3) // 4, _lib.stream()))
+      return out
+    return [draw(self.state_size, self.input_dropout)] + [draw(self.mlp.dims[l + 1], self.dropout) for l in range(self.mlp.n_layers - 1)]
+
+  def _log_prob_dropout(self, state: Tensor, action: Tensor, repeat: int = 1, masks: Optional[List[Optional[Tensor]]] = None) -> Tensor:
+    R, S, A = self.replicas, self.state_size, self.action_size
+    s, a = _as_rns(state, R, S, self.device), _as_rns(action, R, A, self.device)
+    n = s.size(1) * repeat
+    if masks is None: masks = self.draw_masks(n)
+    masks = [None if m is None else torch.as_tensor(m, dtype=torch.float32).to(self.device).reshape(R, n, -1).contiguous() for m in masks]
+    m = self.mlp.c_struct()
+    need = _lib.lib().il_actor_dropout_workspace_bytes(C.byref(m), R, n)
+    if self._drop_ws is None or self._drop_ws.numel() < need: self._drop_ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
+    out = torch.empty(R, n, device=self.device)
+    _lib.check(_lib.lib().il_actor_log_prob_dropout(_lib.handle(), C.byref(m), R, n, repeat, s.data_ptr(), s.stride(0), s.stride(1), a.data_ptr(), _lib.ptr(masks[0]), _lib.mask_array(masks[1:]),
+                                                    out.data_ptr(), self._drop_ws.data_ptr(), self._drop_ws.numel(), _lib.stream()))
+    return out
+
+  def _get_action_uncertainty(self, state: Tensor, action: Tensor, masks=None) -> Tensor:  # :104-107
+    lp = self._log_prob_dropout(state, action, repeat=self.ENSEMBLE, masks=masks)
+    R, B = self.replicas, lp.size(1) // self.ENSEMBLE
+    var = torch.empty(R, B, device=self.device)
+    _lib.check(_lib.lib().il_dril_reward(_lib.handle(), lp.data_ptr(), R, B, self.ENSEMBLE, None, 0, None, 0, 0, var.data_ptr(), _lib.stream()))
+    return self._squeeze(var)
+
+  def set_uncertainty_threshold(self, expert_state: Tensor, expert_action: Tensor, quantile_cutoff: float, masks=None):  # :110-111 (one-off set-up statistic)
+    R = self.replicas
+    es = torch.as_tensor(expert_state, dtype=torch.float32).to(self.device)
+    ea = torch.as_tensor(expert_action, dtype=torch.float32).to(self.device)
+    if es.dim() == 2: es, ea = es.unsqueeze(0).expand(R, -1, -1), ea.unsqueeze(0).expand(R, -1, -1)
+    var = self._get_action_uncertainty(es, ea, masks=masks).reshape(R, -1)
+    self._q = torch.quantile(var, quantile_cutoff, dim=1).contiguous()
+    self.q = float(self._q[0]) if R == 1 else self._q
+
+  def predict_reward(self, state: Tensor, action: Tensor, masks=None, out: Optional[Tensor] = None) -> Tensor:  # :113-120
+    lp = self._log_prob_dropout(state, action, repeat=self.ENSEMBLE, masks=masks)
+    R, B = self.replicas, lp.size(1) // self.ENSEMBLE
+    out = torch.empty(R, B, device=self.device) if out is None else out
+    _lib.check(_lib.lib().il_dril_reward(_lib.handle(), lp.data_ptr(), R, B, self.ENSEMBLE, self._q.data_ptr(), 0, out.data_ptr(), out.stride(0), out.stride(1), None, _lib.stream()))
+    return self._squeeze(out) if out.dim() == 2 and out.is_contiguous() else out
+
+  def log_prob(self, state: Tensor, action: Tensor, masks=None) -> Tensor:  # :97-99
+    if self.has_dropout and (self.training or masks is not None): return self._squeeze(self._log_prob_dropout(state, action, masks=masks))
     return self._squeeze(self._run(state, given=action, want=('log_prob', ))['log_prob'])
 
   def get_greedy_action(self, state: Tensor) -> Tensor:  # :101-102
@@ -544,6 +606,96 @@ class PWILDiscriminator:
   def compute_reward(self, state: Tensor, action: Tensor):  # :232-249
     out = self.compute_reward_batch(state, action)
     return float(out[0]) if self.replicas == 1 else out
+
+
+class REDDiscriminator(_Module):
+  """:252-284 — predictor (with dropout) and frozen random target embedding networks (din -> hidden^depth -> din), one pair per replica."""
+
+  def __init__(self, state_size: int, action_size: int, imitation_cfg, replicas: int = 1, rng: Optional[ReplicaRNG] = None, device=None):
+    cfg = imitation_cfg.discriminator
+    self.state_only, self.replicas = bool(imitation_cfg.state_only), replicas
+    self.state_size, self.action_size = state_size, action_size
+    din = state_size if self.state_only else state_size + action_size
+    dims = [din] + [cfg.hidden_size] * cfg.depth + [din]
+    self.input_dropout, self.dropout = float(_cfg_get(cfg, 'input_dropout', 0) or 0), float(_cfg_get(cfg, 'dropout', 0) or 0)
+    self.predictor, self.target = ReplicaMLP(dims, cfg.activation, replicas, 1, device), ReplicaMLP(dims, cfg.activation, replicas, 1, device)
+    self.mlp = self.predictor  # parameters(): only the predictor trains (:267-268; AdamW skips the frozen target, train.py:84)
+    self.device = self.predictor.device
+    for r in range(replicas):
+      with (rng.replica(r) if rng is not None else _null_ctx()):
+        self.predictor.load_params(r, 0, init_fcnn_params(dims, cfg.activation))  # :265
+        self.target.load_params(r, 0, init_fcnn_params(dims, cfg.activation))     # :266
+    s1 = _cfg_get(imitation_cfg, 'reward_bandwidth_scale', None)
+    self.sigma = torch.full((replicas, ), float(s1) if s1 else 0.0, device=self.device)  # :269
+    self._sigma_set = bool(s1)
+    self.training, self._ws, self._rng = True, None, None
+
+  @property
+  def sigma_1(self): return None if not self._sigma_set else (float(self.sigma[0]) if self.replicas == 1 else self.sigma)
+
+  def c_struct(self) -> _lib.Red:
+    d = _lib.Red()
+    d.predictor, d.target, d.sigma, d.state_only = self.predictor.c_struct(), self.target.c_struct(), self.sigma.data_ptr(), int(self.state_only)
+    return d
+
+  def _state_items(self):
+    out = []
+    for name, mlp in (('predictor', self.predictor), ('target', self.target)):
+      v = mlp.layer_views()[0]
+      step = 2 + (1 if (name == 'predictor' and self.dropout > 0) else 0)  # nn.Sequential indices: [Dropout], Linear, [Dropout], activation, ...
+      base = 1 if (name == 'predictor' and self.input_dropout > 0) else 0
+      out += [(f'{name}.embedding.{base + step * l}.{n}', v[2 * l + i]) for l in range(mlp.n_layers) for i, n in enumerate(('weight', 'bias'))]
+    return out
+
+  def workspace(self, B: int) -> Tensor:
+    d = self.c_struct()
+    need = _lib.lib().il_red_workspace_bytes(C.byref(d), self.replicas, B)
+    if self._ws is None or self._ws.numel() < need: self._ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
+    return self._ws
+
+  def draw_masks(self, n: int) -> List[Optional[Tensor]]:
+    if self._rng is None: self._rng = _RNG(default_rng.seed + 1979, self.device)
+    rng, R, lib = self._rng, self.replicas, _lib.lib()
+    def draw(width, p):
+      if p <= 0: return None
+      out = torch.empty(R, n, width, device=self.device)
+      ctr = rng._ctr(self.device)
+      _lib.check(lib.il_fill_dropout_mask(_lib.handle(), out.data_ptr(), out.numel(), p, rng.seed, 32, ctr.data_ptr(), _lib.stream()))
+      _lib.check(lib.il_counter_add(_lib.handle(), ctr.data_ptr(), (out.numel() + 3) // 4, _lib.stream()))
+      return out
+    return [draw(self.predictor.dims[0], self.input_dropout)] + [draw(self.predictor.dims[l + 1], self.dropout) for l in range(self.predictor.n_layers - 1)]
+
+  def _batch_of(self, state: Tensor, action: Tensor) -> TransitionBatch:
+    R = self.replicas
+    s, a = _as_rns(state, R, self.state_size, self.device), _as_rns(action, R, self.action_size, self.device)
+    _, row = _lib.py_row_layout(self.state_size, self.action_size)
+    tb = TransitionBatch(torch.zeros(R, s.size(1), row, device=self.device), self.state_size, self.action_size, False)
+    tb.rows[..., :self.state_size], tb.rows[..., self.state_size:self.state_size + self.action_size] = s, a
+    return tb
+
+  def set_sigma_batch(self, batch: TransitionBatch, masks=None):  # :277-280
+    if self._sigma_set: return
+    if masks is None and self.training: masks = self.draw_masks(batch.B)
+    masks = masks or [None] * self.predictor.n_layers
+    d, b, ws = self.c_struct(), batch.c_struct(), self.workspace(batch.B)
+    _lib.check(_lib.lib().il_red_sigma(_lib.handle(), C.byref(d), self.replicas, C.byref(b), _lib.ptr(masks[0]), _lib.mask_array(masks[1:]), ws.data_ptr(), ws.numel(), _lib.stream()))
+    self._sigma_set = True
+
+  def set_sigma(self, expert_state: Tensor, expert_action: Tensor, masks=None):
+    es, ea = torch.as_tensor(expert_state, dtype=torch.float32).to(self.device), torch.as_tensor(expert_action, dtype=torch.float32).to(self.device)
+    if es.dim() == 2 and self.replicas > 1: es, ea = es.unsqueeze(0).expand(self.replicas, -1, -1), ea.unsqueeze(0).expand(self.replicas, -1, -1)
+    self.set_sigma_batch(self._batch_of(es, ea), masks)
+
+  def predict_reward_batch(self, batch: TransitionBatch, reward_out: Optional[Tensor] = None) -> Tensor:  # :282-284 (eval mode, train.py:147)
+    R, B = self.replicas, batch.B
+    if reward_out is None: reward_out = torch.empty(R, B, device=self.device)
+    d, b, ws = self.c_struct(), batch.c_struct(), self.workspace(B)
+    _lib.check(_lib.lib().il_red_reward(_lib.handle(), C.byref(d), R, C.byref(b), reward_out.data_ptr(), reward_out.stride(0), reward_out.stride(1), ws.data_ptr(), ws.numel(), _lib.stream()))
+    return reward_out
+
+  def predict_reward(self, state: Tensor, action: Tensor) -> Tensor:
+    out = self.predict_reward_batch(self._batch_of(state, action))
+    return out[0] if self.replicas == 1 else out
 
 
 def mix_expert_agent_transitions(transitions: TransitionBatch, expert_transitions: TransitionBatch):

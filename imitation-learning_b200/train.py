@@ -22,11 +22,11 @@ from .config import Config, load_config
 from .environments import D4RLEnv, ENVS
 from .evaluation import evaluate_agent
 from .memory import ReplayMemory, TransitionBatch
-from .models import GAILDiscriminator, GMMILDiscriminator, PWILDiscriminator, RewardRelabeller, SoftActor, TwinCritic, _RNG, create_target_network
+from .models import GAILDiscriminator, GMMILDiscriminator, PWILDiscriminator, REDDiscriminator, RewardRelabeller, SoftActor, TwinCritic, _RNG, create_target_network
 from .net import ReplicaRNG
 from .optim import Adam, AdamW
 
-ACCELERATED = ['AdRIL', 'BC', 'SAC', 'GAIL', 'GMMIL', 'PWIL']
+ACCELERATED = ['AdRIL', 'BC', 'DRIL', 'SAC', 'GAIL', 'GMMIL', 'PWIL', 'RED']
 
 
 def check_config(cfg: Config):
@@ -41,6 +41,7 @@ def check_config(cfg: Config):
   if cfg.algorithm == 'AdRIL':  # train.py:35-37
     assert cfg.imitation.mix_expert_data == 'mixed_batch'
     assert cfg.imitation.update_freq >= 0
+  if cfg.algorithm == 'DRIL': assert 0 <= cfg.imitation.quantile_cutoff <= 1  # train.py:38-39
   if cfg.algorithm == 'GAIL':
     assert cfg.imitation.mix_expert_data != 'prefill_memory'
     assert cfg.imitation.discriminator.reward_function in ['AIRL', 'FAIRL', 'GAIL']
@@ -81,6 +82,8 @@ class Trainer:
     self.actor, self.critic = SoftActor(S, A, cfg.reinforcement.actor, replicas=nrep, rng=rng, device=dev), TwinCritic(S, A, cfg.reinforcement.critic, replicas=nrep, rng=rng, device=dev)
     self.discriminator = None
     if self.algorithm == 'GAIL': self.discriminator = GAILDiscriminator(S, A, cfg.imitation, cfg.reinforcement.discount, replicas=nrep, rng=rng, device=dev)
+    elif self.algorithm == 'DRIL': self.discriminator = SoftActor(S, A, cfg.imitation.discriminator, replicas=nrep, rng=rng, device=dev)  # train.py:74
+    elif self.algorithm == 'RED': self.discriminator = REDDiscriminator(S, A, cfg.imitation, replicas=nrep, rng=rng, device=dev)  # train.py:82
     if fast_init and R > 1: self._replicate()
     self.log_alpha = torch.zeros(R, device=dev)
     self.target_critic, self.entropy_target = create_target_network(self.critic), cfg.reinforcement.target_temperature * A
@@ -95,8 +98,9 @@ class Trainer:
     self.memory = ReplayMemory(cfg.memory.size, S, A, absorbing, replicas=R, device=dev)
     self.memory.seed = seed
     # train.py:70-84
+    if self.algorithm in ('DRIL', 'GAIL', 'RED'):
+      self.discriminator_optimiser = AdamW(self.discriminator.parameters(), lr=cfg.imitation.learning_rate, weight_decay=cfg.imitation.weight_decay)  # train.py:83-84
     if self.algorithm == 'GAIL':
-      self.discriminator_optimiser = AdamW(self.discriminator.parameters(), lr=cfg.imitation.learning_rate, weight_decay=cfg.imitation.weight_decay)
       self.discriminator.eval()  # train.py:147
     elif self.algorithm == 'AdRIL':
       self.discriminator = RewardRelabeller(cfg.imitation.update_freq, cfg.imitation.balanced, device=dev)  # train.py:72
@@ -127,6 +131,7 @@ class Trainer:
     self.gail_losses = f(R, 2)
     self.rng = _RNG(seed, dev)
     self.inject = False  # tests: True = all noise / index buffers are filled by the caller before each step
+    self.dril_masks = None  # tests (inject): the dropout masks of this step's DRIL ensemble pass
     self.device_rng = bool(cfg.get('device_rng', True))
     self.actor_ws = torch.empty(self.lib.il_actor_workspace_bytes(C.byref(self.actor.mlp.c_struct()), R, 1), dtype=torch.uint8, device=dev)
     self._sac_args = None
@@ -174,6 +179,9 @@ class Trainer:
       mod.mlp.flat = mod.mlp.flat.expand(self.R, -1).contiguous()
       mod.mlp.replicas = self.R
       mod.replicas = self.R
+      if isinstance(mod, REDDiscriminator):  # the frozen target network and the bandwidths as well
+        mod.target.flat, mod.target.replicas = mod.target.flat.expand(self.R, -1).contiguous(), self.R
+        mod.sigma = mod.sigma.expand(self.R).contiguous()
       if getattr(mod, 'u', None) is not None: mod.u, mod.v = mod.u.expand(self.R, -1).contiguous(), mod.v.expand(self.R, -1).contiguous()
 
   # ---- train.py:150-168 -------------------------------------------------------------------------------------------
@@ -222,6 +230,15 @@ class Trainer:
         mix_expert_agent_transitions(self.batch, self.expert_batch)  # train.py:183
       if self.algorithm == 'GAIL': self.discriminator.predict_reward_batch(self.batch, write_rewards=True, actor=self.actor)  # train.py:194
       else: self.discriminator.predict_reward_batch(self.batch, self.expert_batch, reward_out=self.batch.rows[..., self.batch.off['rewards']])  # train.py:196
+    if self.algorithm in ('DRIL', 'RED'):  # train.py:183,190-191,196-197
+      if cfg.imitation.mix_expert_data == 'mixed_batch':
+        from .models import mix_expert_agent_transitions
+        mix_expert_agent_transitions(self.batch, self.expert_batch)
+      view = self.batch.rows[..., self.batch.off['rewards']]
+      if self.algorithm == 'DRIL':
+        masks = self.dril_masks if self.inject else None
+        self.discriminator.predict_reward(self.batch.rows[..., :self.S], self.batch.rows[..., self.S:self.S + self.A], masks=masks, out=view)
+      else: self.discriminator.predict_reward_batch(self.batch, reward_out=view)
     if self.algorithm == 'AdRIL':  # train.py:188-189; `step` of the reference = step_f - 1 here (the rollout has already advanced the counter)
       self.discriminator.resample_and_relabel(self.batch, self.expert_batch, self.step_f, self.memory._num_trajectories, self.expert_memory.num_trajectories, step_offset=-1.0)
     from .training import sac_update
@@ -252,6 +269,35 @@ class Trainer:
       self.expert_memory.gather(idx.contiguous(), out=self.expert_batch)
       behavioural_cloning_update(self.actor, self.expert_batch, opt, out_loss=loss)
     return loss
+
+  def pretrain_discriminator(self, iterations: Optional[int] = None, batches=None, masks=None, threshold_masks=None):
+    """train.py:117-133 for DRIL / RED: `iterations` updates of the dropout policy ensemble (behavioural cloning) / the RED predictor (regression onto its random
+    target) on epoch-wise shuffled expert minibatches (every replica draws its own permutations; `batches` injects the index rows instead), then the uncertainty
+    threshold (all expert transitions) / the kernel bandwidth (first minibatch) is fixed, and the expert data optionally pre-fills the replay memory."""
+    from .training import behavioural_cloning_update, target_estimation_update
+    cfg, B, n, d = self.cfg, self.B, self.expert_memory.size, self.discriminator
+    iterations = cfg.imitation.pretraining.iterations if iterations is None else iterations
+    per_epoch, perm = max(n // B, 1), None
+    for it in range(iterations):
+      if batches is not None: idx = torch.as_tensor(batches[it], dtype=torch.int32).to(self.device).reshape(-1, B)
+      else:
+        if it % per_epoch == 0: perm = torch.stack([torch.randperm(n) for _ in range(self.R)]).to(self.device, torch.int32)
+        j = it % per_epoch
+        idx = perm[:, j * B:(j + 1) * B] if n >= B else perm[:, torch.arange(B) % n]
+      self.expert_memory.gather(idx.contiguous(), out=self.expert_batch)
+      m = None if masks is None else masks[it]
+      if self.algorithm == 'DRIL': behavioural_cloning_update(d, self.expert_batch, self.discriminator_optimiser, masks=m)
+      else: target_estimation_update(d, self.expert_batch, self.discriminator_optimiser, masks=m)
+    em = self.expert_memory
+    if self.algorithm == 'DRIL':
+      d.set_uncertainty_threshold(em.rows[0, :, :self.S], em.rows[0, :, self.S:self.S + self.A], cfg.imitation.quantile_cutoff, masks=threshold_masks)  # train.py:127
+    else:
+      first = torch.arange(B, dtype=torch.int32, device=self.device).unsqueeze(0).expand(self.R, -1).contiguous() % n
+      self.expert_memory.gather(first, out=self.expert_batch)
+      d.set_sigma_batch(self.expert_batch, masks=threshold_masks)  # train.py:129: estimated on one minibatch
+      d.eval()  # train.py:147
+    if cfg.imitation.mix_expert_data == 'prefill_memory': self.memory.transfer_transitions(self.expert_memory)  # train.py:133
+    self._pretrained = True
 
   def _will_update(self, step: int) -> bool:
     return step >= self.cfg.training.start and step % self.cfg.training.interval == 0  # train.py:171
@@ -345,6 +391,7 @@ def train(cfg: Config, file_prefix: str = '') -> float:
         torch.save(dict(actor=trainer.actor.state_dict()), f'{file_prefix}agent.pth')  # train.py:108
         torch.save(metrics, f'{file_prefix}metrics.pth')
       return float(np.mean(normalized))
+  if cfg.algorithm in ('DRIL', 'RED'): trainer.pretrain_discriminator()  # train.py:117-133
   for step in range(1, cfg.steps + 1):
     trainer.train_step()
     if cfg.logging.interval > 0 and step % cfg.logging.interval == 0 and trainer._will_update(step): trainer.log_aux()  # train.py:205: only inside the update branch
@@ -360,9 +407,13 @@ def train(cfg: Config, file_prefix: str = '') -> float:
   if cfg.check_time_usage: metrics['training_time'] = time.time() - start_time  # train.py:229-230
   eps = trainer.episodes.cpu().numpy()
   metrics['train_returns'] = (trainer.return_sum.cpu().numpy() / np.maximum(eps, 1)).tolist()
+  if cfg.save_trajectories:  # train.py:232-235: trajectories of the trained agent (every rank writes its own shard of the replica axis; rank 0 keeps the reference's file name)
+    if cfg.render: raise NotImplementedError('render=true needs a PyBullet window (environments.py:52-53); the synthetic device env has none')
+    _, trajectories = evaluate_agent(trainer.actor, trainer.eval_env, cfg.evaluation.episodes, return_trajectories=True)
+    torch.save(trajectories, f'{file_prefix}trajectories.pth' if rank == 0 else f'{file_prefix}trajectories.rank{rank}.pth')
   if rank == 0:  # train.py:237-239
     torch.save(trainer.state_dicts(), f'{file_prefix}agent.pth')
-    if cfg.algorithm == 'GAIL': torch.save(trainer.discriminator.state_dict(), f'{file_prefix}discriminator.pth')
+    if cfg.algorithm in ('DRIL', 'GAIL', 'RED'): torch.save(trainer.discriminator.state_dict(), f'{file_prefix}discriminator.pth')  # train.py:238
     torch.save(metrics, f'{file_prefix}metrics.pth')
   return float(np.mean(score)) if score else float('nan')
 

@@ -122,17 +122,39 @@ def _general_adversarial_update(actor, disc: GAILDiscriminator, pol: TransitionB
   _lib.check(lib.il_gailx_update(_lib.handle(), C.byref(a), _lib.stream()))
 
 
-def behavioural_cloning_update(actor: SoftActor, expert_transition, actor_optimiser: Adam, out_loss: Optional[Tensor] = None):
-  """training.py:57-64: one maximum-likelihood step of the actor on expert (state, action, weight) rows."""
+def behavioural_cloning_update(actor: SoftActor, expert_transition, actor_optimiser: Adam, out_loss: Optional[Tensor] = None, masks=None):
+  """training.py:57-64: one maximum-likelihood step of the actor on expert (state, action, weight) rows. A policy with dropout in train mode (DRIL's
+  ensemble, train.py:120) runs on the dropout program; `masks` injects its dropout draws ([input mask, hidden masks...], pre-scaled)."""
   R, device = actor.replicas, actor.device
   batch, _ = _as_batch(expert_transition, device)
   a = _lib.BcArgs()
   a.actor, a.opt, a.batch, a.R, a.out_loss = actor.mlp.c_struct(), actor_optimiser.c_struct(), batch.c_struct(), R, _lib.ptr(out_loss)
+  if getattr(actor, 'has_dropout', False) and (actor.training or masks is not None):
+    if masks is None: masks = actor.draw_masks(batch.B)
+    masks = [None if m is None else torch.as_tensor(m, dtype=torch.float32).to(device).reshape(R, batch.B, -1).contiguous() for m in masks]
+    need = _lib.lib().il_actor_dropout_workspace_bytes(C.byref(a.actor), R, batch.B)
+    ws = _workspace(actor, 'bc_dropout', need, device)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    _lib.check(_lib.lib().il_bc_update_dropout(_lib.handle(), C.byref(a), _lib.ptr(masks[0]), _lib.mask_array(masks[1:]), _lib.stream()))
+    return
   need = _lib.lib().il_bc_workspace_bytes(C.byref(a))
   ws = _workspace(actor, 'bc', need, device)
   a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
   _lib.check(_lib.lib().il_bc_update(_lib.handle(), C.byref(a), _lib.stream()))
 
 
-def target_estimation_update(discriminator, expert_transition, discriminator_optimiser):
-  raise NotImplementedError('RED (training.py:68-75) is outside the accelerated path (SURVEY §8 scope)')
+def target_estimation_update(discriminator, expert_transition, discriminator_optimiser: Adam, out_loss: Optional[Tensor] = None, masks=None):
+  """training.py:68-75: one regression step of RED's predictor onto its frozen random target on expert rows (dropout masks drawn on the device in train mode,
+  or injected through `masks`)."""
+  R, device = discriminator.replicas, discriminator.device
+  batch, _ = _as_batch(expert_transition, device)
+  if masks is None and discriminator.training and (discriminator.input_dropout > 0 or discriminator.dropout > 0): masks = discriminator.draw_masks(batch.B)
+  masks = [None if m is None else torch.as_tensor(m, dtype=torch.float32).to(device).reshape(R, batch.B, -1).contiguous() for m in (masks or [None] * discriminator.predictor.n_layers)]
+  a = _lib.RedUpdateArgs()
+  a.disc, a.opt, a.batch, a.R = discriminator.c_struct(), discriminator_optimiser.c_struct(), batch.c_struct(), R
+  a.mask_in = _lib.ptr(masks[0])
+  for i, m in enumerate(masks[1:]): a.mask_hid[i] = _lib.ptr(m)
+  a.out_loss = _lib.ptr(out_loss)
+  ws = discriminator.workspace(batch.B)
+  a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+  _lib.check(_lib.lib().il_red_update(_lib.handle(), C.byref(a), _lib.stream()))

@@ -84,7 +84,7 @@ int64_t     il_launch_count(il_handle* h);                         /* kernels la
 /* Kernel-selection toggles for A/B measurements and tests (defaults from the IL_* environment variables at il_create):
  * "tc_fuse_l1" (first MLP layer inside the tcgen05 producers), "gail_tiled", "tc_pairs", "thin_hoist". */
 int         il_set_option(il_handle* h, const char* name, int value);
-int         il_struct_sizes(int32_t* out13);                       /* sizeof il_mlp, il_adam, il_batch, il_replay, il_sac_args, il_gail, il_gail_update_args, il_pwil, il_env, il_bc_args, il_eval_args, il_gailx, il_gailx_update_args */
+int         il_struct_sizes(int32_t* out15);                       /* sizeof il_mlp, il_adam, il_batch, il_replay, il_sac_args, il_gail, il_gail_update_args, il_pwil, il_env, il_bc_args, il_eval_args, il_gailx, il_gailx_update_args, il_red, il_red_update_args */
 int         il_mlp_param_offsets(const int32_t* dims, int n_layers, int64_t* w_off, int64_t* b_off, int64_t* total);
 int         il_row_layout(int S, int A, int32_t* offsets8, int32_t* row_len); /* state, action, reward, next_state, terminal, timeout, weight, step */
 
@@ -167,6 +167,47 @@ typedef struct il_bc_args {
 } il_bc_args;
 int64_t il_bc_workspace_bytes(const il_bc_args* a);
 int il_bc_update(il_handle* h, const il_bc_args* a, void* stream);
+
+/* ---- networks with dropout (models.py:48-69 with input_dropout / dropout > 0): DRIL's policy ensemble and RED's predictor -----------
+ * Dropout masks are explicit inputs, pre-scaled {0, 1/(1-p)}: mask_in [R, n, dims[0]] for the input, mask_hid[l] [R, n, dims[l+1]] for hidden
+ * layer l (applied BEFORE the activation, models.py:54-61); NULL = no dropout at that site. il_fill_dropout_mask draws them (Philox). */
+int il_fill_dropout_mask(il_handle* h, float* out, int64_t n, float p, uint64_t seed, uint64_t stream_id, const uint64_t* counter, void* stream);
+int64_t il_actor_dropout_workspace_bytes(const il_mlp* actor, int R, int n);
+/* SoftActor.log_prob(state, action) (models.py:97-99) of a dropout policy; rows of states / given_action are repeated `repeat` times
+ * (torch.repeat_interleave of the 5-member MC-dropout ensemble, models.py:105): n = repeat * source rows. */
+int il_actor_log_prob_dropout(il_handle* h, const il_mlp* actor, int R, int n, int repeat, const float* states, int64_t states_rs, int ld_states, const float* given_action,
+                              const float* mask_in, const float* const* mask_hid, float* log_prob, void* workspace, int64_t workspace_bytes, void* stream);
+/* behavioural_cloning_update (training.py:57-64) of a dropout policy (train.py:120); workspace: il_actor_dropout_workspace_bytes(actor, R, B). */
+int il_bc_update_dropout(il_handle* h, const il_bc_args* a, const float* mask_in, const float* const* mask_hid, void* stream);
+/* DRIL reward (models.py:104-120): reward = +1 where the unbiased variance over the ensemble of exp(log_prob[r, b * ensemble + e]) is <= q, else -1;
+ * variance (optional [R, B]) receives the raw uncertainty (set_uncertainty_threshold takes its quantile). reward may be NULL. */
+int il_dril_reward(il_handle* h, const float* log_prob, int R, int B, int ensemble, const float* q, int q_shared, float* reward, int64_t reward_rs, int reward_ld, float* variance,
+                   void* stream);
+
+/* ---- REDDiscriminator (models.py:252-284) and target_estimation_update (training.py:68-75) ------------------------------------------ */
+typedef struct il_red {
+  il_mlp  predictor;                /* R nets din -> hidden^depth -> din (EmbeddingNetwork, models.py:252-259); trained */
+  il_mlp  target;                   /* R nets, frozen random embedding (models.py:266-268) */
+  float*  sigma;                    /* [R] sigma_1 (models.py:269,277-280) */
+  int32_t state_only, _pad;
+} il_red;
+typedef struct il_red_update_args {
+  il_red   disc;
+  il_adam  opt;                     /* AdamW over the predictor parameters (the frozen target has no gradient: train.py:84 skips it) */
+  il_batch batch;                   /* expert transitions: states, actions, weights */
+  int32_t  R, _pad;
+  const float* mask_in;             /* predictor dropout masks (NULL = none) */
+  const float* mask_hid[IL_MAX_LAYERS];
+  float*   out_loss;                /* [R] (may be NULL) */
+  void*    workspace;               /* il_red_workspace_bytes */
+  int64_t  workspace_bytes;
+} il_red_update_args;
+int64_t il_red_workspace_bytes(const il_red* disc, int R, int B);
+int il_red_update(il_handle* h, const il_red_update_args* a, void* stream);
+/* set_sigma (models.py:277-280): sigma[r] = 1 / median over the B x B pairs of mean((prediction_i - target_j)^2) — in train mode in the reference, hence the masks */
+int il_red_sigma(il_handle* h, const il_red* disc, int R, const il_batch* batch, const float* mask_in, const float* const* mask_hid, void* workspace, int64_t workspace_bytes, void* stream);
+/* predict_reward (models.py:282-284), eval mode */
+int il_red_reward(il_handle* h, const il_red* disc, int R, const il_batch* batch, float* reward, int64_t reward_rs, int reward_ld, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* AdamW step over a flat buffer (used by the fused updates; exposed for tests): torch _single_tensor_adam. */
 int il_adam_step(il_handle* h, float* params, const float* grads, const il_adam* opt, int64_t n, void* stream);

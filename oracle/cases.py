@@ -57,6 +57,10 @@ CASES: Dict[str, dict] = {
   # a7 / a8 / a16 around expert data: ReplayMemory(transitions=...) prefill (memory.py:18-23), transfer_transitions (:46-48), the
   # "never the last row" sampling rule of a pre-filled memory (:22-23, 55) and mix_expert_agent_transitions (models.py:287-290)
   'prefill_mix': dict(kind='mix', S=12, A=3, Ne=40, size=64, extra=9, B=16, seed=91),
+  # RED (models.py:252-284, training.py:68-75) and DRIL (models.py:104-120) with every dropout mask injected
+  'red_dropout': dict(kind='red', S=12, A=3, H=32, depth=2, activation='relu', input_dropout=0.2, dropout=0.3, B=48, steps=3, seed=101, lr=1e-3, wd=0.1, state_only=False),
+  'red_default': dict(kind='red', S=18, A=6, H=32, depth=1, activation='relu', input_dropout=0.0, dropout=0.0, B=64, steps=2, seed=102, lr=3e-5, wd=0.0, state_only=False),
+  'dril_small': dict(kind='dril', S=12, A=3, H=32, depth=1, activation='tanh', input_dropout=0.1, dropout=0.1, B=24, N=40, steps=2, seed=103, lr=1e-3, wd=0.0, quantile=0.9),
   'gmmil_hopper': dict(kind='gmmil', S=12, A=3, B=64, seed=41),
   'gmmil_halfcheetah': dict(kind='gmmil', S=18, A=6, B=256, seed=42),
   'pwil_small': dict(kind='pwil', S=12, A=3, N=150, T=40, steps=100, seed=51),
@@ -149,6 +153,36 @@ def make_inputs(name: str, seed_offset: int = 0) -> Dict[str, np.ndarray]:
         for l in range(len(sizes) - 1):
           inp[f'{net}u_{l}'] = rs.standard_normal(sizes[l + 1]).astype(np.float32)
           inp[f'{net}v_{l}'] = rs.standard_normal(sizes[l]).astype(np.float32)
+  elif k in ('red', 'dril'):
+    S, A, H = c['S'], c['A'], c['H']
+    def mask(shape, p): return ((rs.uniform(size=shape) >= p) / (1.0 - p)).astype(np.float32) if p > 0 else None
+    def masks(prefix, n, din):
+      m = mask((n, din), c['input_dropout'])
+      if m is not None: inp[f'{prefix}_in'] = m
+      for l in range(c['depth']):
+        m = mask((n, H), c['dropout'])
+        if m is not None: inp[f'{prefix}_h{l}'] = m
+    if k == 'red':
+      din = S if c['state_only'] else S + A
+      sizes = [din] + [H] * c['depth'] + [din]
+      for i, w in enumerate(_mlp_weights(rs, sizes)): inp[f'predictor_{i}'] = w
+      for i, w in enumerate(_mlp_weights(rs, sizes)): inp[f'target_{i}'] = w
+      for s_ in range(c['steps']):
+        for key, v in _batch(rs, c['B'], S, A).items(): inp[f'b{s_}_{key}'] = v
+        masks(f'm{s_}', c['B'], din)
+      for key, v in _batch(rs, c['B'], S, A).items(): inp[f'sig_{key}'] = v
+      masks('msig', c['B'], din)
+      for key, v in _batch(rs, c['B'], S, A).items(): inp[f'p_{key}'] = v
+    else:
+      for i, w in enumerate(_mlp_weights(rs, [S] + [H] * c['depth'] + [2 * A])): inp[f'actor_{i}'] = w
+      for s_ in range(c['steps']):
+        for key, v in _batch(rs, c['B'], S, A).items(): inp[f'b{s_}_{key}'] = v
+        masks(f'm{s_}', c['B'], S)
+      inp['expert_states'] = rs.standard_normal((c['N'], S)).astype(np.float32)
+      inp['expert_actions'] = np.tanh(rs.standard_normal((c['N'], A))).astype(np.float32)
+      masks('mthr', c['N'] * 5, S)
+      for key, v in _batch(rs, c['B'], S, A).items(): inp[f'p_{key}'] = v
+      masks('mrew', c['B'] * 5, S)
   elif k == 'ingest':
     N = c['N']
     inp['observations'] = rs.standard_normal((N, c['obs'])).astype(np.float32)
@@ -204,6 +238,26 @@ def _np(x): return x.detach().cpu().numpy().copy() if isinstance(x, torch.Tensor
 # ----------------------------------------------------------------------------------------------------------
 def _batch_from(inp, prefix) -> Dict[str, torch.Tensor]:
   return {key[len(prefix):]: _t(v) for key, v in inp.items() if key.startswith(prefix) and not key[len(prefix):].startswith('eps')}
+
+
+def _mask_list(inp, prefix, c):
+  """Injected dropout masks of one forward pass in consumption order: input mask (if input_dropout > 0), then one per hidden layer (if dropout > 0)."""
+  out = []
+  if c['input_dropout'] > 0: out.append(_t(inp[f'{prefix}_in']))
+  if c['dropout'] > 0: out += [_t(inp[f'{prefix}_h{l}']) for l in range(c['depth'])]
+  return out
+
+
+@contextlib.contextmanager
+def injected_dropout(masks: List[torch.Tensor]):
+  """nn.Dropout -> F.dropout consumes the case's pre-scaled masks (in call order) instead of torch's RNG; the reference source is untouched."""
+  import torch.nn.functional as Fn
+  saved = Fn.dropout
+  Fn.dropout = lambda x, p=0.5, training=True, inplace=False: (x * masks.pop(0)) if (training and p > 0) else x
+  try:
+    yield
+  finally:
+    Fn.dropout = saved
 
 
 def run_port(name: str, inp: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
@@ -278,6 +332,37 @@ def run_port(name: str, inp: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
         out[f'adam_{net}_m_{i}'], out[f'adam_{net}_v_{i}'] = _np(opt.state[p]['exp_avg']), _np(opt.state[p]['exp_avg_sq'])
       if bufs is not None:
         for l, (u, v) in enumerate(bufs): out[f'{net}u_{l}'], out[f'{net}v_{l}'] = _np(u), _np(v)
+  elif k == 'red':
+    n = 2 * (c['depth'] + 1)
+    disc = port.RedDiscriminator([_t(inp[f'predictor_{i}']) for i in range(n)], [_t(inp[f'target_{i}']) for i in range(n)], c['state_only'], c['activation'], c['input_dropout'], c['dropout'])
+    opt = torch.optim.AdamW(disc.parameters(), lr=c['lr'], weight_decay=c['wd'])
+    for s in range(c['steps']): out[f's{s}_loss'] = _np(port.target_estimation_update(disc, opt, _batch_from(inp, f'b{s}_'), _mask_list(inp, f'm{s}', c)))
+    sb = _batch_from(inp, 'sig_')
+    with torch.no_grad():
+      disc.set_sigma(sb['states'], sb['actions'], _mask_list(inp, 'msig', c))
+      disc.training = False
+      pb = _batch_from(inp, 'p_')
+      out['reward'] = _np(disc.predict_reward(pb['states'], pb['actions']))
+    out['sigma'] = np.float32([disc.sigma_1])
+    for i, p_ in enumerate(disc.predictor):
+      out[f'predictor_{i}'] = _np(p_)
+      out[f'adam_m_{i}'], out[f'adam_v_{i}'] = _np(opt.state[p_]['exp_avg']), _np(opt.state[p_]['exp_avg_sq'])
+  elif k == 'dril':
+    n = 2 * (c['depth'] + 1)
+    actor = [torch.nn.Parameter(_t(inp[f'actor_{i}']).clone()) for i in range(n)]
+    opt = torch.optim.AdamW(actor, lr=c['lr'], weight_decay=c['wd'])
+    dk = dict(input_dropout=c['input_dropout'], dropout=c['dropout'])
+    for s in range(c['steps']): out[f's{s}_loss'] = _np(port.behavioural_cloning_update(actor, opt, _batch_from(inp, f'b{s}_'), c['activation'], masks=_mask_list(inp, f'm{s}', c), **dk))
+    with torch.no_grad():
+      es, ea, pb = _t(inp['expert_states']), _t(inp['expert_actions']), _batch_from(inp, 'p_')
+      out['expert_variance'] = _np(port.dril_action_uncertainty(actor, es, ea, c['activation'], c['input_dropout'], c['dropout'], _mask_list(inp, 'mthr', c)))
+      q = port.dril_uncertainty_threshold(actor, es, ea, c['quantile'], c['activation'], c['input_dropout'], c['dropout'], _mask_list(inp, 'mthr', c))
+      out['q'] = np.float32([q])
+      out['variance'] = _np(port.dril_action_uncertainty(actor, pb['states'], pb['actions'], c['activation'], c['input_dropout'], c['dropout'], _mask_list(inp, 'mrew', c)))
+      out['reward'] = _np(port.dril_predict_reward(actor, q, pb['states'], pb['actions'], c['activation'], c['input_dropout'], c['dropout'], _mask_list(inp, 'mrew', c)))
+    for i, p_ in enumerate(actor):
+      out[f'actor_{i}'] = _np(p_)
+      out[f'adam_m_{i}'], out[f'adam_v_{i}'] = _np(opt.state[p_]['exp_avg']), _np(opt.state[p_]['exp_avg_sq'])
   elif k == 'ingest':
     raw = {key: _t(inp[key]) for key in ('observations', 'next_observations', 'actions', 'terminals', 'timeouts')}
     tr = port.build_expert_transitions(raw, c['trajectories'], c['subsample'], c['absorbing'], rng=np.random.RandomState(int(inp['np_seed'][0])))
@@ -496,6 +581,48 @@ def run_reference(name: str, inp: Dict[str, np.ndarray]) -> Dict[str, np.ndarray
         out[f'adam_{net}_m_{i}'], out[f'adam_{net}_v_{i}'] = _np(opt.state[p]['exp_avg']), _np(opt.state[p]['exp_avg_sq'])
       if c['spectral_norm']:
         for l, lin in enumerate(nets[net]): out[f'{net}u_{l}'], out[f'{net}v_{l}'] = _np(lin.parametrizations.weight[0]._u), _np(lin.parametrizations.weight[0]._v)
+  elif k == 'red':
+    S, A = c['S'], c['A']
+    icfg = DC(state_only=c['state_only'], reward_bandwidth_scale=None,
+              discriminator=DC(hidden_size=c['H'], depth=c['depth'], activation=c['activation'], input_dropout=c['input_dropout'], dropout=c['dropout']))
+    disc = ref.models.REDDiscriminator(S, A, icfg)
+    n = 2 * (c['depth'] + 1)
+    _load_mlp(disc.predictor.embedding, [inp[f'predictor_{i}'] for i in range(n)])
+    _load_mlp(disc.target.embedding, [inp[f'target_{i}'] for i in range(n)])
+    opt = torch.optim.AdamW(disc.parameters(), lr=c['lr'], weight_decay=c['wd'])
+    for s in range(c['steps']):
+      with injected_dropout(_mask_list(inp, f'm{s}', c)):
+        ref.training.target_estimation_update(disc, _batch_from(inp, f'b{s}_'), opt)
+    sb, pb = _batch_from(inp, 'sig_'), _batch_from(inp, 'p_')
+    with torch.inference_mode(), injected_dropout(_mask_list(inp, 'msig', c)):
+      disc.set_sigma(sb['states'], sb['actions'])  # train mode here (train.py:129 runs before :147)
+    disc.eval()
+    with torch.inference_mode(): out['reward'] = _np(disc.predict_reward(pb['states'], pb['actions']))
+    out['sigma'] = np.float32([disc.sigma_1])
+    plist = [p_ for m in disc.predictor.embedding if isinstance(m, torch.nn.Linear) for p_ in (m.weight, m.bias)]
+    for i, p_ in enumerate(plist):
+      out[f'predictor_{i}'] = _np(p_)
+      out[f'adam_m_{i}'], out[f'adam_v_{i}'] = _np(opt.state[p_]['exp_avg']), _np(opt.state[p_]['exp_avg_sq'])
+  elif k == 'dril':
+    S, A = c['S'], c['A']
+    actor = ref.models.SoftActor(S, A, DC(hidden_size=c['H'], depth=c['depth'], activation=c['activation'], input_dropout=c['input_dropout'], dropout=c['dropout']))
+    n = 2 * (c['depth'] + 1)
+    _load_mlp(actor.actor, [inp[f'actor_{i}'] for i in range(n)])
+    opt = torch.optim.AdamW(actor.parameters(), lr=c['lr'], weight_decay=c['wd'])
+    for s in range(c['steps']):
+      with injected_dropout(_mask_list(inp, f'm{s}', c)):
+        ref.training.behavioural_cloning_update(actor, _batch_from(inp, f'b{s}_'), opt)
+    es, ea, pb = _t(inp['expert_states']), _t(inp['expert_actions']), _batch_from(inp, 'p_')
+    with torch.inference_mode():
+      with injected_dropout(_mask_list(inp, 'mthr', c)): out['expert_variance'] = _np(actor._get_action_uncertainty(es, ea))
+      with injected_dropout(_mask_list(inp, 'mthr', c)): actor.set_uncertainty_threshold(es, ea, c['quantile'])
+      out['q'] = np.float32([actor.q])
+      with injected_dropout(_mask_list(inp, 'mrew', c)): out['variance'] = _np(actor._get_action_uncertainty(pb['states'], pb['actions']))
+      with injected_dropout(_mask_list(inp, 'mrew', c)): out['reward'] = _np(actor.predict_reward(pb['states'], pb['actions']))
+    plist = [p_ for m in actor.actor if isinstance(m, torch.nn.Linear) for p_ in (m.weight, m.bias)]
+    for i, p_ in enumerate(plist):
+      out[f'actor_{i}'] = _np(p_)
+      out[f'adam_m_{i}'], out[f'adam_v_{i}'] = _np(opt.state[p_]['exp_avg']), _np(opt.state[p_]['exp_avg_sq'])
   elif k == 'ingest':
     import types
     D4RLEnv = ref.evaluation.D4RLEnv  # evaluation.py:6 imports it from environments.py (gym / d4rl stubbed)

@@ -49,7 +49,8 @@ class OracleLoop:
     tt = (-0.5 if gail else -1.0) if target_temperature is None else target_temperature  # GAIL.yaml:6 / train_config.yaml:37
     self.im = dict(hidden_size=64, learning_rate=3e-5, weight_decay=10.0, grad_penalty=1.0, spectral_norm=True, entropy_bonus=0.0, loss_function='BCE', reward_function='AIRL',
                    mixup_alpha=1.0, pos_class_prior=0.7, nonnegative_margin=float('inf'), reward_scale=5.0, reward_bandwidth_scale=5.0,
-                   depth=1, activation='relu', reward_shaping=False, subtract_log_policy=False, state_only=False, update_freq=1250, balanced=True)  # GAIL.yaml:8-27, PWIL.yaml:4-6, AdRIL.yaml:9-10, train_config.yaml:45
+                   depth=1, activation='relu', reward_shaping=False, subtract_log_policy=False, state_only=False, update_freq=1250, balanced=True,
+                   input_dropout=0.0, dropout=0.0, pretraining_iterations=0, quantile_cutoff=0.98, red_sigma=None)  # GAIL.yaml:8-27, PWIL.yaml:4-6, AdRIL.yaml:9-10, RED.yaml / DRIL.yaml, train_config.yaml:45
     self.im.update(imitation or {})
     np.random.seed(seed)
     torch.manual_seed(seed)  # train.py:51-52
@@ -100,6 +101,18 @@ class OracleLoop:
       self.disc = port.GailDiscriminator(g, sn if im['spectral_norm'] else None, self.discount, activation=im['activation'], reward_function=im['reward_function'],
                                          state_only=im['state_only'], subtract_log_policy=im['subtract_log_policy'], h=h, h_sn=h_sn if im['spectral_norm'] else None)
       self.disc_opt = torch.optim.AdamW(self.disc.parameters(), lr=self.im['learning_rate'], weight_decay=self.im['weight_decay'])  # train.py:84
+    elif algorithm in ('DRIL', 'RED'):
+      im = self.im
+      din = S if im['state_only'] else S + A
+      if algorithm == 'DRIL':  # train.py:74: SoftActor(state_size, action_size, cfg.imitation.discriminator) — a dropout policy
+        self.disc = [torch.nn.Parameter(p) for p in port.init_mlp([S] + [im['hidden_size']] * im['depth'] + [2 * A], im['activation'])]
+        params = self.disc
+      else:  # train.py:82: predictor then target EmbeddingNetwork (models.py:265-266)
+        sizes = [din] + [im['hidden_size']] * im['depth'] + [din]
+        self.disc = port.RedDiscriminator(port.init_mlp(sizes, im['activation']), port.init_mlp(sizes, im['activation']), im['state_only'], im['activation'], im['input_dropout'], im['dropout'],
+                                          im['red_sigma'])
+        params = self.disc.parameters()
+      self.disc_opt = torch.optim.AdamW(params, lr=im['learning_rate'], weight_decay=im['weight_decay'])  # train.py:84
     elif algorithm == 'AdRIL':
       assert mix_expert_data == 'mixed_batch'  # train.py:36
       self.disc = port.RewardRelabeller(self.im['update_freq'], self.im['balanced'])  # train.py:72
@@ -115,6 +128,7 @@ class OracleLoop:
           d['rewards'][i] = self.disc.compute_reward(d['states'][i].unsqueeze(0), d['actions'][i].unsqueeze(0))
           if d['terminals'][i] or d['timeouts'][i]: self.disc.reset()
     if algorithm in ('PWIL', 'GMMIL') and mix_expert_data == 'prefill_memory': self.memory.transfer_transitions(self.expert_memory)  # train.py:141,143
+    self._pretrained = algorithm not in ('DRIL', 'RED')  # DRIL / RED: call pretrain_discriminator() before the first run_step (train.py:117-133)
     self.t, self.train_return, self.step = 0, 0.0, 0
     self.state = self.env.reset(self.noise.reset_u())  # train.py:146
     self.episode_returns = []
@@ -128,6 +142,7 @@ class OracleLoop:
 
   def run_step(self):
     """One iteration of train.py:149-211."""
+    assert self._pretrained, 'DRIL / RED: call pretrain_discriminator() first (train.py:117-133)'
     self.step += 1
     step, env, agent = self.step, self.env, self.agent
     with torch.inference_mode():  # train.py:151-158
@@ -167,6 +182,13 @@ class OracleLoop:
             rewards = self.disc.predict_reward(transitions['states'], transitions['actions'], transitions['next_states'], transitions['terminals'], lp)
           else: rewards = self.disc.predict_reward(transitions['states'], transitions['actions'], expert['states'], expert['actions'], transitions['weights'], expert['weights'])
         transitions['rewards'] = rewards.clone()
+      if self.algorithm in ('DRIL', 'RED'):  # train.py:183,190-191,196-197
+        if self.mix == 'mixed_batch': port.mix_expert_agent_transitions(transitions, expert)
+        im = self.im
+        with torch.inference_mode():
+          if self.algorithm == 'DRIL': rewards = port.dril_predict_reward(self.disc, self.dril_q, transitions['states'], transitions['actions'], im['activation'], im['input_dropout'], im['dropout'])
+          else: rewards = self.disc.predict_reward(transitions['states'], transitions['actions'])
+        transitions['rewards'] = rewards.clone()
       if self.algorithm == 'AdRIL':  # train.py:188-189 (mix_expert_agent_transitions of :183 is skipped for AdRIL)
         with torch.inference_mode():
           self.disc.resample_and_relabel(transitions, expert, step, self.memory.num_trajectories, self.expert_memory.num_trajectories)
@@ -191,6 +213,32 @@ class OracleLoop:
         batch = {k: self.expert_memory.data[k][idx] for k in port.FIELDS}
         port.behavioural_cloning_update(self.agent.actor, opt, batch)
         done += 1
+
+  def pretrain_discriminator(self, batches=None):
+    """train.py:117-133: DRIL's dropout policy ensemble is behaviour-cloned / RED's predictor is regressed onto its random target on shuffled expert minibatches
+    (same DataLoader stream as bc_pretrain), then the uncertainty threshold / kernel bandwidth is fixed and (optionally) the expert data pre-fills the replay.
+    `batches` (tests): the minibatch index lists, instead of the DataLoader's shuffles."""
+    im, n, B, done = self.im, self.expert_memory.size, self.B, 0
+    drop = dict(input_dropout=im['input_dropout'], dropout=im['dropout'], training=True)
+    while done < im['pretraining_iterations']:
+      if batches is None:
+        torch.empty((), dtype=torch.int64).random_()
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())
+        perm = torch.randperm(n, generator=torch.Generator().manual_seed(seed)).tolist()
+      for b in range(n // B if batches is None else len(batches)):
+        if done == im['pretraining_iterations']: break
+        idx = perm[b * B:(b + 1) * B] if batches is None else list(batches[b])
+        batch = {k: self.expert_memory.data[k][idx] for k in port.FIELDS}
+        if self.algorithm == 'DRIL': port.behavioural_cloning_update(self.disc, self.disc_opt, batch, im['activation'], **drop)
+        else: port.target_estimation_update(self.disc, self.disc_opt, batch)
+        done += 1
+    d = self.expert_memory.data
+    with torch.inference_mode():
+      if self.algorithm == 'DRIL': self.dril_q = port.dril_uncertainty_threshold(self.disc, d['states'], d['actions'], im['quantile_cutoff'], im['activation'], im['input_dropout'], im['dropout'])
+      else: self.disc.set_sigma(d['states'][:B], d['actions'][:B])
+    if self.mix == 'prefill_memory': self.memory.transfer_transitions(self.expert_memory)  # train.py:133
+    if self.algorithm == 'RED': self.disc.training = False  # train.py:147
+    self._pretrained = True
 
   def prefill(self, n: int):
     """Runs the warm-up phase of train.py:171 (`training.start` env steps without updates)."""

@@ -36,12 +36,20 @@ def _act(x: Tensor, activation: str) -> Tensor:
   raise ValueError(activation)
 
 
-def mlp_forward(params: Sequence[Tensor], x: Tensor, activation: str = 'relu') -> Tensor:
-  """models.py:48-69 (`_create_fcnn` as an nn.Sequential): hidden layers with activation, linear head."""
+def mlp_forward(params: Sequence[Tensor], x: Tensor, activation: str = 'relu', input_dropout: float = 0.0, dropout: float = 0.0, training: bool = False,
+                masks: Optional[List[Tensor]] = None) -> Tensor:
+  """models.py:48-69 (`_create_fcnn` as an nn.Sequential): [Dropout(input_dropout)], then per hidden layer Linear -> [Dropout(dropout)] -> activation,
+  then the linear head. Train-mode dropout draws its masks with torch's own F.dropout (the reference's RNG consumption); `masks` (a list consumed
+  front to back of pre-scaled {0, 1/(1-p)} tensors) injects them instead — used for the CUDA parity cases."""
   n_layers = len(params) // 2
+  active = training or masks is not None
+  def drop(t, p):
+    if p <= 0 or not active: return t
+    return t * masks.pop(0) if masks is not None else F.dropout(t, p, True)
+  x = drop(x, input_dropout)
   for l in range(n_layers):
     x = F.linear(x, params[2 * l], params[2 * l + 1])
-    if l < n_layers - 1: x = _act(x, activation)
+    if l < n_layers - 1: x = _act(drop(x, dropout), activation)
   return x
 
 
@@ -60,9 +68,9 @@ def init_mlp(sizes: Sequence[int], activation: str = 'relu', final_gain: float =
 # ----------------------------------------------------------------------------------------------------------
 # Soft actor (models.py:84-102) and the tanh-Gaussian policy (torch TransformedDistribution semantics)
 # ----------------------------------------------------------------------------------------------------------
-def actor_mean_logstd(actor: Sequence[Tensor], state: Tensor, activation: str = 'relu') -> Tuple[Tensor, Tensor]:
-  """models.py:90-92: chunk the head into mean / log-std, clamp log-std to [-20, 2]."""
-  mean, log_std = mlp_forward(actor, state, activation).chunk(2, dim=1)
+def actor_mean_logstd(actor: Sequence[Tensor], state: Tensor, activation: str = 'relu', **drop) -> Tuple[Tensor, Tensor]:
+  """models.py:90-92: chunk the head into mean / log-std, clamp log-std to [-20, 2]. `drop`: the dropout arguments of mlp_forward (DRIL, models.py:88)."""
+  mean, log_std = mlp_forward(actor, state, activation, **drop).chunk(2, dim=1)
   return mean, torch.clamp(log_std, min=LOG_STD_MIN, max=LOG_STD_MAX)
 
 
@@ -81,10 +89,10 @@ def tanh_gaussian_logprob_from_pre_tanh(mean: Tensor, log_std: Tensor, x: Tensor
   return (0.0 - ladj.sum(dim=-1)) + normal_lp.sum(dim=-1)
 
 
-def actor_log_prob(actor: Sequence[Tensor], state: Tensor, action: Tensor, activation: str = 'relu') -> Tensor:
+def actor_log_prob(actor: Sequence[Tensor], state: Tensor, action: Tensor, activation: str = 'relu', **drop) -> Tensor:
   """models.py:97-99: clamp the action into (-1, 1), invert tanh (atanh), evaluate the density."""
   action = action.clamp(-1 + 1e-6, 1 - 1e-6)
-  mean, log_std = actor_mean_logstd(actor, state, activation)
+  mean, log_std = actor_mean_logstd(actor, state, activation, **drop)
   return tanh_gaussian_logprob_from_pre_tanh(mean, log_std, torch.atanh(action))
 
 
@@ -178,11 +186,11 @@ def sac_update(agent: SacAgent, batch: Dict[str, Tensor], eps_next: Tensor, eps_
               policy_loss=policy_loss.detach(), temperature_loss=temperature_loss.detach(), target_values=target_values)
 
 
-def behavioural_cloning_update(actor_params: Sequence[torch.nn.Parameter], optimiser, expert: Dict[str, Tensor], activation: str = 'relu') -> Tensor:
-  """training.py:57-64."""
+def behavioural_cloning_update(actor_params: Sequence[torch.nn.Parameter], optimiser, expert: Dict[str, Tensor], activation: str = 'relu', **drop) -> Tensor:
+  """training.py:57-64 (`drop`: dropout arguments when the "actor" is DRIL's dropout policy ensemble, train.py:120)."""
   expert_action = expert['actions'].clamp(min=-1 + 1e-6, max=1 - 1e-6)
   optimiser.zero_grad(set_to_none=True)
-  loss = (expert['weights'] * -actor_log_prob(actor_params, expert['states'], expert_action, activation)).mean()
+  loss = (expert['weights'] * -actor_log_prob(actor_params, expert['states'], expert_action, activation, **drop)).mean()
   loss.backward()
   optimiser.step()
   return loss.detach()
@@ -324,6 +332,73 @@ def gail_update(disc: GailDiscriminator, optimiser, policy: Dict[str, Tensor], e
   optimiser.step()  # :134
   disc.training = False  # train.py:180
   return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# DRIL (models.py:104-120): the "discriminator" is a dropout policy trained by behavioural cloning; reward = agreement of a 5-member MC-dropout ensemble
+# ----------------------------------------------------------------------------------------------------------
+DRIL_ENSEMBLE = 5  # models.py:105
+
+
+def dril_action_uncertainty(policy: Sequence[Tensor], state: Tensor, action: Tensor, activation: str, input_dropout: float, dropout: float, masks: Optional[List[Tensor]] = None) -> Tensor:
+  """models.py:104-107: variance over the ensemble of pi(a|s) under independent dropout masks (always train mode: train.py:147 leaves DRIL's policy in train())."""
+  state, action = torch.repeat_interleave(state, DRIL_ENSEMBLE, dim=0), torch.repeat_interleave(action, DRIL_ENSEMBLE, dim=0)
+  prob = actor_log_prob(policy, state, action, activation, input_dropout=input_dropout, dropout=dropout, training=True, masks=masks).exp()
+  return prob.view(-1, DRIL_ENSEMBLE).var(dim=1)
+
+
+def dril_uncertainty_threshold(policy, expert_state, expert_action, quantile_cutoff: float, activation: str, input_dropout: float, dropout: float, masks=None) -> float:
+  """models.py:110-111."""
+  return torch.quantile(dril_action_uncertainty(policy, expert_state, expert_action, activation, input_dropout, dropout, masks), quantile_cutoff).item()
+
+
+def dril_predict_reward(policy, q: float, state, action, activation: str, input_dropout: float, dropout: float, masks=None) -> Tensor:
+  """models.py:113-120: +1 where the ensemble variance is at most the threshold, -1 elsewhere."""
+  cost = dril_action_uncertainty(policy, state, action, activation, input_dropout, dropout, masks)
+  neg = cost.less_equal(q)
+  cost[neg], cost[~neg] = -1, 1
+  return -cost
+
+
+# ----------------------------------------------------------------------------------------------------------
+# RED (models.py:252-284, training.py:68-75): random network distillation on the expert data
+# ----------------------------------------------------------------------------------------------------------
+class RedDiscriminator:
+  def __init__(self, predictor: Sequence[Tensor], target: Sequence[Tensor], state_only: bool = False, activation: str = 'relu', input_dropout: float = 0.0, dropout: float = 0.0,
+               sigma_1: Optional[float] = None):
+    self.predictor = [torch.nn.Parameter(p.detach().clone().float()) for p in predictor]
+    self.target = [p.detach().clone().float() for p in target]  # requires_grad = False (models.py:267-268)
+    self.state_only, self.activation, self.input_dropout, self.dropout, self.sigma_1 = state_only, activation, input_dropout, dropout, sigma_1
+    self.training = True  # nn.Module default; train.py:147 switches RED to eval() before the loop
+
+  def parameters(self): return list(self.predictor)
+
+  def forward(self, state: Tensor, action: Tensor, masks: Optional[List[Tensor]] = None) -> Tuple[Tensor, Tensor]:
+    """models.py:271-274 (dropout only in the predictor, models.py:265-266)."""
+    x = state if self.state_only else torch.cat([state, action], dim=1)
+    prediction = mlp_forward(self.predictor, x, self.activation, self.input_dropout, self.dropout, self.training, masks)
+    return prediction, mlp_forward(self.target, x, self.activation)
+
+  def set_sigma(self, expert_state: Tensor, expert_action: Tensor, masks=None):
+    """models.py:277-280: kernel median heuristic on one minibatch (the module is still in train mode here: dropout is active)."""
+    if not self.sigma_1:
+      prediction, target = self.forward(expert_state, expert_action, masks)
+      self.sigma_1 = 1 / squared_distance_mean(prediction, target).median().item()
+
+  def predict_reward(self, state: Tensor, action: Tensor) -> Tensor:
+    """models.py:282-284."""
+    prediction, target = self.forward(state, action)
+    return torch.exp(-self.sigma_1 * (prediction - target).pow(2).mean(dim=1))
+
+
+def target_estimation_update(disc: RedDiscriminator, optimiser, expert: Dict[str, Tensor], masks=None) -> Tensor:
+  """training.py:68-75."""
+  optimiser.zero_grad(set_to_none=True)
+  prediction, target = disc.forward(expert['states'], expert['actions'], masks)
+  loss = (expert['weights'] * (prediction - target).pow(2).mean(dim=1)).mean()
+  loss.backward()
+  optimiser.step()
+  return loss.detach()
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -179,6 +179,49 @@ def run_cuda(name, inps):
             od, idim = mlp.dims[l + 1], mlp.dims[l]
             outs[r][f'{name}u_{l}'], outs[r][f'{name}v_{l}'] = _np(getattr(disc, un)[r, uo:uo + od]), _np(getattr(disc, vn)[r, vo:vo + idim])
             uo, vo = uo + od, vo + idim
+  elif k in ('red', 'dril'):  # the dropout MLP program (csrc/dropout_nets.cu) with every mask injected
+    S, A, H, depth = c['S'], c['A'], c['H'], c['depth']
+    n = 2 * (depth + 1)
+    dcfg = Cfg(hidden_size=H, depth=depth, activation=c['activation'], input_dropout=c['input_dropout'], dropout=c['dropout'])
+    def masks(prefix):
+      out = [_stack(inps, f'{prefix}_in') if c['input_dropout'] > 0 else None]
+      return out + [_stack(inps, f'{prefix}_h{l}') if c['dropout'] > 0 else None for l in range(depth)]
+    if k == 'red':
+      disc = il_b200.REDDiscriminator(S, A, Cfg(state_only=c['state_only'], reward_bandwidth_scale=None, discriminator=dcfg), replicas=R)
+      _load_mlp(disc.predictor, inps, 'predictor', 0, n)
+      _load_mlp(disc.target, inps, 'target', 0, n)
+      opt = il_b200.AdamW(disc.parameters(), lr=c['lr'], weight_decay=c['wd'])
+      for s in range(c['steps']):
+        loss = torch.empty(R, device=DEV)
+        il_b200.target_estimation_update(disc, _batch(inps, f'b{s}_', S, A, absorbing=False), opt, out_loss=loss, masks=masks(f'm{s}'))
+        for r in range(R): outs[r][f's{s}_loss'] = _np(loss[r])
+      disc.set_sigma_batch(_batch(inps, 'sig_', S, A, absorbing=False), masks=masks('msig'))
+      disc.eval()
+      rew = disc.predict_reward_batch(_batch(inps, 'p_', S, A, absorbing=False))
+      for r in range(R):
+        outs[r]['reward'], outs[r]['sigma'] = _np(rew[r]), _np(disc.sigma[r:r + 1])
+        _export(disc.predictor, r, 0, 'predictor', outs[r])
+        _export(disc.predictor, r, 0, 'adam_m', outs[r], opt.exp_avg)
+        _export(disc.predictor, r, 0, 'adam_v', outs[r], opt.exp_avg_sq)
+    else:
+      actor = il_b200.SoftActor(S, A, dcfg, replicas=R)
+      _load_mlp(actor.mlp, inps, 'actor', 0, n)
+      opt = il_b200.AdamW(actor.parameters(), lr=c['lr'], weight_decay=c['wd'])
+      for s in range(c['steps']):
+        loss = torch.empty(R, device=DEV)
+        il_b200.behavioural_cloning_update(actor, _batch(inps, f'b{s}_', S, A, absorbing=False), opt, out_loss=loss, masks=masks(f'm{s}'))
+        for r in range(R): outs[r][f's{s}_loss'] = _np(loss[r])
+      es, ea = _stack(inps, 'expert_states'), _stack(inps, 'expert_actions')
+      ps, pa = _stack(inps, 'p_states'), _stack(inps, 'p_actions')
+      ev = actor._get_action_uncertainty(es, ea, masks=masks('mthr')).reshape(R, -1)
+      actor.set_uncertainty_threshold(es, ea, c['quantile'], masks=masks('mthr'))
+      var = actor._get_action_uncertainty(ps, pa, masks=masks('mrew')).reshape(R, -1)
+      rew = actor.predict_reward(ps, pa, masks=masks('mrew')).reshape(R, -1)
+      for r in range(R):
+        outs[r].update(expert_variance=_np(ev[r]), q=_np(actor._q[r:r + 1]), variance=_np(var[r]), reward=_np(rew[r]))
+        _export(actor.mlp, r, 0, 'actor', outs[r])
+        _export(actor.mlp, r, 0, 'adam_m', outs[r], opt.exp_avg)
+        _export(actor.mlp, r, 0, 'adam_v', outs[r], opt.exp_avg_sq)
   elif k == 'gmmil':
     S, A = c['S'], c['A']
     d = il_b200.GMMILDiscriminator(S, A, Cfg(state_only=False), replicas=R)

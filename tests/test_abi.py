@@ -28,9 +28,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_sizes_match_c():
-  out = (C.c_int32 * 13)()
+  out = (C.c_int32 * 15)()
   assert _lib.lib().il_struct_sizes(out) == 0
-  py = [C.sizeof(x) for x in (_lib.Mlp, _lib.Adam, _lib.Batch, _lib.Replay, _lib.SacArgs, _lib.Gail, _lib.GailUpdateArgs, _lib.Pwil, _lib.Env, _lib.BcArgs, _lib.EvalArgs, _lib.Gailx, _lib.GailxUpdateArgs)]
+  py = [C.sizeof(x) for x in (_lib.Mlp, _lib.Adam, _lib.Batch, _lib.Replay, _lib.SacArgs, _lib.Gail, _lib.GailUpdateArgs, _lib.Pwil, _lib.Env, _lib.BcArgs, _lib.EvalArgs, _lib.Gailx, _lib.GailxUpdateArgs, _lib.Red, _lib.RedUpdateArgs)]
   assert list(out) == py
 
 

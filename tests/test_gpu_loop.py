@@ -157,3 +157,100 @@ def test_loop_adril_sqil_matches_oracle(extra, imitation):
   assert err.get('q', 0) < 5e-3, err
   assert err.get('reward', 0) < 1e-6, err
   assert err['actor'] < 5e-4, err
+
+
+def _mask(rs, shape, p): return ((rs.uniform(size=shape) >= p) / (1.0 - p)).astype(np.float32)
+
+
+@pytest.mark.parametrize('algorithm', ['DRIL', 'RED'])
+def test_dropout_discriminator_loops_match_oracle(algorithm):
+  """SURVEY §8f row 4 inside the loop (train.py:117-133 pre-training, :190-191 / :196-197 relabelling): DRIL's dropout policy ensemble and RED's predictor are
+  pre-trained on injected expert minibatches with injected dropout masks, the threshold / bandwidth is fixed, then 40 loop steps (10 updates) with the reward of
+  every sampled batch coming from the pre-trained network — all on csrc/dropout_nets.cu, against the oracle loop (pinned to the reference's train())."""
+  from il_b200.config import load_config
+  from il_b200.train import Trainer
+  from oracle import cases, loop as oloop
+  R, B, H, steps, start, iters = 2, 32, 64, 40, 30, 6
+  p_in, p_h = (0.1, 0.1) if algorithm == 'DRIL' else (0.2, 0.3)
+  dH = 32
+  extra = [f'imitation.discriminator.hidden_size={dH}', f'imitation.discriminator.input_dropout={p_in}', f'imitation.discriminator.dropout={p_h}', f'imitation.pretraining.iterations={iters}',
+           'imitation.learning_rate=0.001']
+  cfg = load_config([f'algorithm={algorithm}', 'env=hopper', f'steps={steps}', f'training.start={start}', f'training.batch_size={B}', 'imitation.trajectories=2',
+                     f'reinforcement.actor.hidden_size={H}', f'reinforcement.critic.hidden_size={H}', 'cuda_graphs=false', 'gemm_mode=fp32', f'replicas={R}', 'seed=3', *extra])
+  tr = Trainer(cfg, replicas=R)
+  tr.inject = True
+  rs = np.random.RandomState(321)
+  S, A, obs = tr.S, tr.A, tr.env.obs
+  din = S if algorithm == 'DRIL' else S + A
+  expert_raw = tr.env.synthesize_raw_dataset(5)
+  im = dict(hidden_size=dH, input_dropout=p_in, dropout=p_h, pretraining_iterations=iters, learning_rate=1e-3, weight_decay=cfg.imitation.weight_decay,
+            depth=cfg.imitation.discriminator.depth, activation=cfg.imitation.discriminator.activation)
+  if algorithm == 'DRIL': im['quantile_cutoff'] = cfg.imitation.quantile_cutoff
+  loops = []
+  for r in range(R):
+    init = dict(actor=tr.actor.mlp.export_params(r, 0), twin=[tr.critic.mlp.export_params(r, 0), tr.critic.mlp.export_params(r, 1)])
+    lp = oloop.OracleLoop(algorithm, 'hopper', seed=3 + r, batch_size=B, start=start, memory_size=cfg.memory.size, hidden_size=H, trajectories=2, expert_raw=expert_raw, init=init,
+                          mix_expert_data=cfg.imitation.mix_expert_data, imitation=im)
+    d = tr.discriminator
+    if algorithm == 'DRIL':
+      for P_, src in zip(lp.disc, d.mlp.export_params(r, 0)): P_.data.copy_(src)
+    else:
+      for P_, src in zip(lp.disc.predictor, d.predictor.export_params(r, 0)): P_.data.copy_(src)
+      for P_, src in zip(lp.disc.target, d.target.export_params(r, 0)): P_.data.copy_(src)
+    loops.append(lp)
+  Ne = tr.expert_memory.size
+  depth = im['depth']
+  def draw(n): return [_mask(rs, (R, n, din), p_in)] + [_mask(rs, (R, n, dH), p_h) for _ in range(depth)]
+  # ---- pre-training: same minibatches, same masks -------------------------------------------------------------------------------
+  batches = rs.randint(0, Ne, size=(iters, R, B)).astype(np.int32)
+  masks = [draw(B) for _ in range(iters)]
+  thr = draw(Ne * 5) if algorithm == 'DRIL' else draw(B)
+  tr.pretrain_discriminator(iters, batches=[torch.from_numpy(batches[i]) for i in range(iters)], masks=[[torch.from_numpy(m).cuda() for m in ms] for ms in masks],
+                            threshold_masks=[torch.from_numpy(m).cuda() for m in thr])
+  for r, lp in enumerate(loops):
+    seq = [torch.from_numpy(m[r]) for ms in masks for m in ms] + [torch.from_numpy(m[r]) for m in thr]
+    with cases.injected_dropout(seq):
+      lp.pretrain_discriminator(batches=[batches[i, r].tolist() for i in range(iters)])
+    assert not seq, 'the oracle consumed a different number of dropout draws'
+    if algorithm == 'DRIL': np.testing.assert_allclose(float(tr.discriminator._q[r]), lp.dril_q, rtol=2e-3, atol=1e-9)
+    else: np.testing.assert_allclose(float(tr.discriminator.sigma[r]), lp.disc.sigma_1, rtol=1e-4)
+  u0 = rs.uniform(size=(R, obs)).astype(np.float32)
+  tr.env.batch.reset(torch.from_numpy(u0).cuda(), tr.state)
+  for r, lp in enumerate(loops): lp.state, lp.t = lp.env.reset(torch.from_numpy(u0[r])), 0
+  err = {}
+  for step in range(1, steps + 1):
+    noise = dict(act_eps=rs.standard_normal((R, A)).astype(np.float32), reset_u=rs.uniform(size=(R, obs)).astype(np.float32),
+                 eps_next=rs.standard_normal((R, B, A)).astype(np.float32), eps_new=rs.standard_normal((R, B, A)).astype(np.float32))
+    upd = step >= start
+    rew_masks = None
+    if upd:
+      noise['idx_pol'] = np.stack([rs.randint(0, max(lp.memory.idx - 1, 1), size=B) for lp in loops]).astype(np.int32)
+      noise['idx_exp'] = rs.randint(0, Ne - 1, size=(R, B)).astype(np.int32)
+      if algorithm == 'DRIL': rew_masks = draw(B * 5)
+    tr.eps_act.copy_(torch.from_numpy(noise['act_eps']))
+    tr.u_reset.copy_(torch.from_numpy(noise['reset_u']))
+    if upd:
+      tr.idx_pol.copy_(torch.from_numpy(noise['idx_pol']))
+      tr.idx_exp.copy_(torch.from_numpy(noise['idx_exp']))
+      tr.eps_next.copy_(torch.from_numpy(noise['eps_next']))
+      tr.eps_new.copy_(torch.from_numpy(noise['eps_new']))
+      tr.dril_masks = None if rew_masks is None else [torch.from_numpy(m).cuda() for m in rew_masks]
+    tr.train_step()
+    for r, lp in enumerate(loops):
+      seq = {k: [torch.from_numpy(np.asarray(v[r]))] for k, v in noise.items()}
+      seq['act_eps'] = [torch.from_numpy(noise['act_eps'][r:r + 1])]
+      lp.noise = _Injected(seq)
+      with cases.injected_dropout([] if rew_masks is None else [torch.from_numpy(m[r]) for m in rew_masks]):
+        lp.run_step()
+      err['state'] = max(err.get('state', 0), float((tr.state[r].cpu() - lp.state[0]).abs().max()))
+      if upd:
+        err['q'] = max(err.get('q', 0), float((tr.sac_out['q_values'][r].cpu() - lp.last['sac']['q_values']).abs().max()))
+        err['reward'] = max(err.get('reward', 0), float((tr.batch['rewards'][r].cpu() - lp.last['rewards']).abs().max()))
+  for r, lp in enumerate(loops):
+    for i, p in enumerate(lp.agent.actor):
+      err['actor'] = max(err.get('actor', 0), float((tr.actor.mlp.layer_views()[0][i][r].cpu() - p.detach()).abs().max()))
+  print(algorithm, err)
+  assert err['state'] < 2e-3, err
+  assert err.get('q', 0) < 5e-3, err
+  assert err.get('reward', 0) < 5e-3, err
+  assert err['actor'] < 5e-4, err

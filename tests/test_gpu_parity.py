@@ -34,7 +34,7 @@ def test_cuda_matches_reference_fixture(name):
   assert not bad, '\n'.join(bad)
 
 
-@pytest.mark.parametrize('name', ['actor_small', 'sac_small', 'sac_small_wd', 'sac_ant_small', 'bc_small', 'gail_ant', 'gail_default', 'gail_entropy_nosn', 'gail_pugail', 'gail_mixup', 'gmmil_hopper', 'replay_ring'])
+@pytest.mark.parametrize('name', ['actor_small', 'sac_small', 'sac_small_wd', 'sac_ant_small', 'bc_small', 'gail_ant', 'gail_default', 'gail_entropy_nosn', 'gail_pugail', 'gail_mixup', 'gmmil_hopper', 'replay_ring', 'red_dropout', 'dril_small'])
 def test_cuda_matches_oracle_across_replicas(name):
   """3 replicas with independent inputs in ONE batched call == 3 independent oracle runs."""
   from cuda_cases import run_cuda

@@ -84,7 +84,7 @@ def test_config_defaults_and_overrides():
   tuned = config.load_config(['algorithm=GAIL', 'optimised_hyperparameters=GAIL_5_trajectories'])
   assert tuned.training.batch_size == 1024 and tuned.imitation.loss_function == 'Mixup'
   with pytest.raises(FileNotFoundError): config.load_config(['algorithm=NOPE'])
-  with pytest.raises(NotImplementedError): config.load_config(['algorithm=RED'])
+  assert config.load_config(['algorithm=RED']).imitation.pretraining.iterations == 100000 and config.load_config(['algorithm=DRIL']).imitation.quantile_cutoff == 0.98
   assert config.load_config(['algorithm=AdRIL']).imitation.update_freq == 1250
   with pytest.raises(AttributeError): _ = cfg.training.no_such_key
 

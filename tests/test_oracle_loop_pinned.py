@@ -50,6 +50,18 @@ CONFIGS = [
   ('AdRIL', 'hopper', ('imitation.update_freq=20', ), dict(mix_expert_data='mixed_batch', imitation=dict(update_freq=20, balanced=True))),
   ('AdRIL', 'walker2d', ('imitation.update_freq=15', 'imitation.balanced=false'), dict(mix_expert_data='mixed_batch', imitation=dict(update_freq=15, balanced=False))),
   ('AdRIL', 'hopper', ('imitation.update_freq=0', ), dict(mix_expert_data='mixed_batch', imitation=dict(update_freq=0, balanced=True))),
+  # DRIL (dropout policy ensemble, BC pretraining, quantile threshold, MC-dropout reward; bc_aux_loss from DRIL.yaml) and RED (predictor / target
+  # embeddings, regression pretraining, median-heuristic bandwidth, with and without dropout / prefill)
+  ('DRIL', 'hopper', ('imitation.pretraining.iterations=9', 'imitation.discriminator.hidden_size=16'),
+   dict(bc_aux_loss=True, imitation=dict(hidden_size=16, activation='tanh', input_dropout=0.1, dropout=0.1, pretraining_iterations=9, learning_rate=3e-5, weight_decay=0.0))),
+  ('DRIL', 'walker2d', ('imitation.pretraining.iterations=5', 'imitation.discriminator.hidden_size=16', 'imitation.discriminator.depth=2', 'imitation.discriminator.dropout=0.4',
+                        'imitation.mix_expert_data=mixed_batch', 'imitation.quantile_cutoff=0.9', 'imitation.bc_aux_loss=false'),
+   dict(mix_expert_data='mixed_batch', imitation=dict(hidden_size=16, depth=2, activation='tanh', input_dropout=0.1, dropout=0.4, pretraining_iterations=5, quantile_cutoff=0.9,
+                                                      learning_rate=3e-5, weight_decay=0.0))),
+  ('RED', 'hopper', ('imitation.pretraining.iterations=11', ), dict(imitation=dict(hidden_size=32, pretraining_iterations=11, learning_rate=3e-5, weight_decay=0.0))),
+  ('RED', 'halfcheetah', ('imitation.pretraining.iterations=6', 'imitation.discriminator.input_dropout=0.2', 'imitation.discriminator.dropout=0.3', 'imitation.discriminator.depth=2',
+                          'imitation.mix_expert_data=prefill_memory', 'imitation.weight_decay=0.5'),
+   dict(mix_expert_data='prefill_memory', imitation=dict(hidden_size=32, depth=2, input_dropout=0.2, dropout=0.3, pretraining_iterations=6, learning_rate=3e-5, weight_decay=0.5))),
   ('SAC', 'hopper', (), {}),
   ('SAC', 'ant', ('training.weight_decay=0.01', ), dict(weight_decay=0.01)),
   ('GMMIL', 'halfcheetah', (), {}),
@@ -74,6 +86,7 @@ def test_restated_loop_equals_the_reference_train_function(algorithm, env, extra
   try:
     ol = loop.OracleLoop(algorithm, env, seed=seed, batch_size=B, start=START, memory_size=STEPS, hidden_size=H, trajectories=3, max_episode_steps=MAX_EPISODE_STEPS,
                          expert_raw=raw, **kwargs)
+    if algorithm in ('DRIL', 'RED'): ol.pretrain_discriminator()
     for _ in range(STEPS): ol.run_step()
   finally:
     torch.set_num_threads(threads)
@@ -84,6 +97,12 @@ def test_restated_loop_equals_the_reference_train_function(algorithm, env, extra
   for t in range(2):
     for i in range(6): _close(f'critic.{critic[6 * t + i][0]}', critic[6 * t + i][1], ol.agent.twin[t][i])
   _close('log_alpha', ref['agent']['log_alpha'], ol.agent.log_alpha)
+  if algorithm == 'DRIL':  # discriminator.pth = the dropout policy's state dict (train.py:238)
+    for i, (k, v) in enumerate(ref['discriminator'].items()): _close(f'dril.{k}', v, ol.disc[i])
+  if algorithm == 'RED':
+    sd = ref['discriminator']
+    for i, (k, v) in enumerate((k, v) for k, v in sd.items() if k.startswith('predictor')): _close(f'red.{k}', v, ol.disc.predictor[i])
+    for i, (k, v) in enumerate((k, v) for k, v in sd.items() if k.startswith('target')): _close(f'red.{k}', v, ol.disc.target[i])
   if algorithm == 'GAIL':
     sd, sn = ref['discriminator'], ol.disc.g_sn is not None
     for net, params, bufs in (('g', ol.disc.g, ol.disc.g_sn), ('h', ol.disc.h, ol.disc.h_sn)):
