@@ -129,6 +129,7 @@ SIGNATURES = {
   'il_bc_workspace_bytes': (i64, [P(BcArgs)]),
   'il_bc_update': (C.c_int, [vp, P(BcArgs), vp]),
   'il_adam_step': (C.c_int, [vp, vp, vp, P(Adam), i64, vp]),
+  'il_adam_step_polyak': (C.c_int, [vp, vp, vp, P(Adam), i64, vp, C.c_float, vp]),
   'il_fill_dropout_mask': (C.c_int, [vp, vp, i64, f32, u64, u64, vp, vp]),
   'il_actor_dropout_workspace_bytes': (i64, [P(Mlp), C.c_int, C.c_int]),
   'il_actor_log_prob_dropout': (C.c_int, [vp, P(Mlp), C.c_int, C.c_int, C.c_int, vp, i64, C.c_int, vp, vp, P(vp), vp, vp, i64, vp]),

@@ -355,26 +355,80 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 // Same update with TMA staging: persistent CTAs stream 8 KB tiles of every operand into shared memory with 1-D bulk copies
 // (cp.async.bulk ... mbarrier::complete_tx, issued by one thread), update in place, and write the results back with bulk stores —
 // the LSU only sees shared-memory traffic, global traffic is 128-byte-line bulk transfers on the copy engine path. Double buffered.
-constexpr int ADAM_TILE = 2048;                 // floats per operand per stage
 constexpr int ADAM_STREAMS = 5;                 // p, g, m, v, target
-constexpr int ADAM_TMA_SMEM = 2 * ADAM_STREAMS * ADAM_TILE * 4 + 64;
-__global__ void __launch_bounds__(256) adam_tma_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, const int64_t* __restrict__ step,
-                                                       double lr, double beta1_d, double beta2_d, double eps_d, double wd, int64_t n, float* __restrict__ target, float tau, float one_minus_tau) {
+constexpr int ADAM_CONSUMERS = 256;             // threads 0..255 compute; warp 8 (one elected lane) drives the copy engine
+template <int TILE, int STAGES> constexpr int adam_tma_smem() { return STAGES * ADAM_STREAMS * TILE * 4 + 2 * STAGES * 8 + 64; }
+__device__ __forceinline__ void adam_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "ADAM_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n\t"
+      "@q bra ADAM_DONE;\n\t"
+      "bra ADAM_WAIT;\n\t"
+      "ADAM_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// TILE floats per operand per stage, STAGES-deep ring. Warp-specialised: the copy thread keeps STAGES - 1 tiles of loads in flight and turns
+// every computed stage into bulk stores; the 256 compute threads only ever wait on "stage full" and signal "stage computed" (no CTA-wide barrier
+// in the loop).
+template <int TILE, int STAGES>
+__global__ void __launch_bounds__(ADAM_CONSUMERS + 32) adam_tma_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                                      const int64_t* __restrict__ step, double lr, double beta1_d, double beta2_d, double eps_d, double wd, int64_t n,
+                                                                      float* __restrict__ target, float tau, float one_minus_tau) {
   extern __shared__ __align__(128) uint8_t adam_smem[];
-  float* buf = reinterpret_cast<float*>(adam_smem);                                  // [stage][stream][ADAM_TILE]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(adam_smem + 2 * ADAM_STREAMS * ADAM_TILE * 4);
+  float* buf = reinterpret_cast<float*>(adam_smem);                                  // [stage][stream][TILE]
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(buf);
+  const uint32_t full0 = smem0 + (uint32_t)(STAGES * ADAM_STREAMS * TILE * 4), done0 = full0 + 8u * STAGES;  // full[stage] (tx bytes), done[stage] (256 compute threads)
   __shared__ float s_step_size, s_bc2_sqrt;
   const int tid = threadIdx.x;
-  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars), smem0 = (uint32_t)__cvta_generic_to_shared(buf);
   if (tid == 0) {
     const double t = (double)*step;
     s_step_size = (float)(lr / (1.0 - pow(beta1_d, t)));
     s_bc2_sqrt = (float)sqrt(1.0 - pow(beta2_d, t));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+    for (int s_ = 0; s_ < STAGES; ++s_) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full0 + 8u * s_));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(done0 + 8u * s_), "r"(ADAM_CONSUMERS));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  const int64_t n_tiles = (n + TILE - 1) / TILE;
+  const int n_streams = target ? 5 : 4;
+  auto tile_floats = [&](int64_t tile) { const int64_t left = n - tile * TILE; return (int)(left < TILE ? left : TILE); };
+  const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (tid >= ADAM_CONSUMERS) {  // ---- copy warp ----
+    if (tid != ADAM_CONSUMERS) return;
+    auto issue_loads = [&](int64_t k) {
+      const int64_t tile = blockIdx.x + k * gridDim.x;
+      const int stage = (int)(k % STAGES);
+      const uint32_t bytes = (uint32_t)tile_floats(tile) * 4u, bar = full0 + 8u * stage;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * (uint32_t)n_streams) : "memory");
+      const float* src[5] = {p, g, m, v, target};
+      for (int q = 0; q < n_streams; ++q)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem0 + (uint32_t)((stage * ADAM_STREAMS + q) * TILE * 4)),
+                     "l"(src[q] + tile * TILE), "r"(bytes), "r"(bar) : "memory");
+    };
+    for (int64_t k = 0; k < STAGES - 1 && k < my_tiles; ++k) issue_loads(k);
+    for (int64_t k = 0; k < my_tiles; ++k) {
+      const int stage = (int)(k % STAGES);
+      const int64_t tile = blockIdx.x + k * gridDim.x;
+      if (k + STAGES - 1 < my_tiles) {  // tile k + STAGES - 1 goes into the stage of tile k - 1: its stores (the last committed group) must have left shared memory
+        if (k > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        issue_loads(k + STAGES - 1);
+      }
+      adam_mbar_wait(done0 + 8u * stage, (uint32_t)((k / STAGES) & 1));  // stage computed (each compute thread fenced its writes to the async proxy before arriving)
+      const uint32_t bytes = (uint32_t)tile_floats(tile) * 4u;
+      float* dst[5] = {p, nullptr, m, v, target};
+      for (int q = 0; q < n_streams; ++q) {
+        if (!dst[q]) continue;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst[q] + tile * TILE), "r"(smem0 + (uint32_t)((stage * ADAM_STREAMS + q) * TILE * 4)), "r"(bytes)
+                     : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before the CTA (and its shared memory) goes away
+    return;
+  }
+  // ---- compute threads ----
   const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
   const float decay = (float)(1.0 - lr * wd), w1 = (float)(1.0 - beta1_d), w2 = (float)(1.0 - beta2_d), beta2 = (float)beta2_d, eps = (float)eps_d;
   const bool has_wd = wd != 0.0;
@@ -385,42 +439,17 @@ __global__ void __launch_bounds__(256) adam_tma_kernel(float* __restrict__ p, co
     const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);
     pi = __fadd_rn(pi, __fmul_rn(-step_size, __fdiv_rn(mi, denom)));
   };
-  const int64_t n_tiles = (n + ADAM_TILE - 1) / ADAM_TILE;
-  const int n_streams = target ? 5 : 4;
-  auto tile_floats = [&](int64_t tile) { const int64_t left = n - tile * ADAM_TILE; return (int)(left < ADAM_TILE ? left : ADAM_TILE); };
-  auto issue_loads = [&](int64_t tile, int stage) {  // thread 0 only
-    const uint32_t bytes = (uint32_t)tile_floats(tile) * 4u, bar = bar0 + 8u * stage;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * (uint32_t)n_streams) : "memory");
-    const float* src[5] = {p, g, m, v, target};
-    for (int q = 0; q < n_streams; ++q)
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem0 + (uint32_t)((stage * ADAM_STREAMS + q) * ADAM_TILE * 4)),
-                   "l"(src[q] + tile * ADAM_TILE), "r"(bytes), "r"(bar) : "memory");
-  };
-  int64_t tile = blockIdx.x;
-  if (tid == 0 && tile < n_tiles) issue_loads(tile, 0);
-  for (int k = 0; tile < n_tiles; ++k, tile += gridDim.x) {
-    const int stage = k & 1;
-    if (tid == 0 && tile + gridDim.x < n_tiles) {
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stores that last read the other stage have left shared memory
-      issue_loads(tile + gridDim.x, stage ^ 1);
-    }
-    {  // wait for this stage's bytes
-      const uint32_t bar = bar0 + 8u * stage, parity = (uint32_t)((k >> 1) & 1);
-      asm volatile(
-          "{\n\t.reg .pred q;\n\t"
-          "ADAM_WAIT:\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n\t"
-          "@q bra ADAM_DONE;\n\t"
-          "bra ADAM_WAIT;\n\t"
-          "ADAM_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-    }
+  for (int64_t k = 0; k < my_tiles; ++k) {
+    const int stage = (int)(k % STAGES);
+    const int64_t tile = blockIdx.x + k * gridDim.x;
+    adam_mbar_wait(full0 + 8u * stage, (uint32_t)((k / STAGES) & 1));
     const int nf4 = tile_floats(tile) >> 2;
-    float4* sp = reinterpret_cast<float4*>(buf + (stage * ADAM_STREAMS + 0) * ADAM_TILE);
-    const float4* sg = reinterpret_cast<const float4*>(buf + (stage * ADAM_STREAMS + 1) * ADAM_TILE);
-    float4* smm = reinterpret_cast<float4*>(buf + (stage * ADAM_STREAMS + 2) * ADAM_TILE);
-    float4* sv = reinterpret_cast<float4*>(buf + (stage * ADAM_STREAMS + 3) * ADAM_TILE);
-    float4* stg = reinterpret_cast<float4*>(buf + (stage * ADAM_STREAMS + 4) * ADAM_TILE);
-    for (int i = tid; i < nf4; i += 256) {
+    float4* sp = reinterpret_cast<float4*>(buf + (stage * ADAM_STREAMS + 0) * TILE);
+    const float4* sg = reinterpret_cast<const float4*>(buf + (stage * ADAM_STREAMS + 1) * TILE);
+    float4* smm = reinterpret_cast<float4*>(buf + (stage * ADAM_STREAMS + 2) * TILE);
+    float4* sv = reinterpret_cast<float4*>(buf + (stage * ADAM_STREAMS + 3) * TILE);
+    float4* stg = reinterpret_cast<float4*>(buf + (stage * ADAM_STREAMS + 4) * TILE);
+    for (int i = tid; i < nf4; i += ADAM_CONSUMERS) {
       float4 pv = sp[i], mv = smm[i], vv = sv[i];
       const float4 gv = sg[i];
       upd(pv.x, mv.x, vv.x, gv.x); upd(pv.y, mv.y, vv.y, gv.y); upd(pv.z, mv.z, vv.z, gv.z); upd(pv.w, mv.w, vv.w, gv.w);
@@ -433,20 +462,19 @@ __global__ void __launch_bounds__(256) adam_tma_kernel(float* __restrict__ p, co
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk-copy engine
-    __syncthreads();
-    if (tid == 0) {
-      const uint32_t bytes = (uint32_t)tile_floats(tile) * 4u;
-      float* dst[5] = {p, nullptr, m, v, target};
-      for (int q = 0; q < n_streams; ++q) {
-        if (!dst[q]) continue;
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst[q] + tile * ADAM_TILE), "r"(smem0 + (uint32_t)((stage * ADAM_STREAMS + q) * ADAM_TILE * 4)), "r"(bytes)
-                     : "memory");
-      }
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(done0 + 8u * stage) : "memory");
   }
-  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before the CTA (and its shared memory) goes away
 }
+
+template <int TILE, int STAGES>
+static int launch_adam_tma(il_handle* h, int ctas_per_sm, float* params, const float* grads, const il_adam* opt, int64_t n, cudaStream_t stream, float* polyak_target, float polyak_factor) {
+  static bool attr_set = false;
+  if (!attr_set) { IL_CUDA(cudaFuncSetAttribute(adam_tma_kernel<TILE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, adam_tma_smem<TILE, STAGES>())); attr_set = true; }
+  IL_LAUNCH(h, (adam_tma_kernel<TILE, STAGES>), h->sm_count * ctas_per_sm, ADAM_CONSUMERS + 32, (adam_tma_smem<TILE, STAGES>()), stream, params, grads, opt->m, opt->v, opt->step, opt->lr, opt->beta1,
+            opt->beta2, opt->eps, opt->weight_decay, n, polyak_target, polyak_factor, (float)(1.0 - (double)polyak_factor));
+  return 0;
+}
+constexpr int ADAM_TMA_MIN_TILES = 4096;        // floats per CTA-iteration below which the plain kernel is used
 
 
 // ---- fused backward of the linear head + last hidden activation (one pass over the hidden output) -----------------------------------
@@ -580,10 +608,16 @@ int launch_adam(il_handle* h, float* params, const float* grads, const il_adam* 
   IL_CHECK(opt->m && opt->v && opt->step, "adam: null state");
   IL_CHECK(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(opt->m) | reinterpret_cast<uintptr_t>(opt->v) |
              reinterpret_cast<uintptr_t>(polyak_target)) & 15) == 0, "adam: buffers must be 16-byte aligned");
-  if (h->adam_tma && n % 4 == 0 && n >= (int64_t)ADAM_TILE * h->sm_count * 2) {  // large flat buffers: TMA-staged streaming variant
-    IL_LAUNCH(h, adam_tma_kernel, h->sm_count * 2, 256, ADAM_TMA_SMEM, stream, params, grads, opt->m, opt->v, opt->step, opt->lr, opt->beta1, opt->beta2, opt->eps, opt->weight_decay, n,
-              polyak_target, polyak_factor, (float)(1.0 - (double)polyak_factor));
-    return 0;
+  if (h->adam_tma && n % 4 == 0 && n >= (int64_t)ADAM_TMA_MIN_TILES * h->sm_count * 2) {  // large flat buffers: TMA-staged streaming variant
+    switch (h->adam_tma) {  // (tile floats, stages, CTAs per SM): 20 B/float of shared memory per stage
+      case 2: return launch_adam_tma<4096, 2>(h, 1, params, grads, opt, n, stream, polyak_target, polyak_factor);
+      case 3: return launch_adam_tma<2048, 3>(h, 1, params, grads, opt, n, stream, polyak_target, polyak_factor);
+      case 4: return launch_adam_tma<1024, 4>(h, 2, params, grads, opt, n, stream, polyak_target, polyak_factor);
+      case 5: return launch_adam_tma<1024, 3>(h, 3, params, grads, opt, n, stream, polyak_target, polyak_factor);
+      case 6: return launch_adam_tma<512, 4>(h, 4, params, grads, opt, n, stream, polyak_target, polyak_factor);
+      case 7: return launch_adam_tma<2048, 4>(h, 1, params, grads, opt, n, stream, polyak_target, polyak_factor);
+      default: return launch_adam_tma<2048, 2>(h, 2, params, grads, opt, n, stream, polyak_target, polyak_factor);
+    }
   }
   IL_LAUNCH(h, adam_kernel, ew_blocks(n / 4 + 1, 256, h->sm_count), 256, 0, stream, params, grads, opt->m, opt->v, opt->step, opt->lr, opt->beta1, opt->beta2, opt->eps,
             opt->weight_decay, n, polyak_target, polyak_factor, (float)(1.0 - (double)polyak_factor));
@@ -597,7 +631,6 @@ int launch_head_backward(il_handle* h, const HeadBwdArgs& a, int G, cudaStream_t
 }
 
 int mlp_init() {
-  IL_CUDA(cudaFuncSetAttribute(adam_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ADAM_TMA_SMEM));
   IL_CUDA(cudaFuncSetAttribute(head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1024 * HB_MAXN + 4 * (HB_MAXN + 1) * 64 * 4) * 4));
   return 0;
 }
@@ -628,6 +661,12 @@ extern "C" int il_adam_step(il_handle* h, float* params, const float* grads, con
   IL_CHECK(h && params && grads && opt, "il_adam_step: null argument");
   IL_TRY(launch_tick(h, opt->step, nullptr, nullptr, (cudaStream_t)stream));
   return launch_adam(h, params, grads, opt, n, (cudaStream_t)stream);
+}
+
+extern "C" int il_adam_step_polyak(il_handle* h, float* params, const float* grads, const il_adam* opt, int64_t n, float* target, float polyak_factor, void* stream) {
+  IL_CHECK(h && params && grads && opt && target, "il_adam_step_polyak: null argument");
+  IL_TRY(launch_tick(h, opt->step, nullptr, nullptr, (cudaStream_t)stream));
+  return launch_adam(h, params, grads, opt, n, (cudaStream_t)stream, target, polyak_factor);
 }
 
 extern "C" int il_polyak(il_handle* h, float* target, const float* online, int64_t n, float polyak_factor, void* stream) {

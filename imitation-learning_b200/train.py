@@ -104,6 +104,7 @@ class Trainer:
       self.discriminator.eval()  # train.py:147
     elif self.algorithm == 'AdRIL':
       self.discriminator = RewardRelabeller(cfg.imitation.update_freq, cfg.imitation.balanced, device=dev)  # train.py:72
+      self._expert_trajectories = int(self.expert_memory.num_trajectories)  # constant: read once, outside any graph capture
     elif self.algorithm == 'GMMIL':
       self.discriminator = GMMILDiscriminator(S, A, cfg.imitation, replicas=R, device=dev)
     elif self.algorithm == 'PWIL':
@@ -240,7 +241,7 @@ class Trainer:
         self.discriminator.predict_reward(self.batch.rows[..., :self.S], self.batch.rows[..., self.S:self.S + self.A], masks=masks, out=view)
       else: self.discriminator.predict_reward_batch(self.batch, reward_out=view)
     if self.algorithm == 'AdRIL':  # train.py:188-189; `step` of the reference = step_f - 1 here (the rollout has already advanced the counter)
-      self.discriminator.resample_and_relabel(self.batch, self.expert_batch, self.step_f, self.memory._num_trajectories, self.expert_memory.num_trajectories, step_offset=-1.0)
+      self.discriminator.resample_and_relabel(self.batch, self.expert_batch, self.step_f, self.memory._num_trajectories, self._expert_trajectories, step_offset=-1.0)
     from .training import sac_update
     if cfg.imitation.bc_aux_loss:  # train.py:201
       from .training import behavioural_cloning_update
@@ -385,7 +386,9 @@ def train(cfg: Config, file_prefix: str = '') -> float:
       returns = trainer.evaluate()
       mean, std, n = distributed.return_statistics(returns)
       normalized = (returns.cpu().numpy() - trainer.normalization_min) / (trainer.normalization_max - trainer.normalization_min)
-      metrics['test_steps'], metrics['test_returns'], metrics['test_returns_normalized'] = [0], [returns.cpu().numpy().tolist()], [normalized.tolist()]
+      flat = total == 1
+      metrics['test_steps'], metrics['test_returns'], metrics['test_returns_normalized'] = [0], [returns.cpu().numpy().reshape(-1).tolist() if flat else returns.cpu().numpy().tolist()], \
+          [normalized.reshape(-1).tolist() if flat else normalized.tolist()]
       if rank == 0:
         print(f'BC: test return {mean:.3f} +- {std:.3f} over {n} episodes', flush=True)
         torch.save(dict(actor=trainer.actor.state_dict()), f'{file_prefix}agent.pth')  # train.py:108
@@ -401,8 +404,9 @@ def train(cfg: Config, file_prefix: str = '') -> float:
       normalized = (returns.cpu().numpy() - trainer.normalization_min) / (trainer.normalization_max - trainer.normalization_min)
       score.append(float((mean - trainer.normalization_min) / (trainer.normalization_max - trainer.normalization_min)))
       metrics['test_steps'].append(step)
-      metrics['test_returns'].append(returns.cpu().numpy().tolist())
-      metrics['test_returns_normalized'].append(normalized.tolist())
+      flat = total == 1  # the reference's schema: one list of `episodes` floats per evaluation (train.py:214-219); R > 1 keeps [R][episodes]
+      metrics['test_returns'].append(returns.cpu().numpy().reshape(-1).tolist() if flat else returns.cpu().numpy().tolist())
+      metrics['test_returns_normalized'].append(normalized.reshape(-1).tolist() if flat else normalized.tolist())
       if rank == 0: print(f'step {step}: test return {mean:.3f} +- {std:.3f} over {n} episodes ({world} rank(s))', flush=True)
   if cfg.check_time_usage: metrics['training_time'] = time.time() - start_time  # train.py:229-230
   eps = trainer.episodes.cpu().numpy()

@@ -211,6 +211,8 @@ int il_red_reward(il_handle* h, const il_red* disc, int R, const il_batch* batch
 
 /* AdamW step over a flat buffer (used by the fused updates; exposed for tests): torch _single_tensor_adam. */
 int il_adam_step(il_handle* h, float* params, const float* grads, const il_adam* opt, int64_t n, void* stream);
+/* The same step with update_target_network fused (training.py:33 + models.py:78-81): target = polyak * target + (1 - polyak) * params_new. */
+int il_adam_step_polyak(il_handle* h, float* params, const float* grads, const il_adam* opt, int64_t n, float* target, float polyak_factor, void* stream);
 
 /* ---- ReplayMemory (memory.py:12-68) --------------------------------------------------------------------- */
 /* append (memory.py:40-44) of one transition per replica, with the train.py:157-162 flags: `terminal`

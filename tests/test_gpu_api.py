@@ -283,26 +283,31 @@ def test_return_allreduce_single_process_matches_torch():
   assert n == 210 and abs(mean - float(r.mean())) < 1e-3 and abs(std - float(r.std(unbiased=False))) < 1e-2
 
 
-def test_adam_tma_staged_kernel_is_bitwise_the_plain_kernel():
-  """AdamW (+ fused polyak) with TMA staging (cp.async.bulk tiles through shared memory, mbarrier complete_tx) against the plain 128-bit
-  streaming kernel: same arithmetic, so bit-identical parameters / moments / target, including a ragged last tile."""
+@pytest.mark.parametrize('polyak', [False, True])
+def test_adam_tma_staged_kernel_is_bitwise_the_plain_kernel(polyak):
+  """AdamW (+ fused polyak) with TMA staging (cp.async.bulk tiles through shared memory, mbarrier complete_tx, a copy thread feeding 256 compute
+  threads) against the plain 128-bit streaming kernel: same arithmetic, so bit-identical parameters / moments / target for every tile / ring
+  geometry, including a ragged last tile and CTAs with different tile counts."""
   import il_b200
   from il_b200 import _lib
-  n = 2048 * 148 * 2 + 2048 * 3 + 12  # > the switch-over size, not a multiple of the 2048-float tile
+  n = 4096 * 148 * 2 * 3 + 2048 * 3 + 12  # > the switch-over size, several tiles per CTA, not a multiple of any tile
   torch.manual_seed(0)
   p0, g = torch.randn(n, device='cuda'), torch.randn(n, device='cuda') * 0.1
   outs = []
-  for tma in (0, 1):
+  lib, h = _lib.lib(), _lib.handle()
+  for tma in range(8):
     _lib.set_option('adam_tma', tma)
     try:
       p, tgt = p0.clone(), p0.clone() * 0.5
       opt = il_b200.AdamW([p], lr=1e-3, weight_decay=0.01)
       opt.exp_avg.copy_(torch.sin(p0)); opt.exp_avg_sq.copy_(torch.cos(p0) ** 2)
       a = opt.c_struct()
-      lib, h = _lib.lib(), _lib.handle()
-      for _ in range(2): _lib.check(lib.il_adam_step(h, p.data_ptr(), g.data_ptr(), C.byref(a), n, _lib.stream()))
+      for _ in range(2):
+        if polyak: _lib.check(lib.il_adam_step_polyak(h, p.data_ptr(), g.data_ptr(), C.byref(a), n, tgt.data_ptr(), 0.995, _lib.stream()))
+        else: _lib.check(lib.il_adam_step(h, p.data_ptr(), g.data_ptr(), C.byref(a), n, _lib.stream()))
       torch.cuda.synchronize()
-      outs.append((p.clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone()))
+      outs.append((p.clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone(), tgt.clone()))
     finally:
       _lib.set_option('adam_tma', 1)
-  for x, y in zip(*outs): assert torch.equal(x, y)
+  for variant, o in enumerate(outs[1:], 1):
+    for x, y in zip(outs[0], o): assert torch.equal(x, y), f'adam_tma={variant}'

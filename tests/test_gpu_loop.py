@@ -190,7 +190,7 @@ def test_dropout_discriminator_loops_match_oracle(algorithm):
   for r in range(R):
     init = dict(actor=tr.actor.mlp.export_params(r, 0), twin=[tr.critic.mlp.export_params(r, 0), tr.critic.mlp.export_params(r, 1)])
     lp = oloop.OracleLoop(algorithm, 'hopper', seed=3 + r, batch_size=B, start=start, memory_size=cfg.memory.size, hidden_size=H, trajectories=2, expert_raw=expert_raw, init=init,
-                          mix_expert_data=cfg.imitation.mix_expert_data, imitation=im)
+                          mix_expert_data=cfg.imitation.mix_expert_data, imitation=im, bc_aux_loss=bool(cfg.imitation.bc_aux_loss))  # DRIL.yaml: bc_aux_loss true
     d = tr.discriminator
     if algorithm == 'DRIL':
       for P_, src in zip(lp.disc, d.mlp.export_params(r, 0)): P_.data.copy_(src)
