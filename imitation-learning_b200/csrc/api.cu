@@ -37,7 +37,7 @@ extern "C" int il_create(int device, il_handle** out) {
     const char* wt = getenv("IL_WIDE_TN");
     h->wide_tn = (wt && wt[0] == '0') ? 0 : 1;
     const char* ff = getenv("IL_FIRST_LAYER_FAST");
-    h->first_layer_fast = (ff && ff[0] == '0') ? 0 : 1;
+    h->first_layer_fast = ff ? atoi(ff) : 2;  // 0 generic K-thin kernel, 1 FFMA2 kernel with shared-memory weights, 2 register-resident weights (N == 256)
     const char* hf = getenv("IL_HEAD_FUSED");
     h->head_fused = (hf && hf[0] == '0') ? 0 : 1;
     const char* ds = getenv("IL_DEBUG_SYNC");
@@ -45,7 +45,7 @@ extern "C" int il_create(int device, il_handle** out) {
     // AdamW with TMA staging (cp.async.bulk tiles through shared memory): bit-identical to the plain kernel, 7.309 -> 7.285 ms / step in an
     // A/B inside one gpurun call (profiles/README.md) -> on by default for the large flat buffers
     const char* at = getenv("IL_ADAM_TMA");
-    h->adam_tma = (at && at[0] == '0') ? 0 : 1;
+    h->adam_tma = at ? atoi(at) : 1;  // 0 plain kernel, 1 auto (ring geometry by stream count), 2..7 fixed geometries (scripts/adam_bench.py)
     const char* gt = getenv("IL_GAIL_TILED");
     h->gail_tiled = (gt && gt[0] == '0') ? 0 : 1;
     // first MLP layer computed inside the producers of the tcgen05 launch: measured 7.64 vs 7.59 ms / step against the separate

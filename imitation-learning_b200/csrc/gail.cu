@@ -475,19 +475,27 @@ struct GailTiledParams {
 // Loads rows [b0, b0 + nb) into X [RB][DP] (zero padded columns / rows); CO = sample weight, DF = mixing epsilon.
 __device__ void tiled_load_rows(const TDims& g, const float* pol, const float* exp_, const float* eps, int kind, int b0, int nb, float* X, float* CO, float* DF) {
   const RowLayout L = row_layout(g.S, g.A);
-  for (int idx = threadIdx.x; idx < g.RB * g.DP; idx += blockDim.x) {
-    const int b = idx / g.DP, j = idx % g.DP;
-    float v = 0.f;
-    if (b < nb && j < g.d) {
-      const int64_t ro = (int64_t)(b0 + b) * g.row + j;
-      if (kind == PASS_POLICY) v = pol[ro];
-      else if (kind == PASS_EXPERT) v = exp_[ro];
+  const int nq = g.DP >> 2;  // 128-bit chunks per row (packed rows are 16-byte aligned with a stride that is a multiple of 4 floats)
+  for (int idx = threadIdx.x; idx < g.RB * nq; idx += blockDim.x) {
+    const int b = idx / nq, q = idx % nq;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b < nb) {
+      const int64_t ro = (int64_t)(b0 + b) * g.row + 4 * q;
+      if (kind == PASS_POLICY) v = __ldg(reinterpret_cast<const float4*>(pol + ro));
+      else if (kind == PASS_EXPERT) v = __ldg(reinterpret_cast<const float4*>(exp_ + ro));
       else {
-        const float e = eps[b0 + b];
-        v = __fadd_rn(__fmul_rn(e, exp_[ro]), __fmul_rn(__fsub_rn(1.f, e), pol[ro]));
+        const float e = __ldg(eps + b0 + b), f = __fsub_rn(1.f, e);
+        const float4 x = __ldg(reinterpret_cast<const float4*>(exp_ + ro)), y = __ldg(reinterpret_cast<const float4*>(pol + ro));
+        v = make_float4(__fadd_rn(__fmul_rn(e, x.x), __fmul_rn(f, y.x)), __fadd_rn(__fmul_rn(e, x.y), __fmul_rn(f, y.y)), __fadd_rn(__fmul_rn(e, x.z), __fmul_rn(f, y.z)),
+                        __fadd_rn(__fmul_rn(e, x.w), __fmul_rn(f, y.w)));
       }
+      const int j = 4 * q;  // columns beyond d (the rest of the packed row) are not discriminator inputs
+      if (j + 1 >= g.d) v.y = 0.f;
+      if (j + 2 >= g.d) v.z = 0.f;
+      if (j + 3 >= g.d) v.w = 0.f;
+      if (j >= g.d) v.x = 0.f;
     }
-    X[idx] = v;
+    *reinterpret_cast<float4*>(X + b * g.DP + 4 * q) = v;
   }
   for (int b = threadIdx.x; b < g.RB; b += blockDim.x) {
     float w = 0.f, e = 0.f;
@@ -543,6 +551,26 @@ __device__ __forceinline__ void tiled_hidden(const TDims& g, const float* X, con
   });
 }
 
+// The same, plus the logit of every row FO[b] = w2e . hidden[b] + b2 from the tiles in registers: each thread dots its 4 hidden units with w2e, the
+// H / 4 lanes that share a row block reduce with xor shuffles (the tile loop's trip count is warp-uniform: H / 4 * RB / 4 is a multiple of 32).
+__device__ __forceinline__ void tiled_hidden_logits(const TDims& g, const float* X, const float* W1eT, const float* b1, float* Z, const float* w2e, float b2, float* FO) {
+  const int nth = g.H >> 2;
+  tiled_rows_times_wt(g, X, W1eT, b1, [&](int tb, int th, float (&acc)[4][4]) {
+    const float4 w = *reinterpret_cast<const float4*>(w2e + 4 * th);
+    float f[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 z = make_float4(fmaxf(acc[i][0], 0.f), fmaxf(acc[i][1], 0.f), fmaxf(acc[i][2], 0.f), fmaxf(acc[i][3], 0.f));
+      *reinterpret_cast<float4*>(Z + (4 * tb + i) * g.LDZ + 4 * th) = z;
+      f[i] = fmaf(z.w, w.w, fmaf(z.z, w.z, fmaf(z.y, w.y, z.x * w.x)));
+    }
+    for (int o = nth >> 1; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) f[i] += __shfl_xor_sync(0xffffffffu, f[i], o);
+    }
+    if (th == 0) *reinterpret_cast<float4*>(FO + 4 * tb) = make_float4(f[0] + b2, f[1] + b2, f[2] + b2, f[3] + b2);
+  });
+}
 // acc[4 h][4 j] += sum over this thread's rows of  DZ(b, 4 th + k) * IN[b][4 tj + c]   (weight-gradient shape [H][DP], K = rows split 4 ways
 // over lane groups: lane = th_low + 8 * ks). DZ(b, h) is produced by `dz` from Z / per-row coefficients.
 // Slot q of a thread covers tile (warp * 8 + lane % 8) + 64 q; ks = (lane / 8) is the row group.
@@ -629,16 +657,6 @@ __global__ void __launch_bounds__(THREADS, 2) gail_update_tiled_kernel(const Gai
     }
     for (int h = tid; h < H; h += THREADS) s.w2e[h] = s.w2[h] / sig2;
   };
-  auto logits = [&](int nb, float* FO) {  // FO[b] = w2e . Z[b] + b2, one warp per row
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int b = warp; b < nb; b += THREADS / 32) {
-      float f = 0.f;
-      for (int h = lane; h < H; h += 32) f = fmaf(s.w2e[h], s.Z[b * LDZ + h], f);
-      f = warp_sum(f);
-      if (lane == 0) FO[b] = f + b2;
-    }
-  };
-
   // ---- phase 2 (PUGAIL): batch scalar of the clamp ---------------------------------------------------------------------------------
   float pu_gate = 1.f, loss_bce = 0.f, loss_gp = 0.f;
   if (a.loss_function == IL_LOSS_PUGAIL) {
@@ -651,9 +669,7 @@ __global__ void __launch_bounds__(THREADS, 2) gail_update_tiled_kernel(const Gai
         const int nb = min(g.RB, B - b0);
         tiled_load_rows(g, pol, exp_, nullptr, kinds[k], b0, nb, s.X, s.CO, s.DF);
         __syncthreads();
-        tiled_hidden(g, s.X, s.W1eT, s.b1, s.Z);
-        __syncthreads();
-        logits(nb, s.F);
+        tiled_hidden_logits(g, s.X, s.W1eT, s.b1, s.Z, s.w2e, b2, s.F);
         __syncthreads();
         for (int b = tid; b < nb; b += THREADS) part += s.CO[b] * softplusf(s.F[b]);
         __syncthreads();
@@ -709,11 +725,10 @@ __global__ void __launch_bounds__(THREADS, 2) gail_update_tiled_kernel(const Gai
       const int nb = min(g.RB, B - b0);
       tiled_load_rows(g, pol, exp_, pass_eps[k], kind, b0, nb, s.X, s.CO, s.DF);
       __syncthreads();
-      tiled_hidden(g, s.X, s.W1eT, s.b1, s.Z);  // hidden = relu(W1e x + b1)
+      if (is_gp) tiled_hidden(g, s.X, s.W1eT, s.b1, s.Z);  // hidden = relu(W1e x + b1)
+      else tiled_hidden_logits(g, s.X, s.W1eT, s.b1, s.Z, s.w2e, b2, s.F);  // + logits
       __syncthreads();
       if (!is_gp) {
-        logits(nb, s.F);
-        __syncthreads();
         for (int b = tid; b < g.RB; b += THREADS) {
           float df = 0.f;
           if (b < nb) {
@@ -1001,12 +1016,12 @@ extern "C" int il_gail_update(il_handle* h, const il_gail_update_args* a, void* 
   cudaStream_t st = (cudaStream_t)stream;
   IL_LAUNCH(h, gail_tick_kernel, 1, 1, 0, st, a->opt.step);
   const int tiled_tiles = (p.g.H / 4) * ((p.g.d + 3) / 4);
-  if (h->gail_tiled && p.g.d <= 32 && (p.g.H == 32 || p.g.H == 64 || p.g.H == 128) && a->policy.B % 4 == 0 && tiled_tiles <= 256) {
+  if (h->gail_tiled && p.g.d <= 32 && (p.g.H == 32 || p.g.H == 64 || p.g.H == 128) && a->policy.B % 4 == 0 && tiled_tiles <= 256 && p.g.row % 4 == 0) {
     GailTiledParams tp;
     tp.a = *a;
     TDims& t = tp.g;
     t.S = p.g.S; t.A = p.g.A; t.d = p.g.d; t.DP = (p.g.d + 3) / 4 * 4; t.H = p.g.H; t.B = p.g.B; t.row = p.g.row; t.LDZ = p.g.H + 4; t.HD = (p.g.H * p.g.d + 3) / 4 * 4;
-    t.RB = a->policy.B < 128 ? (a->policy.B + 3) / 4 * 4 : 128;
+    t.RB = a->policy.B < 128 ? (a->policy.B + 15) / 16 * 16 : 128;  // multiple of 16: the tile loops (H / 4 x RB / 4 tiles) have warp-uniform trip counts
     tp.off_w1 = off[0]; tp.off_b1 = off[1]; tp.off_w2 = off[2]; tp.off_b2 = off[3];
     int64_t tsm = tiled_carve(t, nullptr, nullptr);
     while (tsm > 110 * 1024 && t.RB > 32) {  // wider nets: shorter row chunks keep two CTAs per SM

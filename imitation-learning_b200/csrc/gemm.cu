@@ -413,6 +413,93 @@ __global__ void __launch_bounds__(256, 2) first_layer_relu_kernel(const GemmArgs
   }
 }
 
+// Register-resident variant for N == 256 (one CTA = one net's whole [<= 256 rows] x [256 columns] first-layer output): each thread keeps the
+// K x 4 weights of its 4 columns packed as k-pairs in registers for all of its rows, the net's input rows sit in shared memory (one stage, one
+// barrier), and the row loop has no barriers and only warp-broadcast shared loads: per 2 rows x 4 columns 2*ceil(K/4) LDS.128 + 8*ceil(K/2)
+// FFMA2 + 2 STG.128. (ncu on first_layer_relu_kernel: 16 resident warps, issue-active 40 %, stalled on the shared-memory pipe — two 128-bit
+// weight loads per 8 FFMA2 — its per-32-row barriers and the strided weight prologue.) K is a template parameter so the weight registers are
+// statically indexed.
+template <int K>
+__global__ void __launch_bounds__(256, 2) first_layer_reg_kernel(const GemmArgs p) {
+  constexpr int KP = (K + 1) / 2, KQ = (K + 3) / 4, LDS_A = KQ * 4;
+  __shared__ __align__(16) float As[256 * LDS_A];
+  const int tid = threadIdx.x, g = blockIdx.y, m_base = blockIdx.x * 256;
+  const int rows = p.M - m_base < 256 ? p.M - m_base : 256;
+  const float* __restrict__ A = p.A + (int64_t)(g / p.a_gdiv) * p.a_gs + (int64_t)m_base * p.lda;
+  const float* __restrict__ W = p.B + (int64_t)(g / p.b_gdiv) * p.b_gs;
+  const int n = (tid & 63) * 4, tr = tid >> 6;
+  if (tid < rows) {  // stage the input rows (zero padded to a multiple of 4 columns)
+    const float* ar = A + (int64_t)tid * p.lda;
+    float v[LDS_A];
+#pragma unroll
+    for (int k = 0; k < LDS_A; ++k) v[k] = k < K ? __ldg(ar + k) : 0.f;
+#pragma unroll
+    for (int q = 0; q < KQ; ++q) *reinterpret_cast<float4*>(&As[tid * LDS_A + 4 * q]) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+  unsigned long long w[KP][4];
+  {  // rows n .. n + 3 of W [256][K] are 4 K contiguous floats starting on a 16-byte boundary
+    float f[4 * K];
+    const float4* src = reinterpret_cast<const float4*>(W + (int64_t)n * K);
+#pragma unroll
+    for (int q = 0; q < K; ++q) { const float4 x = __ldg(src + q); f[4 * q] = x.x; f[4 * q + 1] = x.y; f[4 * q + 2] = x.z; f[4 * q + 3] = x.w; }
+#pragma unroll
+    for (int kp = 0; kp < KP; ++kp)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float lo = f[c * K + 2 * kp], hi = 2 * kp + 1 < K ? f[c * K + 2 * kp + 1] : 0.f;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(w[kp][c]) : "f"(lo), "f"(hi));
+      }
+  }
+  const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + (int64_t)g * p.bias_gs + n));
+  unsigned long long b2[4];
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b2[0]) : "f"(bv.x), "f"(0.f));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b2[1]) : "f"(bv.y), "f"(0.f));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b2[2]) : "f"(bv.z), "f"(0.f));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b2[3]) : "f"(bv.w), "f"(0.f));
+  float* __restrict__ C = p.C + (int64_t)g * p.c_gs + (int64_t)m_base * p.ldc + n;
+  __syncthreads();
+  for (int r = tr; r < rows; r += 8) {  // rows r and r + 4 (rows is a multiple of 8)
+    unsigned long long a0[2 * KQ], a1[2 * KQ];
+#pragma unroll
+    for (int q = 0; q < KQ; ++q) {
+      const ulonglong2 x0 = *reinterpret_cast<const ulonglong2*>(&As[r * LDS_A + 4 * q]);        // warp-uniform address: broadcast
+      const ulonglong2 x1 = *reinterpret_cast<const ulonglong2*>(&As[(r + 4) * LDS_A + 4 * q]);
+      a0[2 * q] = x0.x; a0[2 * q + 1] = x0.y; a1[2 * q] = x1.x; a1[2 * q + 1] = x1.y;
+    }
+    unsigned long long acc0[4] = {b2[0], b2[1], b2[2], b2[3]}, acc1[4] = {b2[0], b2[1], b2[2], b2[3]};  // {bias + even-k partial, odd-k partial}
+#pragma unroll
+    for (int kp = 0; kp < KP; ++kp)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        acc0[c] = fl_fma2(a0[kp], w[kp][c], acc0[c]);
+        acc1[c] = fl_fma2(a1[kp], w[kp][c], acc1[c]);
+      }
+    float o0[4], o1[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float e, o;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(e), "=f"(o) : "l"(acc0[c]));
+      o0[c] = fmaxf(e + o, 0.f);
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(e), "=f"(o) : "l"(acc1[c]));
+      o1[c] = fmaxf(e + o, 0.f);
+    }
+    *reinterpret_cast<float4*>(C + (int64_t)r * p.ldc) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+    *reinterpret_cast<float4*>(C + (int64_t)(r + 4) * p.ldc) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+  }
+}
+
+bool first_layer_reg_eligible(const GemmArgs& a) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool k_ok = a.K == 11 || a.K == 12 || a.K == 14 || a.K == 15 || a.K == 16;  // hopper-sized inputs (state 11 (+1 absorbing), + 3 action columns)
+  return k_ok && a.N == 256 && a.M % 8 == 0 && a.ldb == a.K && al16(a.B) && a.b_gs % 4 == 0;
+}
+
+template <int K>
+static int launch_first_layer_reg(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
+  IL_LAUNCH(h, first_layer_reg_kernel<K>, dim3((a.M + 255) / 256, a.G), 256, 0, stream, a);
+  return 0;
+}
+
 bool first_layer_eligible(const GemmArgs& a) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   return a.a_kmajor && a.b_kmajor && a.K <= FL_K && a.N % FL_COLS == 0 && a.M % FL_ROWS == 0 && a.act == IL_ACT_RELU && a.bias && !a.mask && !a.colsum && !a.accumulate &&
@@ -532,13 +619,17 @@ __global__ void __launch_bounds__(256, 2) wide_tn_kernel(const GemmArgs p) {
   for (int j = 0; j < WT_MAXN; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (active) {
     const float* ap = A + col;
-    for (int k0 = tr; k0 < K; k0 += 16) {
-      float4 d[4];
+    float4 d[4], dn[4];
+    auto fetch = [&](float4 (&dst)[4], int k0) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int k = k0 + 4 * u;
-        d[u] = k < K ? __ldg(reinterpret_cast<const float4*>(ap + (int64_t)k * p.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dst[u] = k < K ? __ldg(reinterpret_cast<const float4*>(ap + (int64_t)k * p.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    };
+    fetch(d, tr);
+    for (int k0 = tr; k0 < K; k0 += 16) {
+      fetch(dn, k0 + 16);  // the next 4 rows are in flight while these 4 are consumed (ncu: 4.4 long-scoreboard stalls per issue without the prefetch)
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int k = k0 + 4 * u;
@@ -557,6 +648,8 @@ __global__ void __launch_bounds__(256, 2) wide_tn_kernel(const GemmArgs p) {
           }
         }
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) d[u] = dn[u];
     }
   }
 #pragma unroll
@@ -724,6 +817,15 @@ int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
     if (wide_a) IL_LAUNCH(h, gemm_stream_tn_kernel<true>, grid, 256, smem, stream, a);
     else IL_LAUNCH(h, gemm_stream_tn_kernel<false>, grid, 256, smem, stream, a);
     return 0;
+  }
+  if (h->first_layer_fast >= 2 && a.M > 16 && first_layer_eligible(a) && first_layer_reg_eligible(a)) {
+    switch (a.K) {
+      case 11: return launch_first_layer_reg<11>(h, a, stream);
+      case 12: return launch_first_layer_reg<12>(h, a, stream);
+      case 14: return launch_first_layer_reg<14>(h, a, stream);
+      case 15: return launch_first_layer_reg<15>(h, a, stream);
+      default: return launch_first_layer_reg<16>(h, a, stream);
+    }
   }
   if (h->first_layer_fast && a.M > 16 && first_layer_eligible(a)) {
     dim3 grid(a.N / FL_COLS, (a.M + FL_ROWS * FL_ITERS - 1) / (FL_ROWS * FL_ITERS), a.G);

@@ -609,7 +609,9 @@ int launch_adam(il_handle* h, float* params, const float* grads, const il_adam* 
   IL_CHECK(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(opt->m) | reinterpret_cast<uintptr_t>(opt->v) |
              reinterpret_cast<uintptr_t>(polyak_target)) & 15) == 0, "adam: buffers must be 16-byte aligned");
   if (h->adam_tma && n % 4 == 0 && n >= (int64_t)ADAM_TMA_MIN_TILES * h->sm_count * 2) {  // large flat buffers: TMA-staged streaming variant
-    switch (h->adam_tma) {  // (tile floats, stages, CTAs per SM): 20 B/float of shared memory per stage
+    // isolated launches on the bench buffers (profiles/r2_adam_variants.jsonl, copy = 6.5-6.6 TB/s): 9 streams 4096 x 2 = 6.55 TB/s, 7 streams 2048 x 4 = 6.57 TB/s
+    const int variant = h->adam_tma == 1 ? (polyak_target ? 2 : 7) : h->adam_tma;
+    switch (variant) {  // (tile floats, stages, CTAs per SM): 20 B/float of shared memory per stage
       case 2: return launch_adam_tma<4096, 2>(h, 1, params, grads, opt, n, stream, polyak_target, polyak_factor);
       case 3: return launch_adam_tma<2048, 3>(h, 1, params, grads, opt, n, stream, polyak_target, polyak_factor);
       case 4: return launch_adam_tma<1024, 4>(h, 2, params, grads, opt, n, stream, polyak_target, polyak_factor);
