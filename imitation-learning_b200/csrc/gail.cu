@@ -969,6 +969,66 @@ __global__ void __launch_bounds__(THREADS) gail_reward_kernel(const GailRewParam
   }
 }
 
+// predict_reward on the register-tiled forward (same helpers as gail_update_tiled_kernel): ~30 KB of shared memory instead of the update kernel's carve-up, so
+// several replicas share an SM (the first kernel ran one CTA per SM with two shared loads per FMA: 112 us per step for 39 MB of input).
+struct GailRewTiledParams { GailRewParams r; TDims g; };
+__host__ __device__ inline int64_t reward_tiled_floats(const TDims& g) {
+  auto r4 = [](int n) { return (n + 3) / 4 * 4; };
+  return r4(g.HD) + r4(g.DP * g.H) + 6 * r4(g.H) + r4(g.d) + r4(g.H > g.d ? g.H : g.d) + r4(g.RB * g.DP) + r4(g.RB * g.LDZ) + 3 * r4(g.RB) + 32;
+}
+__global__ void __launch_bounds__(THREADS, 3) gail_reward_tiled_kernel(const GailRewTiledParams tp) {
+  extern __shared__ __align__(16) float sm[];
+  const GailRewParams& p = tp.r;
+  const TDims g = tp.g;
+  const int r = blockIdx.x, tid = threadIdx.x, H = g.H, d = g.d, B = g.B, DP = g.DP;
+  int64_t o = 0;
+  auto take = [&](int n) { float* q = sm + o; o += (n + 3) / 4 * 4; return q; };
+  float *W1 = take(g.HD), *W1eT = take(DP * H), *b1 = take(H), *w2 = take(H), *w2e = take(H), *u1 = take(H), *v2 = take(H), *spare = take(H), *v1 = take(d), *tvec = take(H > d ? H : d);
+  float *X = take(g.RB * DP), *Z = take(g.RB * g.LDZ), *F = take(g.RB), *CO = take(g.RB), *DF = take(g.RB), *red = take(32);
+  (void)spare;
+  const float* prm = p.disc.g.params + (int64_t)r * p.disc.g.stride;
+  const bool sn = p.disc.u != nullptr;
+  for (int i = tid; i < H * d; i += THREADS) W1[i] = prm[p.off_w1 + i];
+  for (int h = tid; h < H; h += THREADS) {
+    b1[h] = prm[p.off_b1 + h]; w2[h] = prm[p.off_w2 + h];
+    if (sn) { u1[h] = p.disc.u[(int64_t)r * p.disc.u_stride + h]; v2[h] = p.disc.v[(int64_t)r * p.disc.v_stride + d + h]; }
+  }
+  if (sn) for (int j = tid; j < d; j += THREADS) v1[j] = p.disc.v[(int64_t)r * p.disc.v_stride + j];
+  const float b2 = prm[p.off_b2];
+  __syncthreads();
+  float sig1 = 1.f, sig2 = 1.f;
+  if (sn) {  // eval mode: no power iteration, sigma from the stored (u, v) (train.py:180,194)
+    sig1 = spectral_sigma(W1, u1, v1, tvec, red, H, d, false);
+    float t = 0.f;
+    for (int h = tid; h < H; h += THREADS) t = fmaf(w2[h], v2[h], t);
+    sig2 = p.disc.u[(int64_t)r * p.disc.u_stride + H] * bsum(t, red);
+  }
+  for (int i = tid; i < H * DP; i += THREADS) {
+    const int h = i / DP, j = i % DP;
+    W1eT[j * H + h] = j < d ? W1[h * d + j] / sig1 : 0.f;
+  }
+  for (int h = tid; h < H; h += THREADS) w2e[h] = w2[h] / sig2;
+  __syncthreads();
+  const float* rows = p.batch.rows + (int64_t)r * p.batch.replica_stride;
+  for (int b0 = 0; b0 < B; b0 += g.RB) {
+    const int nb = min(g.RB, B - b0);
+    tiled_load_rows(g, rows, rows, nullptr, PASS_POLICY, b0, nb, X, CO, DF);
+    __syncthreads();
+    tiled_hidden_logits(g, X, W1eT, b1, Z, w2e, b2, F);
+    __syncthreads();
+    for (int b = tid; b < nb; b += THREADS) {
+      const float f = F[b];
+      if (p.logits) p.logits[(int64_t)r * B + b0 + b] = f;
+      if (p.reward) {  // models.py:177-180
+        const float D = sigmoidf(f);
+        float hh = p.disc.reward_function == IL_REWARD_GAIL ? -log1pf(-D + 1e-6f) : logf(D + 1e-6f) - log1pf(-D + 1e-6f);
+        if (p.disc.reward_function == IL_REWARD_FAIRL) hh = expf(hh) * -hh;
+        p.reward[(int64_t)r * p.reward_rs + (int64_t)(b0 + b) * p.reward_ld] = hh;
+      }
+    }
+  }
+}
+
 __global__ void gail_tick_kernel(int64_t* s) { *s += 1; }
 
 int gail_setup(const il_gail* disc, const il_batch* batch, GailDims* g, int64_t* smem, int64_t off[4], const char* what) {
@@ -1053,6 +1113,18 @@ extern "C" int il_gail_reward(il_handle* h, const il_gail* disc, int R, const il
   IL_TRY(gail_setup(disc, batch, &p.g, &smem, off, "il_gail_reward"));
   p.off_w1 = off[0]; p.off_b1 = off[1]; p.off_w2 = off[2]; p.off_b2 = off[3];
   p.reward = reward; p.reward_rs = reward_rs; p.reward_ld = reward_ld; p.logits = logits;
+  if (h->gail_tiled && p.g.d <= 32 && (p.g.H == 32 || p.g.H == 64 || p.g.H == 128) && p.g.row % 4 == 0) {
+    GailRewTiledParams tp;
+    tp.r = p;
+    TDims& t = tp.g;
+    t.S = p.g.S; t.A = p.g.A; t.d = p.g.d; t.DP = (p.g.d + 3) / 4 * 4; t.H = p.g.H; t.B = p.g.B; t.row = p.g.row; t.LDZ = p.g.H + 4; t.HD = (p.g.H * p.g.d + 3) / 4 * 4;
+    t.RB = batch->B < 64 ? (batch->B + 15) / 16 * 16 : 64;
+    const int64_t tsm = reward_tiled_floats(t) * 4;
+    if (tsm <= 72 * 1024) {
+      IL_LAUNCH(h, gail_reward_tiled_kernel, R, THREADS, (size_t)tsm, (cudaStream_t)stream, tp);
+      return 0;
+    }
+  }
   IL_LAUNCH(h, gail_reward_kernel, R, THREADS, (size_t)smem, (cudaStream_t)stream, p);
   return 0;
 }
@@ -1064,6 +1136,7 @@ int gail_init() {
   IL_CUDA(cudaFuncSetAttribute(gail_update_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   IL_CUDA(cudaFuncSetAttribute(gail_update_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   IL_CUDA(cudaFuncSetAttribute(gail_reward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  IL_CUDA(cudaFuncSetAttribute(gail_reward_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
   IL_CUDA(cudaFuncSetAttribute(gail_update_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   IL_CUDA(cudaFuncSetAttribute(gail_update_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   IL_CUDA(cudaFuncSetAttribute(gail_update_tiled_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));

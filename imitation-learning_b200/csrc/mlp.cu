@@ -609,8 +609,10 @@ int launch_adam(il_handle* h, float* params, const float* grads, const il_adam* 
   IL_CHECK(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(opt->m) | reinterpret_cast<uintptr_t>(opt->v) |
              reinterpret_cast<uintptr_t>(polyak_target)) & 15) == 0, "adam: buffers must be 16-byte aligned");
   if (h->adam_tma && n % 4 == 0 && n >= (int64_t)ADAM_TMA_MIN_TILES * h->sm_count * 2) {  // large flat buffers: TMA-staged streaming variant
-    // isolated launches on the bench buffers (profiles/r2_adam_variants.jsonl, copy = 6.5-6.6 TB/s): 9 streams 4096 x 2 = 6.55 TB/s, 7 streams 2048 x 4 = 6.57 TB/s
-    const int variant = h->adam_tma == 1 ? (polyak_target ? 2 : 7) : h->adam_tma;
+    // Isolated launches on the bench buffers (profiles/r2_adam_variants.jsonl; copy = 6.5-6.6 TB/s): every geometry is within 8 % of the copy rate, the
+    // 1-CTA-per-SM ones (4096 x 2, 2048 x 4) are the fastest alone (6.55 TB/s) — but inside the step the 2-CTA-per-SM 2048 x 2 ring wins (6.49 vs 6.59
+    // ms / step, A/B in one gpurun call): its CTAs co-reside with the tail of the previous kernel and the head of the next.
+    const int variant = h->adam_tma;
     switch (variant) {  // (tile floats, stages, CTAs per SM): 20 B/float of shared memory per stage
       case 2: return launch_adam_tma<4096, 2>(h, 1, params, grads, opt, n, stream, polyak_target, polyak_factor);
       case 3: return launch_adam_tma<2048, 3>(h, 1, params, grads, opt, n, stream, polyak_target, polyak_factor);

@@ -74,7 +74,7 @@ struct Geo {
 constexpr int RING_BYTES = Geo<1>::RING_BYTES;
 static_assert(Geo<2>::RING_BYTES <= RING_BYTES, "the pair kernel uses the same shared-memory carve-up");
 static_assert(Geo<2, true>::RING_BYTES + Geo<2, true>::L1_BYTES <= RING_BYTES, "the fused-first-layer variant fits the same carve-up");
-constexpr int EPI_LD = 33;                                           // padded row of the epilogue staging tile
+constexpr int EPI_LD = 36;                                           // padded row of the epilogue staging tile: 144-byte rows keep 128-bit accesses aligned and conflict-free
 constexpr int EPI_BYTES = N_EPI_WARPS * 32 * EPI_LD * 4;
 constexpr int HEAD_MAX = 8;                                          // fused head: up to 8 output units (N = 1 critic, 2A <= 8 actor)
 constexpr int HEAD_BYTES = (BN + HEAD_MAX * BN) * 4;                 // bias [256] + head weights [8][256]
@@ -605,25 +605,35 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (EPI == 4) {  // bias + ReLU in registers (lane = row), then the head dot products with smem-broadcast weights
-          const float* bs = head_s + cb * 32;
+          const float4* bs = reinterpret_cast<const float4*>(head_s + cb * 32);  // 128-bit broadcast loads: the shared-memory pipe is the contended unit of this kernel
 #pragma unroll
-          for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(fmaxf(__uint_as_float(r[c]) + bs[c], 0.f));
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 b = bs[c4];
+            r[4 * c4] = __float_as_uint(fmaxf(__uint_as_float(r[4 * c4]) + b.x, 0.f));
+            r[4 * c4 + 1] = __float_as_uint(fmaxf(__uint_as_float(r[4 * c4 + 1]) + b.y, 0.f));
+            r[4 * c4 + 2] = __float_as_uint(fmaxf(__uint_as_float(r[4 * c4 + 2]) + b.z, 0.f));
+            r[4 * c4 + 3] = __float_as_uint(fmaxf(__uint_as_float(r[4 * c4 + 3]) + b.w, 0.f));
+          }
 #pragma unroll
           for (int j = 0; j < HEAD_MAX; ++j) {
             if (j < p.head_n) {
-              const float* ws = head_s + BN + j * BN + cb * 32;
+              const float4* ws = reinterpret_cast<const float4*>(head_s + BN + j * BN + cb * 32);
               float a = hacc[j];
 #pragma unroll
-              for (int c = 0; c < 32; ++c) a = fmaf(__uint_as_float(r[c]), ws[c], a);
+              for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 w = ws[c4];
+                a = fmaf(__uint_as_float(r[4 * c4]), w.x, a); a = fmaf(__uint_as_float(r[4 * c4 + 1]), w.y, a);
+                a = fmaf(__uint_as_float(r[4 * c4 + 2]), w.z, a); a = fmaf(__uint_as_float(r[4 * c4 + 3]), w.w, a);
+              }
               hacc[j] = a;
             }
           }
           if (!p.store_c) continue;
         }
-        // lane = row (32 rows of this warp), registers = 32 consecutive columns -> staging tile [row][col] (padded: no bank conflicts)
+        // lane = row (32 rows of this warp), registers = 32 consecutive columns -> staging tile [row][col] (36-float rows: the 128-bit stores of a quarter warp hit 32 distinct banks)
         const uint32_t wrow = stg + (uint32_t)(lane * EPI_LD * 4);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) asm volatile("st.shared.b32 [%0], %1;" ::"r"(wrow + c * 4), "r"(r[c]) : "memory");
+        for (int c = 0; c < 32; c += 4) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wrow + c * 4), "r"(r[c]), "r"(r[c + 1]), "r"(r[c + 2]), "r"(r[c + 3]) : "memory");
         __syncwarp();
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + cb * 32));
@@ -632,10 +642,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
         for (int pass = 0; pass < 8; ++pass) {
           const uint32_t rrow = stg + (uint32_t)(((pass * 4 + rsub) * EPI_LD + cq) * 4);
           float4 v;
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v.x) : "r"(rrow));
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v.y) : "r"(rrow + 4));
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v.z) : "r"(rrow + 8));
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v.w) : "r"(rrow + 12));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(rrow));
           const int64_t ro = (int64_t)(pass * 4) * g.ldc + cb * 32;
           if (EPI == 1) {
             v.x = fmaxf(v.x + bv.x, 0.f); v.y = fmaxf(v.y + bv.y, 0.f); v.z = fmaxf(v.z + bv.z, 0.f); v.w = fmaxf(v.w + bv.w, 0.f);

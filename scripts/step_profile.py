@@ -37,7 +37,7 @@ def main():
   prof.export_chrome_trace(trace)  # kernels launched by the library (and replayed from graphs) carry their names in the trace's "kernel" category
   for ev in json.load(open(trace))['traceEvents']:
     if ev.get('cat') != 'kernel': continue
-    name = re.sub(r'\(.*', '', ev['name']).replace('(anonymous namespace)::', '').replace('void ', '')
+    name = re.sub(r'\(.*', '', ev['name'].replace('(anonymous namespace)::', '').replace('<unnamed>::', '')).replace('void ', '')
     a = agg.setdefault(name, [0, 0.0])
     a[0] += 1
     a[1] += float(ev['dur'])
