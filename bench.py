@@ -353,7 +353,10 @@ def measure_dense_gemm(tr, a):
 def main():
   a = parse()
   if a.impl == 'reference': run_reference(a)
-  else: run_b200(a)
+  else:
+    run_b200(a)
+    from il_b200 import distributed
+    distributed.shutdown()
 
 
 if __name__ == '__main__':

@@ -608,26 +608,26 @@ __global__ void __launch_bounds__(256, 2) wide_tn_kernel(const GemmArgs p) {
   float4* red = reinterpret_cast<float4*>(wt_sm + K * WT_MAXN);
   const float* __restrict__ A = p.A + (int64_t)(g / p.a_gdiv) * p.a_gs;
   const float* __restrict__ B = p.B + (int64_t)(g / p.b_gdiv) * p.b_gs;
+  const bool active = col < p.M;
+  const float* ap = A + col;
+  float4 d[4], dn[4];
+  auto fetch = [&](float4 (&dst)[4], int k0) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + 4 * u;
+      dst[u] = (active && k < K) ? __ldg(reinterpret_cast<const float4*>(ap + (int64_t)k * p.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  fetch(d, tr);  // the first wide rows are in flight while the small operand is staged
   for (int i = tid; i < K * WT_MAXN; i += 256) {
     const int k = i / WT_MAXN, j = i % WT_MAXN;
     xs[i] = j < N ? __ldg(B + (int64_t)k * p.ldb + j) : 0.f;
   }
   __syncthreads();
-  const bool active = col < p.M;
   float4 acc[WT_MAXN], cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int j = 0; j < WT_MAXN; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (active) {
-    const float* ap = A + col;
-    float4 d[4], dn[4];
-    auto fetch = [&](float4 (&dst)[4], int k0) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int k = k0 + 4 * u;
-        dst[u] = k < K ? __ldg(reinterpret_cast<const float4*>(ap + (int64_t)k * p.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    fetch(d, tr);
     for (int k0 = tr; k0 < K; k0 += 16) {
       fetch(dn, k0 + 16);  // the next 4 rows are in flight while these 4 are consumed (ncu: 4.4 long-scoreboard stalls per issue without the prefetch)
 #pragma unroll
@@ -656,10 +656,12 @@ __global__ void __launch_bounds__(256, 2) wide_tn_kernel(const GemmArgs p) {
   for (int j = 0; j < WT_MAXN; ++j) red[(tr * (WT_MAXN + 1) + j) * 64 + tc] = acc[j];
   red[(tr * (WT_MAXN + 1) + WT_MAXN) * 64 + tc] = cs;
   __syncthreads();
-  if (tr == 0 && active) {
+  if (active) {  // every row group finishes a quarter of the outputs (fixed summation order over the 4 partials)
     float* __restrict__ C = p.C + (int64_t)g * p.c_gs;
 #pragma unroll
-    for (int j = 0; j <= WT_MAXN; ++j) {
+    for (int jj = 0; jj < (WT_MAXN + 4) / 4; ++jj) {
+      const int j = tr + 4 * jj;
+      if (j > WT_MAXN) continue;
       if (j < N || j == WT_MAXN) {
         float4 a = red[(0 * (WT_MAXN + 1) + j) * 64 + tc];
 #pragma unroll
@@ -687,6 +689,7 @@ bool wide_tn_eligible(const GemmArgs& a) {
 // B = a column slice of W_1 [K, N <= 8] (the action columns, training.py:36-41). One warp per row: the lanes own 4-wide slices of k (128-bit
 // coalesced loads of the row), their slice of B lives in registers for the whole CTA, 4 rows in flight, butterfly reduction per row.
 constexpr int RD_MAXN = 8, RD_MAXKV = 4;  // N <= 8 output columns, K <= 512 (K / 128 float4 per lane)
+constexpr int RD_ROWS = 256;              // rows per CTA: the register-resident slice of B is loaded once per 256 rows (was 64: the strided prologue dominated the CTA's life)
 template <int RD_MAXKV, int RD_MAXN>
 __global__ void __launch_bounds__(256) row_dot_kernel(const GemmArgs p) {
   const int g = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, N = p.N, kv = p.K / 128;
@@ -700,16 +703,21 @@ __global__ void __launch_bounds__(256) row_dot_kernel(const GemmArgs p) {
 #pragma unroll
       for (int j = 0; j < RD_MAXN; ++j) w[v][e][j] = (v < kv && j < N) ? __ldg(B + (int64_t)(v * 128 + lane * 4 + e) * p.ldb + j) : 0.f;
   float* __restrict__ C = p.C + (int64_t)g * p.c_gs;
-  const int rows_per_cta = 64, m_end = min(p.M, (int)(blockIdx.x + 1) * rows_per_cta);
-  for (int m0 = blockIdx.x * rows_per_cta + warp; m0 < m_end; m0 += 32) {  // rows m0, m0 + 8, m0 + 16, m0 + 24 in flight
-    float4 a[4][RD_MAXKV];
+  const int m_end = min(p.M, (int)(blockIdx.x + 1) * RD_ROWS);
+  constexpr bool PF = RD_MAXKV <= 2;  // the prefetch buffer does not fit next to a K = 512 slice of B
+  float4 a[4][RD_MAXKV], an[PF ? 4 : 1][RD_MAXKV];
+  auto fetch = [&](float4 (*dst)[RD_MAXKV], int m0) {  // rows m0, m0 + 8, m0 + 16, m0 + 24
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int v = 0; v < RD_MAXKV; ++v) {
         const int m = m0 + 8 * u;
-        a[u][v] = (v < kv && m < m_end) ? __ldg(reinterpret_cast<const float4*>(A + (int64_t)m * p.lda + v * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dst[u][v] = (v < kv && m < m_end) ? __ldg(reinterpret_cast<const float4*>(A + (int64_t)m * p.lda + v * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+  };
+  fetch(a, blockIdx.x * RD_ROWS + warp);
+  for (int m0 = blockIdx.x * RD_ROWS + warp; m0 < m_end; m0 += 32) {
+    if (PF) fetch(an, m0 + 32);  // the next 4 rows of this warp are in flight while these 4 are reduced
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int m = m0 + 8 * u;
@@ -730,6 +738,14 @@ __global__ void __launch_bounds__(256) row_dot_kernel(const GemmArgs p) {
         for (int j = 1; j < RD_MAXN; ++j) v = lane == j ? acc[j] : v;
         C[(int64_t)m * p.ldc + lane] = v;
       }
+    }
+    if (PF) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < RD_MAXKV; ++v) a[u][v] = an[PF ? u : 0][v];
+    } else if (m0 + 32 < m_end) {
+      fetch(a, m0 + 32);
     }
   }
 }
@@ -798,7 +814,7 @@ int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   IL_CHECK(!(a.accumulate && a.act >= 0), "gemm: accumulate with activation is not supported");
   const bool plain = !a.bias && a.act < 0 && !a.mask && !a.accumulate;
   if (h->wide_tn && row_dot_eligible(a)) {
-    const dim3 grid((a.M + 63) / 64, a.G);
+    const dim3 grid((a.M + RD_ROWS - 1) / RD_ROWS, a.G);
     if (a.K <= 256 && a.N <= 4) IL_LAUNCH(h, (row_dot_kernel<2, 4>), grid, 256, 0, stream, a);
     else if (a.K <= 256) IL_LAUNCH(h, (row_dot_kernel<2, 8>), grid, 256, 0, stream, a);
     else IL_LAUNCH(h, (row_dot_kernel<4, 8>), grid, 256, 0, stream, a);

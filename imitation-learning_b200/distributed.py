@@ -22,7 +22,8 @@ def init(backend: str = 'nccl') -> Tuple[int, int]:
   if world > 1 and not dist.is_initialized():
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
     os.environ.setdefault('MASTER_PORT', '29512')
-    dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    kw = dict(device_id=torch.device('cuda', torch.cuda.current_device())) if backend == 'nccl' else {}
+    dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
   return rank, world
 
 
@@ -85,3 +86,14 @@ def stats_from_sums(stats3: torch.Tensor) -> Tuple[float, float, int]:
 
 def barrier():
   if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1: dist.barrier()
+
+
+def shutdown():
+  """Destroys the library's NCCL communicator and the torch process group (end of train.py / bench.py)."""
+  global _nccl_comm
+  if _nccl_comm is not None:
+    _lib.check(_lib.lib().il_nccl_comm_destroy(_nccl_comm))
+    _nccl_comm = None
+  if dist.is_available() and dist.is_initialized():
+    dist.barrier()
+    dist.destroy_process_group()

@@ -427,4 +427,7 @@ def main(argv: Optional[List[str]] = None) -> float:
   cfg = load_config(sys.argv[1:] if argv is None else argv)
   out_dir = os.path.join(cfg.get('output_dir', './outputs'), f'{cfg.algorithm}_{cfg.env}', time.strftime('%m-%d_%H-%M-%S'))  # conf/train_config.yaml:54-60
   os.makedirs(out_dir, exist_ok=True)
-  return train(cfg, file_prefix=out_dir + os.sep)
+  try:
+    return train(cfg, file_prefix=out_dir + os.sep)
+  finally:
+    distributed.shutdown()
