@@ -225,8 +225,15 @@ __global__ void __launch_bounds__(256) mlp_small_forward_kernel(const SmallFwdAr
     const int r = idx / p.m.dims[0], k = idx % p.m.dims[0];
     bufs[0][r * maxd + k] = r < nr ? __ldg(X + (int64_t)(r0 + r) * p.ldx + k) : 0.f;
   }
-  __syncthreads();
   const float* prm = p.m.params + (int64_t)g * p.m.stride;
+  if (NR == 1) {
+    // The layers are dependent phases, each a latency-bound stream of its own weights: start the HBM fetch of ALL later layers now (L2 prefetch,
+    // one 128-byte line per instruction) so that they arrive while the first layer runs and the later phases read from L2.
+    const char* base = reinterpret_cast<const char*>(prm + p.o.w[L > 1 ? 1 : 0]);
+    const int64_t bytes = (int64_t)(p.o.total - p.o.w[L > 1 ? 1 : 0]) * 4;
+    for (int64_t i = (int64_t)tid * 128; i < bytes; i += 256 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + i));
+  }
+  __syncthreads();
   for (int l = 0; l < L; ++l) {
     const int in = p.m.dims[l], od = p.m.dims[l + 1];
     const float* W = prm + p.o.w[l];
