@@ -38,6 +38,8 @@ extern "C" int il_create(int device, il_handle** out) {
     h->wide_tn = (wt && wt[0] == '0') ? 0 : 1;
     const char* ff = getenv("IL_FIRST_LAYER_FAST");
     h->first_layer_fast = ff ? atoi(ff) : 2;  // 0 generic K-thin kernel, 1 FFMA2 kernel with shared-memory weights, 2 register-resident weights (N == 256)
+    const char* mb = getenv("IL_MASK_BITS");
+    h->mask_bits = (mb && mb[0] == '0') ? 0 : 1;
     const char* hf = getenv("IL_HEAD_FUSED");
     h->head_fused = (hf && hf[0] == '0') ? 0 : 1;
     const char* ds = getenv("IL_DEBUG_SYNC");
@@ -86,6 +88,7 @@ extern "C" int il_set_option(il_handle* h, const char* name, int value) {
   else if (!strcmp(name, "gail_tiled")) h->gail_tiled = value;
   else if (!strcmp(name, "adam_tma")) h->adam_tma = value;
   else if (!strcmp(name, "head_fused")) h->head_fused = value;
+  else if (!strcmp(name, "mask_bits")) h->mask_bits = value;
   else if (!strcmp(name, "first_layer_fast")) h->first_layer_fast = value;
   else if (!strcmp(name, "wide_tn")) h->wide_tn = value;
   else if (!strcmp(name, "tc_pairs")) { h->tc_pairs = value; h->tc_pair_groups = 0; }

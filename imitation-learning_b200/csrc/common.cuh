@@ -23,6 +23,7 @@ struct il_handle {
   int tc_pairs;                         // tcgen05 engine: use CTA pairs (cta_group::2) when rows are a multiple of 256 (IL_TC_PAIRS=0 disables)
   int wide_tn;                          // first-layer weight gradient: 128-bit row-group kernel (IL_WIDE_TN=0 keeps the column-streaming kernel)
   int first_layer_fast;                 // first MLP layer: specialised FFMA2 kernel for K <= 16 (IL_FIRST_LAYER_FAST=0 keeps the generic K-thin kernel)
+  int mask_bits;                        // ReLU masks of the MLP backward as sign-bit words written by the forward kernels (IL_MASK_BITS=0: fp32 activations as masks)
   int head_fused;                       // MLP backward: fused head kernel (dZ, dW_L, db_L, db_{L-1} in one pass; IL_HEAD_FUSED=0 disables)
   int debug_sync;                       // IL_DEBUG_SYNC=1: multi-kernel programs synchronise after every stage and name the one that failed
   int adam_tma;                         // AdamW: TMA-staged (cp.async.bulk) streaming kernel for large flat buffers (IL_ADAM_TMA=1 enables)
@@ -189,8 +190,15 @@ struct GemmArgs {
   int64_t colsum_gs;
   int accumulate;        // C += result (before activation; only with act == -1)
   int M, N, K, G;
+  // ReLU sign bits instead of fp32 activations where only the derivative mask is needed (1/32 of the bytes): word [m][n / 32], bit n % 32 set <=> output (m, n) > 0
+  const uint32_t* mask_bits;  // alternative to `mask` (mask_act == relu); honoured by the tcgen05 engine
+  int64_t mask_bits_gs;       // words per group
+  uint32_t* bits_out;         // optional extra output of the kernels that support it (first_layer_reg_kernel, the fused-head tcgen05 launch)
+  int64_t bits_out_gs;
 };
 int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream);
+bool gemm_uses_tc(const il_handle* h, const GemmArgs& a);                  // the dense tcgen05 engine takes this launch
+bool gemm_first_layer_emits_bits(const il_handle* h, const GemmArgs& a);   // first_layer_reg_kernel takes this launch (bits_out supported)
 double gemm_algorithmic_bytes(const GemmArgs& a, bool stores_c);
 int profile_open(il_handle* h, ProfiledLaunch* pl, double flops, double bytes, cudaStream_t stream);
 int profile_close(il_handle* h, ProfiledLaunch* pl, cudaStream_t stream);

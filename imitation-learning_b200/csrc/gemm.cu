@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(256, 2) first_layer_relu_kernel(const GemmArgs
 // FFMA2 + 2 STG.128. (ncu on first_layer_relu_kernel: 16 resident warps, issue-active 40 %, stalled on the shared-memory pipe — two 128-bit
 // weight loads per 8 FFMA2 — its per-32-row barriers and the strided weight prologue.) K is a template parameter so the weight registers are
 // statically indexed.
-template <int K>
+template <int K, bool BITS>
 __global__ void __launch_bounds__(256, 2) first_layer_reg_kernel(const GemmArgs p) {
   constexpr int KP = (K + 1) / 2, KQ = (K + 3) / 4, LDS_A = KQ * 4;
   __shared__ __align__(16) float As[256 * LDS_A];
@@ -485,6 +485,18 @@ __global__ void __launch_bounds__(256, 2) first_layer_reg_kernel(const GemmArgs 
     }
     *reinterpret_cast<float4*>(C + (int64_t)r * p.ldc) = make_float4(o0[0], o0[1], o0[2], o0[3]);
     *reinterpret_cast<float4*>(C + (int64_t)(r + 4) * p.ldc) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+    if (BITS) {  // sign-bit words for the backward mask: 8 consecutive lanes hold the 32 columns of one word (the row loop is warp-uniform)
+      const int lane = tid & 31, sh = 4 * (lane & 7);
+      uint32_t w0 = ((o0[0] > 0.f ? 1u : 0u) | (o0[1] > 0.f ? 2u : 0u) | (o0[2] > 0.f ? 4u : 0u) | (o0[3] > 0.f ? 8u : 0u)) << sh;
+      uint32_t w1 = ((o1[0] > 0.f ? 1u : 0u) | (o1[1] > 0.f ? 2u : 0u) | (o1[2] > 0.f ? 4u : 0u) | (o1[3] > 0.f ? 8u : 0u)) << sh;
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) { w0 |= __shfl_xor_sync(0xffffffffu, w0, o); w1 |= __shfl_xor_sync(0xffffffffu, w1, o); }
+      if ((lane & 7) == 0) {
+        uint32_t* bo = p.bits_out + (int64_t)g * p.bits_out_gs + (int64_t)(m_base + r) * 8 + ((tid & 63) >> 3);
+        bo[0] = w0;
+        bo[32] = w1;  // row r + 4
+      }
+    }
   }
 }
 
@@ -496,7 +508,8 @@ bool first_layer_reg_eligible(const GemmArgs& a) {
 
 template <int K>
 static int launch_first_layer_reg(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
-  IL_LAUNCH(h, first_layer_reg_kernel<K>, dim3((a.M + 255) / 256, a.G), 256, 0, stream, a);
+  if (a.bits_out) IL_LAUNCH(h, (first_layer_reg_kernel<K, true>), dim3((a.M + 255) / 256, a.G), 256, 0, stream, a);
+  else IL_LAUNCH(h, (first_layer_reg_kernel<K, false>), dim3((a.M + 255) / 256, a.G), 256, 0, stream, a);
   return 0;
 }
 
@@ -773,8 +786,12 @@ int launch_cfg(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
-static bool gemm_uses_tc(const il_handle* h, const GemmArgs& a) {
+bool gemm_uses_tc(const il_handle* h, const GemmArgs& a) {
   return a.M >= 128 && a.N >= 128 && a.K >= 128 && h->gemm_mode != IL_GEMM_FP32 && tc_gemm_eligible(a);
+}
+// launch_gemm routes this first-layer shape to first_layer_reg_kernel, which can also emit the ReLU sign-bit words
+bool gemm_first_layer_emits_bits(const il_handle* h, const GemmArgs& a) {
+  return h->first_layer_fast >= 2 && a.M > 16 && first_layer_eligible(a) && first_layer_reg_eligible(a);
 }
 
 int gemm_init() {
@@ -789,7 +806,8 @@ double gemm_algorithmic_bytes(const GemmArgs& a, bool stores_c) {
   const double ga = (a.G + a.a_gdiv - 1) / a.a_gdiv, gb = (a.G + a.b_gdiv - 1) / a.b_gdiv;
   double b = 4.0 * (ga * a.M * a.K + gb * a.K * a.N);
   if (stores_c) b += 4.0 * a.G * (double)a.M * a.N;
-  if (a.mask) b += 4.0 * a.G * (double)a.M * a.N;
+  if (a.mask_bits) b += 4.0 * a.G * (double)a.M * (a.N / 32);
+  else if (a.mask) b += 4.0 * a.G * (double)a.M * a.N;
   if (a.bias) b += 4.0 * a.G * a.N;
   return b;
 }
@@ -812,7 +830,9 @@ int launch_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   IL_CHECK(a.G <= 65535, "gemm: too many groups (%d)", a.G);
   IL_CHECK(!(a.colsum && a.a_kmajor), "gemm: colsum needs the [K, M] operand layout");
   IL_CHECK(!(a.accumulate && a.act >= 0), "gemm: accumulate with activation is not supported");
-  const bool plain = !a.bias && a.act < 0 && !a.mask && !a.accumulate;
+  const bool plain = !a.bias && a.act < 0 && !a.mask && !a.mask_bits && !a.accumulate;
+  IL_CHECK(!a.mask_bits || gemm_uses_tc(h, a), "gemm: sign-bit masks need the tcgen05 engine (M=%d N=%d K=%d)", a.M, a.N, a.K);
+  IL_CHECK(!a.bits_out || gemm_first_layer_emits_bits(h, a), "gemm: this launch cannot emit sign-bit words (M=%d N=%d K=%d)", a.M, a.N, a.K);
   if (h->wide_tn && row_dot_eligible(a)) {
     const dim3 grid((a.M + RD_ROWS - 1) / RD_ROWS, a.G);
     if (a.K <= 256 && a.N <= 4) IL_LAUNCH(h, (row_dot_kernel<2, 4>), grid, 256, 0, stream, a);

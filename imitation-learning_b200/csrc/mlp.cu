@@ -13,6 +13,7 @@ struct HeadBwdArgs {
   int n, H, Nh;
 };
 int launch_head_backward(il_handle* h, const HeadBwdArgs& a, int G, cudaStream_t stream);
+int launch_head_dx_bits(il_handle* h, const HeadBwdArgs& a, const uint32_t* bits, int64_t bits_gs, int G, cudaStream_t stream);
 
 int mlp_validate(const il_mlp* m, const char* what) {
   IL_CHECK(m != nullptr && m->params != nullptr, "%s: null mlp", what);
@@ -31,24 +32,35 @@ int mlp_max_hidden(const il_mlp* m) {
   return mx;
 }
 
+static int64_t mlp_bits_bytes(const il_mlp* m, int G, int n, int l) {  // sign-bit words of hidden layer l (0 when the width is not a multiple of 32)
+  return m->dims[l + 1] % 32 == 0 ? il_align_up((int64_t)G * n * (m->dims[l + 1] / 32) * 4, 256) : 0;
+}
+
 int64_t mlp_acts_bytes(const il_mlp* m, int G, int n) {
   int64_t b = 0;
-  for (int l = 0; l + 1 < m->n_layers; ++l) b += il_align_up((int64_t)G * n * m->dims[l + 1] * 4, 256);
+  for (int l = 0; l + 1 < m->n_layers; ++l) b += il_align_up((int64_t)G * n * m->dims[l + 1] * 4, 256) + mlp_bits_bytes(m, G, n, l);
   return b;
 }
 
 char* mlp_acts_carve(const il_mlp* m, int G, int n, char* ws, MlpActs* acts) {
-  for (int l = 0; l < IL_MAX_LAYERS; ++l) acts->hid[l] = nullptr;
+  for (int l = 0; l < IL_MAX_LAYERS; ++l) { acts->hid[l] = nullptr; acts->bits[l] = nullptr; acts->bits_valid[l] = false; }
   for (int l = 0; l + 1 < m->n_layers; ++l) {
     acts->hid[l] = reinterpret_cast<float*>(ws);
     ws += il_align_up((int64_t)G * n * m->dims[l + 1] * 4, 256);
+    if (mlp_bits_bytes(m, G, n, l)) {
+      acts->bits[l] = reinterpret_cast<uint32_t*>(ws);
+      ws += mlp_bits_bytes(m, G, n, l);
+    }
   }
   return ws;
 }
 
-int mlp_forward(il_handle* h, const il_mlp* m, int G, int n, MatView X, const MlpActs& acts, float* out, int64_t out_gs, int ld_out, cudaStream_t stream, bool keep_hidden) {
+int mlp_forward(il_handle* h, const il_mlp* m, int G, int n, MatView X, MlpActs& acts, float* out, int64_t out_gs, int ld_out, cudaStream_t stream, int keep) {
   const MlpOffsets o = mlp_offsets(m->dims, m->n_layers);
   const int L = m->n_layers;
+  const bool keep_hidden = keep != MLP_KEEP_NONE;
+  const bool want_bits = h->mask_bits && keep_hidden && m->activation == IL_ACT_RELU;
+  for (int l = 0; l < IL_MAX_LAYERS; ++l) acts.bits_valid[l] = false;
   auto layer_args = [&](int l) {
     GemmArgs a{};
     if (l == 0) { a.A = X.ptr; a.a_gs = X.gs; a.a_gdiv = X.gdiv; a.lda = X.ld; }
@@ -65,9 +77,12 @@ int mlp_forward(il_handle* h, const il_mlp* m, int G, int n, MatView X, const Ml
   const bool head_shape = L >= 2 && m->activation == IL_ACT_RELU && ld_out == m->dims[L] && out_gs == (int64_t)n * m->dims[L];
   for (int l = 0; l < L; ++l) {
     if (head_shape && l == L - 2) {
-      const GemmArgs a = layer_args(l);
+      GemmArgs a = layer_args(l);
       if (tc_head_fusable(h, a, m->dims[L])) {
-        IL_TRY(launch_tc_gemm_head(h, a, m->params + o.w[L - 1], m->params + o.b[L - 1], m->stride, m->dims[L], out, out_gs, keep_hidden ? 1 : 0, stream));
+        // MLP_KEEP_MASKS: an input-gradient pass needs the last hidden layer only as its ReLU mask -> sign bits (1/32 of the bytes) instead of the fp32 tile
+        const bool bits = want_bits && keep == MLP_KEEP_MASKS && acts.bits[l] && m->dims[L] <= HB_MAXN;
+        if (bits) { a.bits_out = acts.bits[l]; a.bits_out_gs = (int64_t)n * (m->dims[l + 1] / 32); acts.bits_valid[l] = true; }
+        IL_TRY(launch_tc_gemm_head(h, a, m->params + o.w[L - 1], m->params + o.b[L - 1], m->stride, m->dims[L], out, out_gs, keep_hidden && !bits ? 1 : 0, stream));
         return 0;
       }
     }
@@ -86,7 +101,12 @@ int mlp_forward(il_handle* h, const il_mlp* m, int G, int n, MatView X, const Ml
         return 0;
       }
     }
-    IL_TRY(launch_gemm(h, layer_args(l), stream));
+    GemmArgs a = layer_args(l);
+    if (want_bits && l + 1 < L && acts.bits[l] && gemm_first_layer_emits_bits(h, a)) {  // the mask of the next layer's input-gradient product
+      a.bits_out = acts.bits[l]; a.bits_out_gs = (int64_t)n * (m->dims[l + 1] / 32);
+      acts.bits_valid[l] = true;
+    }
+    IL_TRY(launch_gemm(h, a, stream));
   }
   return 0;
 }
@@ -120,6 +140,18 @@ int mlp_backward(il_handle* h, const il_mlp* m, int G, int n, MatView X, const M
       bias_done = true;
       continue;
     }
+    if (l == L - 1 && l > 0 && !grads && acts.bits_valid[l - 1] && m->dims[l + 1] <= HB_MAXN) {
+      // input-gradient pass: dZ_{L-2} = (dOut W_L) * 1[hidden > 0] straight from the sign-bit words (the hidden tile itself was never stored)
+      HeadBwdArgs a{};
+      a.dout = dZ.ptr; a.dout_gs = dZ.gs; a.dout_gdiv = dZ.gdiv; a.ld_dout = dZ.ld;
+      a.w = m->params + o.w[l]; a.w_gs = m->stride;
+      a.dz = next_tmp; a.dz_gs = (int64_t)n * m->dims[l];
+      a.n = n; a.H = m->dims[l]; a.Nh = m->dims[l + 1];
+      IL_TRY(launch_head_dx_bits(h, a, acts.bits[l - 1], (int64_t)n * (m->dims[l] / 32), G, stream));
+      dZ = MatView{next_tmp, (int64_t)n * m->dims[l], 1, m->dims[l]};
+      next_tmp = next_tmp == tmpA ? tmpB : tmpA;
+      continue;
+    }
     if (grads) {  // dW_l[o, i] = sum_b dZ[b, o] * Xin[b, i];  db_l[o] = sum_b dZ[b, o]
       GemmArgs a{};
       a.A = dZ.ptr; a.a_gs = dZ.gs; a.a_gdiv = dZ.gdiv; a.lda = dZ.ld; a.a_kmajor = 0;
@@ -135,8 +167,13 @@ int mlp_backward(il_handle* h, const il_mlp* m, int G, int n, MatView X, const M
       a.A = dZ.ptr; a.a_gs = dZ.gs; a.a_gdiv = dZ.gdiv; a.lda = dZ.ld; a.a_kmajor = 1;
       a.B = m->params + o.w[l]; a.b_gs = m->stride; a.b_gdiv = 1; a.ldb = m->dims[l]; a.b_kmajor = 0;
       a.C = next_tmp; a.c_gs = (int64_t)n * m->dims[l]; a.ldc = m->dims[l]; a.act = -1;
-      a.mask = acts.hid[l - 1]; a.mask_gs = (int64_t)n * m->dims[l]; a.ldmask = m->dims[l]; a.mask_act = m->activation;
+      a.mask_act = m->activation;
       a.M = n; a.N = m->dims[l]; a.K = m->dims[l + 1]; a.G = G;
+      if (acts.bits_valid[l - 1] && m->activation == IL_ACT_RELU && gemm_uses_tc(h, a)) {  // ReLU mask from the sign-bit words: 8 KB instead of 256 KB per 256 x 256 tile
+        a.mask_bits = acts.bits[l - 1]; a.mask_bits_gs = (int64_t)n * (m->dims[l] / 32);
+      } else {
+        a.mask = acts.hid[l - 1]; a.mask_gs = (int64_t)n * m->dims[l]; a.ldmask = m->dims[l];
+      }
       IL_TRY(launch_gemm(h, a, stream));
       dZ = MatView{next_tmp, (int64_t)n * m->dims[l], 1, m->dims[l]};
       next_tmp = next_tmp == tmpA ? tmpB : tmpA;
@@ -632,6 +669,42 @@ int launch_adam(il_handle* h, float* params, const float* grads, const il_adam* 
   }
   IL_LAUNCH(h, adam_kernel, ew_blocks(n / 4 + 1, 256, h->sm_count), 256, 0, stream, params, grads, opt->m, opt->v, opt->step, opt->lr, opt->beta1, opt->beta2, opt->eps,
             opt->weight_decay, n, polyak_target, polyak_factor, (float)(1.0 - (double)polyak_factor));
+  return 0;
+}
+
+namespace {
+// Input-gradient pass through the linear head when the last hidden activation exists only as ReLU sign bits (MLP_KEEP_MASKS):
+// dZ[b, o] = (sum_j dOut[b, j] W_L[j, o]) * bit(b, o). One CTA per (net, 256 hidden columns): thread = 4 columns x every 4th row, W_L columns in
+// registers, 128-bit stores; reads 1/32 of what the fp32 mask would cost.
+__global__ void __launch_bounds__(256) head_dx_bits_kernel(const HeadBwdArgs p, const uint32_t* __restrict__ bits, int64_t bits_gs) {
+  const int g = blockIdx.y, tid = threadIdx.x, tc = tid & 63, tr = tid >> 6, col = blockIdx.x * 256 + tc * 4;
+  if (col >= p.H) return;
+  const float* __restrict__ dout = p.dout + (int64_t)(g / p.dout_gdiv) * p.dout_gs;
+  const uint32_t* __restrict__ bw = bits + (int64_t)g * bits_gs + (col >> 5);
+  const int sh = col & 31, wpr = p.H >> 5;
+  float4 w[HB_MAXN];
+#pragma unroll
+  for (int j = 0; j < HB_MAXN; ++j) w[j] = j < p.Nh ? __ldg(reinterpret_cast<const float4*>(p.w + (int64_t)g * p.w_gs + (int64_t)j * p.H + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float* __restrict__ dz = p.dz + (int64_t)g * p.dz_gs + col;
+  for (int b = tr; b < p.n; b += 4) {
+    const uint32_t m = __ldg(bw + (int64_t)b * wpr) >> sh;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < HB_MAXN; ++j)
+      if (j < p.Nh) {
+        const float d = __ldg(dout + (int64_t)b * p.ld_dout + j);
+        v.x = fmaf(d, w[j].x, v.x); v.y = fmaf(d, w[j].y, v.y); v.z = fmaf(d, w[j].z, v.z); v.w = fmaf(d, w[j].w, v.w);
+      }
+    v.x = m & 1u ? v.x : 0.f; v.y = m & 2u ? v.y : 0.f; v.z = m & 4u ? v.z : 0.f; v.w = m & 8u ? v.w : 0.f;
+    *reinterpret_cast<float4*>(dz + (int64_t)b * p.H) = v;
+  }
+}
+}  // namespace
+
+int launch_head_dx_bits(il_handle* h, const HeadBwdArgs& a, const uint32_t* bits, int64_t bits_gs, int G, cudaStream_t stream) {
+  IL_CHECK(a.H % 32 == 0 && a.Nh <= HB_MAXN && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0 && a.w_gs % 4 == 0 && (reinterpret_cast<uintptr_t>(a.dz) & 15) == 0 && a.dz_gs % 4 == 0,
+           "head_dx_bits: H=%d Nh=%d or unaligned buffers", a.H, a.Nh);
+  IL_LAUNCH(h, head_dx_bits_kernel, dim3((a.H + 255) / 256, G), 256, 0, stream, a, bits, bits_gs);
   return 0;
 }
 

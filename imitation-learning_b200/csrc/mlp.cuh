@@ -12,7 +12,12 @@ struct MatView {
 
 struct MlpActs {  // outputs of the hidden layers ([G, n, dims[l+1]] contiguous), kept for the backward pass
   float* hid[IL_MAX_LAYERS];
+  // ReLU sign bits of the same outputs ([G, n, dims[l+1] / 32] words): what a backward pass needs of an activation that only serves as the derivative mask.
+  // Carved for widths that are multiples of 32; bits_valid[l] is set by mlp_forward when the kernel that produced hid[l] also wrote the words.
+  uint32_t* bits[IL_MAX_LAYERS];
+  bool bits_valid[IL_MAX_LAYERS];
 };
+enum { MLP_KEEP_NONE = 0, MLP_KEEP_ALL = 1, MLP_KEEP_MASKS = 2 };  // what the forward pass keeps: nothing / activations for a full backward / only what an input-gradient pass needs
 
 // Bytes for the hidden activations of G nets on n rows (il_align_up'ed per buffer).
 int64_t mlp_acts_bytes(const il_mlp* m, int G, int n);
@@ -20,10 +25,11 @@ int64_t mlp_acts_bytes(const il_mlp* m, int G, int n);
 char* mlp_acts_carve(const il_mlp* m, int G, int n, char* ws, MlpActs* acts);
 
 // Forward of G nets: out[g] ([n, dims[L]], row stride ld_out, group stride out_gs) = net_g(X[g]).
-// keep_hidden == false: the hidden activations are not needed afterwards (no backward pass follows), which lets the
-// fused head epilogue skip writing the last hidden layer.
-int mlp_forward(il_handle* h, const il_mlp* m, int G, int n, MatView X, const MlpActs& acts, float* out, int64_t out_gs, int ld_out,
-                cudaStream_t stream, bool keep_hidden = true);
+// keep == MLP_KEEP_NONE: the hidden activations are not needed afterwards (no backward pass follows), which lets the fused head epilogue skip
+// writing the last hidden layer. MLP_KEEP_MASKS: only mlp_backward(grads = nullptr, dX) follows — the last hidden layer is kept as sign bits only
+// when the kernels support it. (bool arguments convert: false = NONE, true = ALL.)
+int mlp_forward(il_handle* h, const il_mlp* m, int G, int n, MatView X, MlpActs& acts, float* out, int64_t out_gs, int ld_out,
+                cudaStream_t stream, int keep = MLP_KEEP_ALL);
 
 // Backward of G nets from dOut (gradient at the linear head), using the saved hidden outputs.
 //  grads != nullptr : parameter gradients written in the flat parameter layout (net stride grad_stride).

@@ -266,7 +266,8 @@ extern "C" int il_sac_update(il_handle* h, const il_sac_args* a, void* stream) {
     IL_TRY(launch_actor_head(h, ha, st));
   }
   const float* lp_new = a->out_log_probs ? a->out_log_probs : w.lp_next;
-  IL_TRY(mlp_forward(h, &a->critic, 2 * R, B, MatView{w.xn, (int64_t)B * d, 2, d}, w.critic_acts, w.q, (int64_t)B, 1, st));
+  // only the action gradient of Q(s, pi(s)) is needed (no critic parameter gradients): the hidden layers are kept as ReLU sign bits where the kernels allow
+  IL_TRY(mlp_forward(h, &a->critic, 2 * R, B, MatView{w.xn, (int64_t)B * d, 2, d}, w.critic_acts, w.q, (int64_t)B, 1, st, MLP_KEEP_MASKS));
   IL_LAUNCH(h, sac_actor_loss_kernel, R, 256, 0, st, w.q, lp_new, a->log_alpha, rows, rs, row, L.weight, av, w.dq, a->out_losses, B);
   IL_TRY(mlp_backward(h, &a->critic, 2 * R, B, MatView{w.xn, (int64_t)B * d, 2, d}, w.critic_acts, MatView{w.dq, (int64_t)B, 1, 1}, nullptr, 0, w.dxa, (int64_t)B * A, A, S,
                       A, w.tmpA, w.tmpB, st));

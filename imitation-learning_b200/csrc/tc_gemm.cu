@@ -262,7 +262,7 @@ struct ChunkMap {  // chunk j of a thread: global chunk id ptid + j * PT over [A
   }
 };
 
-// EPI: 0 plain store, 1 bias + relu, 2 relu-derivative mask, 3 generic (runtime bias / activation / mask),
+// EPI: 0 plain store, 1 bias + relu, 2 relu-derivative mask, 3 generic (runtime bias / activation / mask), 5 relu-derivative mask from sign-bit words,
 //      4 bias + relu + fused linear head (the next, final layer of the MLP computed from the accumulator row in registers)
 template <int EPI, int CG, bool FUSE = false>
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
@@ -628,7 +628,18 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
               hacc[j] = a;
             }
           }
+          if (g.bits_out) {  // sign bits of this row's 32 hidden outputs: all a dX-only backward pass needs of them (1/32 of the bytes)
+            uint32_t word = 0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) word |= (__uint_as_float(r[c]) > 0.f ? 1u : 0u) << c;
+            g.bits_out[(int64_t)grp * g.bits_out_gs + (int64_t)(m0 + warp * 32 + lane) * (BN / 32) + cb] = word;
+          }
           if (!p.store_c) continue;
+        }
+        if (EPI == 5) {  // ReLU derivative from the sign-bit words the forward kernel wrote (lane = row, register c = column cb * 32 + c)
+          const uint32_t word = __ldg(g.mask_bits + (int64_t)grp * g.mask_bits_gs + (int64_t)(m0 + warp * 32 + lane) * (BN / 32) + cb);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) r[c] = (word >> c) & 1u ? r[c] : 0u;
         }
         // lane = row (32 rows of this warp), registers = 32 consecutive columns -> staging tile [row][col] (36-float rows: the 128-bit stores of a quarter warp hit 32 distinct banks)
         const uint32_t wrow = stg + (uint32_t)(lane * EPI_LD * 4);
@@ -717,6 +728,7 @@ int tc_gemm_init() {
   IL_TRY((tc_set_attr<0, 1>())); IL_TRY((tc_set_attr<1, 1>())); IL_TRY((tc_set_attr<2, 1>())); IL_TRY((tc_set_attr<3, 1>())); IL_TRY((tc_set_attr<4, 1>()));
   IL_TRY((tc_set_attr<0, 2>())); IL_TRY((tc_set_attr<1, 2>())); IL_TRY((tc_set_attr<2, 2>())); IL_TRY((tc_set_attr<3, 2>())); IL_TRY((tc_set_attr<4, 2>()));
   IL_TRY((tc_set_attr<4, 2, true>()));
+  IL_TRY((tc_set_attr<5, 1>())); IL_TRY((tc_set_attr<5, 2>()));
   return 0;
 }
 
@@ -808,10 +820,14 @@ int launch_tc_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
   TcParams p{};
   p.g = a;
   p.split = h->gemm_mode == IL_GEMM_TF32X3 ? 1 : 0;
-  const bool plain = !a.bias && a.act < 0 && !a.mask;
+  const bool bits = a.mask_bits != nullptr;  // sign-bit mask: takes precedence over an fp32 mask of the same activation
+  IL_CHECK(!bits || (!a.bias && a.act < 0 && a.mask_act == IL_ACT_RELU), "tc_gemm: sign-bit masks are the ReLU derivative of a plain product");
+  if (bits) p.g.mask = nullptr;
+  const bool plain = !a.bias && a.act < 0 && !a.mask && !bits;
   const bool bias_relu = a.bias && a.act == IL_ACT_RELU && !a.mask;
-  const bool mask_relu = !a.bias && a.act < 0 && a.mask && a.mask_act == IL_ACT_RELU;
-  if (plain) IL_TRY(tc_launch<0>(h, p, stream));
+  const bool mask_relu = !a.bias && a.act < 0 && a.mask && a.mask_act == IL_ACT_RELU && !bits;
+  if (bits) IL_TRY(tc_launch<5>(h, p, stream));
+  else if (plain) IL_TRY(tc_launch<0>(h, p, stream));
   else if (bias_relu) IL_TRY(tc_launch<1>(h, p, stream));
   else if (mask_relu) IL_TRY(tc_launch<2>(h, p, stream));
   else IL_TRY(tc_launch<3>(h, p, stream));
