@@ -39,7 +39,7 @@ extern "C" int il_create(int device, il_handle** out) {
     const char* ff = getenv("IL_FIRST_LAYER_FAST");
     h->first_layer_fast = ff ? atoi(ff) : 2;  // 0 generic K-thin kernel, 1 FFMA2 kernel with shared-memory weights, 2 register-resident weights (N == 256)
     const char* mb = getenv("IL_MASK_BITS");
-    h->mask_bits = (mb && mb[0] == '0') ? 0 : 1;
+    h->mask_bits = mb ? atoi(mb) : 2;  // 0: fp32 activations as masks; 1: sign-bit words; 2: + the input-gradient slice fused into the masked dX launch
     const char* hf = getenv("IL_HEAD_FUSED");
     h->head_fused = (hf && hf[0] == '0') ? 0 : 1;
     const char* ds = getenv("IL_DEBUG_SYNC");

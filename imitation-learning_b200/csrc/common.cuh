@@ -222,5 +222,7 @@ struct TcFuseL1 {
 // dense hidden layer + bias + ReLU with the following (final, <= 8 units) linear layer fused into the epilogue
 bool tc_head_fusable(const il_handle* h, const GemmArgs& a, int head_n);
 bool tc_l1_fusable(const il_handle* h, const GemmArgs& a, int x_k);
+bool tc_dx_head_fusable(const il_handle* h, const GemmArgs& a, int head_n);
+int launch_tc_gemm_dx_head(il_handle* h, const GemmArgs& a, const float* w, int64_t w_gs, int w_ns, int head_n, float* out, int64_t out_gs, cudaStream_t stream);
 int launch_tc_gemm_head(il_handle* h, const GemmArgs& a, const float* head_w, const float* head_b, int64_t head_gs, int head_n, float* head_out, int64_t head_out_gs, int store_c,
                         cudaStream_t stream, const TcFuseL1* l1 = nullptr);

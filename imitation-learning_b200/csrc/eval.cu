@@ -187,7 +187,7 @@ static int eval_build_impl(il_handle* h, EvalGraph* eg, const il_eval_args* a, f
       MlpActs acts;
       char* w2 = mlp_acts_carve(&a->actor, R, E, ws, &acts);
       float* head = reinterpret_cast<float*>(w2);
-      rc = mlp_forward(h, &a->actor, R, E, X, acts, head, (int64_t)E * 2 * act, 2 * act, st);
+      rc = mlp_forward(h, &a->actor, R, E, X, acts, head, (int64_t)E * 2 * act, 2 * act, st, MLP_KEEP_NONE);
       if (rc == 0) {
         HeadFwdArgs ha{};
         ha.head = head; ha.action = action; ha.action_rs = (int64_t)E * act; ha.ld_action = act; ha.R = R; ha.n = E; ha.A = act;

@@ -458,7 +458,8 @@ __global__ void __launch_bounds__(256, 2) first_layer_reg_kernel(const GemmArgs 
   asm("mov.b64 %0, {%1, %2};" : "=l"(b2[3]) : "f"(bv.w), "f"(0.f));
   float* __restrict__ C = p.C + (int64_t)g * p.c_gs + (int64_t)m_base * p.ldc + n;
   __syncthreads();
-  for (int r = tr; r < rows; r += 8) {  // rows r and r + 4 (rows is a multiple of 8)
+  // rows r and r + 4: outputs in o0 / o1 (also stored), returns the two sign nibbles {row r | row r + 4 << 4}
+  auto two_rows = [&](int r) -> uint32_t {
     unsigned long long a0[2 * KQ], a1[2 * KQ];
 #pragma unroll
     for (int q = 0; q < KQ; ++q) {
@@ -485,18 +486,32 @@ __global__ void __launch_bounds__(256, 2) first_layer_reg_kernel(const GemmArgs 
     }
     *reinterpret_cast<float4*>(C + (int64_t)r * p.ldc) = make_float4(o0[0], o0[1], o0[2], o0[3]);
     *reinterpret_cast<float4*>(C + (int64_t)(r + 4) * p.ldc) = make_float4(o1[0], o1[1], o1[2], o1[3]);
-    if (BITS) {  // sign-bit words for the backward mask: 8 consecutive lanes hold the 32 columns of one word (the row loop is warp-uniform)
-      const int lane = tid & 31, sh = 4 * (lane & 7);
-      uint32_t w0 = ((o0[0] > 0.f ? 1u : 0u) | (o0[1] > 0.f ? 2u : 0u) | (o0[2] > 0.f ? 4u : 0u) | (o0[3] > 0.f ? 8u : 0u)) << sh;
-      uint32_t w1 = ((o1[0] > 0.f ? 1u : 0u) | (o1[1] > 0.f ? 2u : 0u) | (o1[2] > 0.f ? 4u : 0u) | (o1[3] > 0.f ? 8u : 0u)) << sh;
+    if (!BITS) return 0u;
+    return (o0[0] > 0.f ? 1u : 0u) | (o0[1] > 0.f ? 2u : 0u) | (o0[2] > 0.f ? 4u : 0u) | (o0[3] > 0.f ? 8u : 0u) | (o1[0] > 0.f ? 16u : 0u) | (o1[1] > 0.f ? 32u : 0u) |
+           (o1[2] > 0.f ? 64u : 0u) | (o1[3] > 0.f ? 128u : 0u);
+  };
+  if (!BITS) {
+    for (int r = tr; r < rows; r += 8) two_rows(r);  // rows is a multiple of 8
+    return;
+  }
+  // Sign-bit words for the backward mask (word = 32 columns = the nibbles of 8 consecutive lanes). The nibbles of 8 rows are collected in one register
+  // (nibble i <-> row rb + 8 (i / 2) + 4 (i % 2)) and an 8 x 8 nibble transpose over the 8 lanes (3 butterfly steps, one shuffle each) leaves lane l with
+  // the complete word of row i = l: 3 shuffles per 8 rows instead of 3 per row. rows % 32 == 0 (launch condition).
+  const int l = tid & 7;
+  for (int rb = tr; rb < rows; rb += 32) {
+    uint32_t V = 0;
 #pragma unroll
-      for (int o = 1; o < 8; o <<= 1) { w0 |= __shfl_xor_sync(0xffffffffu, w0, o); w1 |= __shfl_xor_sync(0xffffffffu, w1, o); }
-      if ((lane & 7) == 0) {
-        uint32_t* bo = p.bits_out + (int64_t)g * p.bits_out_gs + (int64_t)(m_base + r) * 8 + ((tid & 63) >> 3);
-        bo[0] = w0;
-        bo[32] = w1;  // row r + 4
-      }
+    for (int q = 0; q < 4; ++q) V |= two_rows(rb + 8 * q) << (8 * q);
+#pragma unroll
+    for (int d = 4; d >= 1; d >>= 1) {
+      const uint32_t md = d == 4 ? 0xFFFF0000u : (d == 2 ? 0xFF00FF00u : 0xF0F0F0F0u);  // nibbles whose index has bit d set
+      const bool hi = (l & d) != 0;
+      const uint32_t send = hi ? (V & ~md) << (4 * d) : (V & md) >> (4 * d);
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, d);
+      V = (hi ? (V & md) : (V & ~md)) | recv;
     }
+    const int row = rb + 8 * (l >> 1) + 4 * (l & 1);
+    p.bits_out[(int64_t)g * p.bits_out_gs + (int64_t)(m_base + row) * 8 + ((tid & 63) >> 3)] = V;
   }
 }
 
@@ -791,7 +806,7 @@ bool gemm_uses_tc(const il_handle* h, const GemmArgs& a) {
 }
 // launch_gemm routes this first-layer shape to first_layer_reg_kernel, which can also emit the ReLU sign-bit words
 bool gemm_first_layer_emits_bits(const il_handle* h, const GemmArgs& a) {
-  return h->first_layer_fast >= 2 && a.M > 16 && first_layer_eligible(a) && first_layer_reg_eligible(a);
+  return h->first_layer_fast >= 2 && a.M > 16 && a.M % 32 == 0 && first_layer_eligible(a) && first_layer_reg_eligible(a);
 }
 
 int gemm_init() {

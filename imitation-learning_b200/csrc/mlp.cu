@@ -171,6 +171,12 @@ int mlp_backward(il_handle* h, const il_mlp* m, int G, int n, MatView X, const M
       a.M = n; a.N = m->dims[l]; a.K = m->dims[l + 1]; a.G = G;
       if (acts.bits_valid[l - 1] && m->activation == IL_ACT_RELU && gemm_uses_tc(h, a)) {  // ReLU mask from the sign-bit words: 8 KB instead of 256 KB per 256 x 256 tile
         a.mask_bits = acts.bits[l - 1]; a.mask_bits_gs = (int64_t)n * (m->dims[l] / 32);
+        if (h->mask_bits >= 2 && l == 1 && !grads && dX && ld_dx == dx_cols && dx_gs == (int64_t)n * dx_cols && tc_dx_head_fusable(h, a, dx_cols)) {
+          // input-gradient pass: dZ_0 is only an intermediate of dX = dZ_0 W_1[:, cols] — the thin product runs in the epilogue on the masked rows, dZ_0 is never stored
+          a.C = nullptr;
+          IL_TRY(launch_tc_gemm_dx_head(h, a, m->params + o.w[0] + dx_col0, m->stride, m->dims[0], dx_cols, dX, dx_gs, stream));
+          return 0;
+        }
       } else {
         a.mask = acts.hid[l - 1]; a.mask_gs = (int64_t)n * m->dims[l]; a.ldmask = m->dims[l];
       }
@@ -676,27 +682,38 @@ namespace {
 // Input-gradient pass through the linear head when the last hidden activation exists only as ReLU sign bits (MLP_KEEP_MASKS):
 // dZ[b, o] = (sum_j dOut[b, j] W_L[j, o]) * bit(b, o). One CTA per (net, 256 hidden columns): thread = 4 columns x every 4th row, W_L columns in
 // registers, 128-bit stores; reads 1/32 of what the fp32 mask would cost.
+template <int NH, int U>  // NH: compile-time bound on the head width; U rows in flight per thread (all their word / dOut loads are issued before the first store)
 __global__ void __launch_bounds__(256) head_dx_bits_kernel(const HeadBwdArgs p, const uint32_t* __restrict__ bits, int64_t bits_gs) {
   const int g = blockIdx.y, tid = threadIdx.x, tc = tid & 63, tr = tid >> 6, col = blockIdx.x * 256 + tc * 4;
   if (col >= p.H) return;
   const float* __restrict__ dout = p.dout + (int64_t)(g / p.dout_gdiv) * p.dout_gs;
   const uint32_t* __restrict__ bw = bits + (int64_t)g * bits_gs + (col >> 5);
   const int sh = col & 31, wpr = p.H >> 5;
-  float4 w[HB_MAXN];
+  float4 w[NH];
 #pragma unroll
-  for (int j = 0; j < HB_MAXN; ++j) w[j] = j < p.Nh ? __ldg(reinterpret_cast<const float4*>(p.w + (int64_t)g * p.w_gs + (int64_t)j * p.H + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < NH; ++j) w[j] = j < p.Nh ? __ldg(reinterpret_cast<const float4*>(p.w + (int64_t)g * p.w_gs + (int64_t)j * p.H + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
   float* __restrict__ dz = p.dz + (int64_t)g * p.dz_gs + col;
-  for (int b = tr; b < p.n; b += 4) {
-    const uint32_t m = __ldg(bw + (int64_t)b * wpr) >> sh;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b0 = tr; b0 < p.n; b0 += 4 * U) {
+    uint32_t m[U];
+    float d[U][NH];
 #pragma unroll
-    for (int j = 0; j < HB_MAXN; ++j)
-      if (j < p.Nh) {
-        const float d = __ldg(dout + (int64_t)b * p.ld_dout + j);
-        v.x = fmaf(d, w[j].x, v.x); v.y = fmaf(d, w[j].y, v.y); v.z = fmaf(d, w[j].z, v.z); v.w = fmaf(d, w[j].w, v.w);
-      }
-    v.x = m & 1u ? v.x : 0.f; v.y = m & 2u ? v.y : 0.f; v.z = m & 4u ? v.z : 0.f; v.w = m & 8u ? v.w : 0.f;
-    *reinterpret_cast<float4*>(dz + (int64_t)b * p.H) = v;
+    for (int u = 0; u < U; ++u) {
+      const int b = b0 + 4 * u;
+      m[u] = b < p.n ? __ldg(bw + (int64_t)b * wpr) >> sh : 0u;
+#pragma unroll
+      for (int j = 0; j < NH; ++j) d[u][j] = (j < p.Nh && b < p.n) ? __ldg(dout + (int64_t)b * p.ld_dout + j) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int b = b0 + 4 * u;
+      if (b >= p.n) break;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < NH; ++j)
+        if (j < p.Nh) { v.x = fmaf(d[u][j], w[j].x, v.x); v.y = fmaf(d[u][j], w[j].y, v.y); v.z = fmaf(d[u][j], w[j].z, v.z); v.w = fmaf(d[u][j], w[j].w, v.w); }
+      v.x = m[u] & 1u ? v.x : 0.f; v.y = m[u] & 2u ? v.y : 0.f; v.z = m[u] & 4u ? v.z : 0.f; v.w = m[u] & 8u ? v.w : 0.f;
+      *reinterpret_cast<float4*>(dz + (int64_t)b * p.H) = v;
+    }
   }
 }
 }  // namespace
@@ -704,7 +721,8 @@ __global__ void __launch_bounds__(256) head_dx_bits_kernel(const HeadBwdArgs p, 
 int launch_head_dx_bits(il_handle* h, const HeadBwdArgs& a, const uint32_t* bits, int64_t bits_gs, int G, cudaStream_t stream) {
   IL_CHECK(a.H % 32 == 0 && a.Nh <= HB_MAXN && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0 && a.w_gs % 4 == 0 && (reinterpret_cast<uintptr_t>(a.dz) & 15) == 0 && a.dz_gs % 4 == 0,
            "head_dx_bits: H=%d Nh=%d or unaligned buffers", a.H, a.Nh);
-  IL_LAUNCH(h, head_dx_bits_kernel, dim3((a.H + 255) / 256, G), 256, 0, stream, a, bits, bits_gs);
+  if (a.Nh == 1) IL_LAUNCH(h, (head_dx_bits_kernel<1, 8>), dim3((a.H + 255) / 256, G), 256, 0, stream, a, bits, bits_gs);
+  else IL_LAUNCH(h, (head_dx_bits_kernel<HB_MAXN, 4>), dim3((a.H + 255) / 256, G), 256, 0, stream, a, bits, bits_gs);
   return 0;
 }
 
@@ -778,7 +796,7 @@ extern "C" int il_actor_forward(il_handle* h, const il_mlp* actor, int R, int n,
   char* ws = mlp_acts_carve(actor, R, n, static_cast<char*>(workspace), &acts);
   float* head = reinterpret_cast<float*>(ws);
   if (n <= 32) IL_TRY(mlp_small_forward(h, actor, R, n, MatView{states, states_rs, 1, ld_states}, head, (cudaStream_t)stream));
-  else IL_TRY(mlp_forward(h, actor, R, n, MatView{states, states_rs, 1, ld_states}, acts, head, (int64_t)n * out, out, (cudaStream_t)stream));
+  else IL_TRY(mlp_forward(h, actor, R, n, MatView{states, states_rs, 1, ld_states}, acts, head, (int64_t)n * out, out, (cudaStream_t)stream, MLP_KEEP_NONE));
   HeadFwdArgs a{};
   a.head = head; a.eps = eps; a.given = given_action;
   a.action = action; a.action_rs = (int64_t)n * (out / 2); a.ld_action = out / 2;
@@ -809,7 +827,7 @@ extern "C" int il_critic_forward(il_handle* h, const il_mlp* twin, int R, int n,
   IL_CHECK(S > 0 && A > 0, "il_critic_forward: S=%d with input width %d", S, d);
   const int64_t total = (int64_t)R * n * d;
   IL_LAUNCH(h, concat_kernel, (unsigned)((total + 255) / 256), 256, 0, st, states, states_rs, ld_states, S, actions, actions_rs, ld_actions, A, X, R, n);
-  IL_TRY(mlp_forward(h, twin, 2 * R, n, MatView{X, (int64_t)n * d, 2, d}, acts, q, (int64_t)n, 1, st));
+  IL_TRY(mlp_forward(h, twin, 2 * R, n, MatView{X, (int64_t)n * d, 2, d}, acts, q, (int64_t)n, 1, st, MLP_KEEP_NONE));
   IL_LAUNCH(h, split_twin_kernel, (unsigned)(((int64_t)R * n + 255) / 256), 256, 0, st, q, q1, q2, R, n);
   return 0;
 }

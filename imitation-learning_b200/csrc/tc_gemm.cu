@@ -199,6 +199,7 @@ struct TcParams {
   float* head_out;
   int64_t head_gs, head_out_gs;  // group strides of head_w / head_b (same buffer family) and of head_out
   int head_n, store_c;           // head units (<= HEAD_MAX); store_c == 0: the hidden output itself is not needed (no backward)
+  int head_js, head_ns;          // strides (floats) of head_w between head units j and between the BN contraction indices n: [head_n][BN] row-major = (BN, 1)
   TcFuseL1 l1;                   // FUSE: the first layer whose output is this product's A operand
   int l1_vec;                    // W1 rows are 16-byte multiples (K0 % 4 == 0): 16-byte staging copies
 };
@@ -263,6 +264,7 @@ struct ChunkMap {  // chunk j of a thread: global chunk id ptid + j * PT over [A
 };
 
 // EPI: 0 plain store, 1 bias + relu, 2 relu-derivative mask, 3 generic (runtime bias / activation / mask), 5 relu-derivative mask from sign-bit words,
+//      6 = 5 followed by a fused thin product of the masked tile (the input-gradient slice dX = dZ_0 W_1[:, cols], <= 8 columns; the tile itself is not stored),
 //      4 bias + relu + fused linear head (the next, final layer of the MLP computed from the accumulator row in registers)
 template <int EPI, int CG, bool FUSE = false>
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
@@ -579,13 +581,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
       tc_fence_after();
       float* C = g.C + (int64_t)grp * g.c_gs + (int64_t)(m0 + warp * 32 + rsub) * g.ldc + cq;
       float hacc[HEAD_MAX];
-      if (EPI == 4) {  // stage this group's bias and head weights once per tile for the 4 epilogue warps
+      if (EPI == 4 || EPI == 6) {  // stage this group's bias and head weights once per tile for the 4 epilogue warps
         asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done
         const int et = threadIdx.x;  // 0..127
-        const float* bsrc = g.bias + (int64_t)grp * g.bias_gs;
         const float* wsrc = p.head_w + (int64_t)grp * p.head_gs;
-        for (int i = et; i < BN; i += 128) head_s[i] = __ldg(bsrc + i);
-        for (int i = et; i < p.head_n * BN; i += 128) head_s[BN + i] = __ldg(wsrc + i);
+        if (EPI == 4) {
+          const float* bsrc = g.bias + (int64_t)grp * g.bias_gs;
+          for (int i = et; i < BN; i += 128) head_s[i] = __ldg(bsrc + i);
+        }
+        for (int i = et; i < p.head_n * BN; i += 128) head_s[BN + i] = __ldg(wsrc + (int64_t)(i / BN) * p.head_js + (int64_t)(i % BN) * p.head_ns);
         asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
         for (int j = 0; j < HEAD_MAX; ++j) hacc[j] = 0.f;
@@ -636,10 +640,27 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
           }
           if (!p.store_c) continue;
         }
-        if (EPI == 5) {  // ReLU derivative from the sign-bit words the forward kernel wrote (lane = row, register c = column cb * 32 + c)
+        if (EPI == 5 || EPI == 6) {  // ReLU derivative from the sign-bit words the forward kernel wrote (lane = row, register c = column cb * 32 + c)
           const uint32_t word = __ldg(g.mask_bits + (int64_t)grp * g.mask_bits_gs + (int64_t)(m0 + warp * 32 + lane) * (BN / 32) + cb);
 #pragma unroll
           for (int c = 0; c < 32; ++c) r[c] = (word >> c) & 1u ? r[c] : 0u;
+        }
+        if (EPI == 6) {  // the next (thin) product on the masked row in registers: hacc[j] += sum_c r[c] * W[c, j]
+#pragma unroll
+          for (int j = 0; j < HEAD_MAX; ++j) {
+            if (j < p.head_n) {
+              const float4* ws = reinterpret_cast<const float4*>(head_s + BN + j * BN + cb * 32);
+              float a = hacc[j];
+#pragma unroll
+              for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 w = ws[c4];
+                a = fmaf(__uint_as_float(r[4 * c4]), w.x, a); a = fmaf(__uint_as_float(r[4 * c4 + 1]), w.y, a);
+                a = fmaf(__uint_as_float(r[4 * c4 + 2]), w.z, a); a = fmaf(__uint_as_float(r[4 * c4 + 3]), w.w, a);
+              }
+              hacc[j] = a;
+            }
+          }
+          if (!p.store_c) continue;
         }
         // lane = row (32 rows of this warp), registers = 32 consecutive columns -> staging tile [row][col] (36-float rows: the 128-bit stores of a quarter warp hit 32 distinct banks)
         const uint32_t wrow = stg + (uint32_t)(lane * EPI_LD * 4);
@@ -673,12 +694,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcParams p) {
         }
         __syncwarp();
       }
-      if (EPI == 4) {
+      if (EPI == 4 || EPI == 6) {
         float* ho = p.head_out + (int64_t)grp * p.head_out_gs + (int64_t)(m0 + warp * 32 + lane) * p.head_n;
-        const float* hb = p.head_b + (int64_t)grp * p.head_gs;
+        const float* hb = p.head_b ? p.head_b + (int64_t)grp * p.head_gs : nullptr;
 #pragma unroll
         for (int j = 0; j < HEAD_MAX; ++j)
-          if (j < p.head_n) ho[j] = hacc[j] + __ldg(hb + j);
+          if (j < p.head_n) ho[j] = hacc[j] + (hb ? __ldg(hb + j) : 0.f);
       }
       tc_fence_before();
       __syncwarp();
@@ -728,7 +749,7 @@ int tc_gemm_init() {
   IL_TRY((tc_set_attr<0, 1>())); IL_TRY((tc_set_attr<1, 1>())); IL_TRY((tc_set_attr<2, 1>())); IL_TRY((tc_set_attr<3, 1>())); IL_TRY((tc_set_attr<4, 1>()));
   IL_TRY((tc_set_attr<0, 2>())); IL_TRY((tc_set_attr<1, 2>())); IL_TRY((tc_set_attr<2, 2>())); IL_TRY((tc_set_attr<3, 2>())); IL_TRY((tc_set_attr<4, 2>()));
   IL_TRY((tc_set_attr<4, 2, true>()));
-  IL_TRY((tc_set_attr<5, 1>())); IL_TRY((tc_set_attr<5, 2>()));
+  IL_TRY((tc_set_attr<5, 1>())); IL_TRY((tc_set_attr<5, 2>())); IL_TRY((tc_set_attr<6, 1>())); IL_TRY((tc_set_attr<6, 2>()));
   return 0;
 }
 
@@ -792,6 +813,7 @@ int launch_tc_gemm_head(il_handle* h, const GemmArgs& a, const float* head_w, co
   p.g = a;
   p.split = h->gemm_mode == IL_GEMM_TF32X3 ? 1 : 0;
   p.head_w = head_w; p.head_b = head_b; p.head_out = head_out; p.head_gs = head_gs; p.head_out_gs = head_out_gs; p.head_n = head_n; p.store_c = store_c;
+  p.head_js = BN; p.head_ns = 1;
   double bytes = gemm_algorithmic_bytes(a, store_c != 0) + 4.0 * a.G * (double)a.M * head_n, flops = 2.0 * a.M * a.N * a.K * a.G;
   if (l1) {
     IL_CHECK(tc_l1_fusable(h, a, l1->x_k), "tc_gemm_head: first layer not fusable (K0=%d)", l1->x_k);
@@ -813,6 +835,30 @@ int launch_tc_gemm_head(il_handle* h, const GemmArgs& a, const float* head_w, co
     return rc;
   }
   return run();
+}
+
+// dX-only backward of a depth-2 ReLU net in one launch: T = (A B) * relu'(bits) on the tensor cores (never stored), then out[g, m, j] = sum_n T[m, n] w[n * w_ns + j]
+// for head_n <= 8 columns in the epilogue (the input-gradient slice of the first layer, training.py:36-41).
+bool tc_dx_head_fusable(const il_handle* h, const GemmArgs& a, int head_n) {
+  return h->gemm_mode != IL_GEMM_FP32 && a.M >= 128 && a.K >= 128 && tc_gemm_eligible(a) && a.mask_bits && !a.mask && !a.bias && a.act < 0 && !a.colsum && a.mask_act == IL_ACT_RELU &&
+         head_n >= 1 && head_n <= HEAD_MAX;
+}
+int launch_tc_gemm_dx_head(il_handle* h, const GemmArgs& a, const float* w, int64_t w_gs, int w_ns, int head_n, float* out, int64_t out_gs, cudaStream_t stream) {
+  IL_CHECK(tc_dx_head_fusable(h, a, head_n), "tc_gemm_dx_head: not fusable");
+  TcParams p{};
+  p.g = a;
+  p.split = h->gemm_mode == IL_GEMM_TF32X3 ? 1 : 0;
+  p.head_w = w; p.head_b = nullptr; p.head_out = out; p.head_gs = w_gs; p.head_out_gs = out_gs; p.head_n = head_n; p.store_c = 0;
+  p.head_js = 1; p.head_ns = w_ns;
+  const double bytes = gemm_algorithmic_bytes(a, false) + 4.0 * a.G * (double)a.M * head_n, flops = 2.0 * a.M * a.N * a.K * a.G;
+  if (h->profiling) {
+    ProfiledLaunch pl;
+    IL_TRY(profile_open(h, &pl, flops, bytes, stream));
+    const int rc = tc_launch<6>(h, p, stream);
+    IL_TRY(profile_close(h, &pl, stream));
+    return rc;
+  }
+  return tc_launch<6>(h, p, stream);
 }
 
 int launch_tc_gemm(il_handle* h, const GemmArgs& a, cudaStream_t stream) {
