@@ -108,3 +108,27 @@ def test_fused_first_layer_is_schedule_independent():
   assert not bad, '\n'.join(bad)
   for r in (1, 37, 73, 74, 79):
     for k in keys: assert np.array_equal(outs[r][k], outs[0][k]), f'replica {r} differs from replica 0 in {k}'
+
+
+def test_sign_bit_masks_equal_fp32_masks():
+  """ReLU derivative masks as sign-bit words (written by the first-layer kernel and the fused-head tcgen05 epilogue, read by the masked dX launches)
+  against fp32 activations as masks: the same `> 0` predicate on the same values, so one SAC update of the 256-wide fixture is bit-identical
+  (option 1); with the input-gradient slice fused into the masked dX launch (option 2, the default) only the summation order of that thin product
+  changes."""
+  from cuda_cases import run_cuda
+  from il_b200 import _lib
+  from oracle import cases
+  lib, h = _lib.lib(), _lib.handle()
+  inp = cases.make_inputs('sac_hopper')
+  outs = {}
+  _lib.check(lib.il_set_gemm_mode(h, _lib.GEMM_MODE['tf32x3']))
+  try:
+    for level in (0, 1, 2):
+      _lib.set_option('mask_bits', level)
+      outs[level] = run_cuda('sac_hopper', [inp])[0]
+  finally:
+    _lib.set_option('mask_bits', 2)
+    _lib.check(lib.il_set_gemm_mode(h, _lib.GEMM_MODE['fp32']))
+  for k in outs[0]:
+    assert np.array_equal(outs[0][k], outs[1][k]), k
+    np.testing.assert_allclose(outs[2][k], outs[0][k], rtol=2e-5, atol=2e-6, err_msg=k)
