@@ -345,6 +345,11 @@ __device__ __forceinline__ unsigned long long fl_fma2(unsigned long long a, unsi
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+__device__ __forceinline__ unsigned long long fl_mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __global__ void __launch_bounds__(256, 2) first_layer_relu_kernel(const GemmArgs p) {
   __shared__ __align__(16) float Ws[(FL_K / 2) * FL_COLS * 2];  // [k pair][n][2]
   __shared__ __align__(16) float As[FL_ROWS][FL_K];
@@ -422,6 +427,9 @@ __global__ void __launch_bounds__(256, 2) first_layer_relu_kernel(const GemmArgs
 template <int K, bool BITS>
 __global__ void __launch_bounds__(256, 2) first_layer_reg_kernel(const GemmArgs p) {
   constexpr int KP = (K + 1) / 2, KQ = (K + 3) / 4, LDS_A = KQ * 4;
+  // odd K: the zero-padded last k slot carries the bias instead (input 1, weight b): the accumulators start from a product, not from a {bias, 0}
+  // register pair that has to be rebuilt (2 MOVs) for each of the 8 accumulators of every iteration
+  constexpr bool BIAS_COL = (K % 2) == 1;
   __shared__ __align__(16) float As[256 * LDS_A];
   const int tid = threadIdx.x, g = blockIdx.y, m_base = blockIdx.x * 256;
   const int rows = p.M - m_base < 256 ? p.M - m_base : 256;
@@ -432,10 +440,12 @@ __global__ void __launch_bounds__(256, 2) first_layer_reg_kernel(const GemmArgs 
     const float* ar = A + (int64_t)tid * p.lda;
     float v[LDS_A];
 #pragma unroll
-    for (int k = 0; k < LDS_A; ++k) v[k] = k < K ? __ldg(ar + k) : 0.f;
+    for (int k = 0; k < LDS_A; ++k) v[k] = k < K ? __ldg(ar + k) : ((BIAS_COL && k == K) ? 1.f : 0.f);
 #pragma unroll
     for (int q = 0; q < KQ; ++q) *reinterpret_cast<float4*>(&As[tid * LDS_A + 4 * q]) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
+  const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + (int64_t)g * p.bias_gs + n));
+  const float bvc[4] = {bv.x, bv.y, bv.z, bv.w};
   unsigned long long w[KP][4];
   {  // rows n .. n + 3 of W [256][K] are 4 K contiguous floats starting on a 16-byte boundary
     float f[4 * K];
@@ -446,11 +456,10 @@ __global__ void __launch_bounds__(256, 2) first_layer_reg_kernel(const GemmArgs 
     for (int kp = 0; kp < KP; ++kp)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const float lo = f[c * K + 2 * kp], hi = 2 * kp + 1 < K ? f[c * K + 2 * kp + 1] : 0.f;
+        const float lo = f[c * K + 2 * kp], hi = 2 * kp + 1 < K ? f[c * K + 2 * kp + 1] : (BIAS_COL ? bvc[c] : 0.f);
         asm("mov.b64 %0, {%1, %2};" : "=l"(w[kp][c]) : "f"(lo), "f"(hi));
       }
   }
-  const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + (int64_t)g * p.bias_gs + n));
   unsigned long long b2[4];
   asm("mov.b64 %0, {%1, %2};" : "=l"(b2[0]) : "f"(bv.x), "f"(0.f));
   asm("mov.b64 %0, {%1, %2};" : "=l"(b2[1]) : "f"(bv.y), "f"(0.f));
@@ -467,9 +476,14 @@ __global__ void __launch_bounds__(256, 2) first_layer_reg_kernel(const GemmArgs 
       const ulonglong2 x1 = *reinterpret_cast<const ulonglong2*>(&As[(r + 4) * LDS_A + 4 * q]);
       a0[2 * q] = x0.x; a0[2 * q + 1] = x0.y; a1[2 * q] = x1.x; a1[2 * q + 1] = x1.y;
     }
-    unsigned long long acc0[4] = {b2[0], b2[1], b2[2], b2[3]}, acc1[4] = {b2[0], b2[1], b2[2], b2[3]};  // {bias + even-k partial, odd-k partial}
+    unsigned long long acc0[4], acc1[4];  // {bias + even-k partial, odd-k partial}
 #pragma unroll
-    for (int kp = 0; kp < KP; ++kp)
+    for (int c = 0; c < 4; ++c) {
+      acc0[c] = BIAS_COL ? fl_mul2(a0[0], w[0][c]) : fl_fma2(a0[0], w[0][c], b2[c]);
+      acc1[c] = BIAS_COL ? fl_mul2(a1[0], w[0][c]) : fl_fma2(a1[0], w[0][c], b2[c]);
+    }
+#pragma unroll
+    for (int kp = 1; kp < KP; ++kp)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         acc0[c] = fl_fma2(a0[kp], w[kp][c], acc0[c]);
@@ -663,11 +677,15 @@ __global__ void __launch_bounds__(256, 2) wide_tn_kernel(const GemmArgs p) {
         const int k = k0 + 4 * u;
         if (k >= K) continue;
         cs.x += d[u].x; cs.y += d[u].y; cs.z += d[u].z; cs.w += d[u].w;
+        // the whole (zero padded) row of the small operand first — four independent broadcast loads — then the FMAs: with one load in front of each
+        // group of 16 FMAs the warp stalled on the shared-memory scoreboard four times per row (ncu: 2.4 short-scoreboard stalls per issue)
+        float4 xv[WT_MAXN / 4];
+#pragma unroll
+        for (int q = 0; q < WT_MAXN / 4; ++q) xv[q] = *reinterpret_cast<const float4*>(xs + k * WT_MAXN + 4 * q);
 #pragma unroll
         for (int q = 0; q < WT_MAXN / 4; ++q) {
           if (q * 4 < N) {
-            const float4 xv = *reinterpret_cast<const float4*>(xs + k * WT_MAXN + 4 * q);
-            const float xj[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float xj[4] = {xv[q].x, xv[q].y, xv[q].z, xv[q].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float4& a = acc[q * 4 + e];

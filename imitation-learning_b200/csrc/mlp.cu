@@ -269,13 +269,6 @@ __global__ void __launch_bounds__(256) mlp_small_forward_kernel(const SmallFwdAr
     bufs[0][r * maxd + k] = r < nr ? __ldg(X + (int64_t)(r0 + r) * p.ldx + k) : 0.f;
   }
   const float* prm = p.m.params + (int64_t)g * p.m.stride;
-  if (NR == 1) {
-    // The layers are dependent phases, each a latency-bound stream of its own weights: start the HBM fetch of ALL later layers now (L2 prefetch,
-    // one 128-byte line per instruction) so that they arrive while the first layer runs and the later phases read from L2.
-    const char* base = reinterpret_cast<const char*>(prm + p.o.w[L > 1 ? 1 : 0]);
-    const int64_t bytes = (int64_t)(p.o.total - p.o.w[L > 1 ? 1 : 0]) * 4;
-    for (int64_t i = (int64_t)tid * 128; i < bytes; i += 256 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + i));
-  }
   __syncthreads();
   for (int l = 0; l < L; ++l) {
     const int in = p.m.dims[l], od = p.m.dims[l + 1];
@@ -284,9 +277,63 @@ __global__ void __launch_bounds__(256) mlp_small_forward_kernel(const SmallFwdAr
     const float* xin = bufs[l & 1];
     float* xout = bufs[(l + 1) & 1];
     const bool vec = (in % 4 == 0) && (p.m.stride % 4 == 0);
+    if (NR == 1 && vec && in <= 16) {
+      // single row, thin layer (the state input of the rollout, train.py:152): one output unit per thread, its whole weight row in flight at once
+      for (int o = tid; o < od; o += 256) {
+        const float4* wr = reinterpret_cast<const float4*>(W + (int64_t)o * in);
+        float4 w4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w4[q] = 4 * q < in ? __ldg(wr + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float v = __ldg(bias + o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (4 * q < in) {
+            const float4 x4 = *reinterpret_cast<const float4*>(xin + 4 * q);
+            v = fmaf(w4[q].x, x4.x, fmaf(w4[q].y, x4.y, fmaf(w4[q].z, x4.z, fmaf(w4[q].w, x4.w, v))));
+          }
+        if (l < L - 1) v = act_apply(v, p.m.activation);
+        xout[o] = v;
+      }
+      __syncthreads();
+      continue;
+    }
+    if (NR == 1 && vec && in % 128 == 0 && in <= 256) {
+      // single row, wide layer: the kernel is a pure weight stream and its layers are dependent phases, so what matters is how many bytes each warp
+      // has in flight per round trip: EIGHT weight rows (8 output units, 16 x 128-bit loads per lane) are issued together and reduced together
+      // (ncu on the 4-rows-per-round version: 2.4 TB/s, long-scoreboard bound: 16 dependent load rounds per warp for a 256 x 256 layer, now 4)
+      const int kv = in >> 7;
+      float4 x4[2];
+#pragma unroll
+      for (int v = 0; v < 2; ++v) x4[v] = v < kv ? *reinterpret_cast<const float4*>(xin + v * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int o0 = warp * 8; o0 < od; o0 += 64) {
+        float4 w4[8][2];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int v = 0; v < 2; ++v)
+            w4[u][v] = (o0 + u < od && v < kv) ? __ldg(reinterpret_cast<const float4*>(W + (int64_t)(o0 + u) * in + v * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float a8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float t = 0.f;
+#pragma unroll
+          for (int v = 0; v < 2; ++v) t = fmaf(w4[u][v].x, x4[v].x, fmaf(w4[u][v].y, x4[v].y, fmaf(w4[u][v].z, x4[v].z, fmaf(w4[u][v].w, x4[v].w, t))));
+          a8[u] = warp_sum(t);
+        }
+        if (lane < 8 && o0 + lane < od) {
+          float v = a8[0];
+#pragma unroll
+          for (int u = 1; u < 8; ++u) v = lane == u ? a8[u] : v;
+          v += __ldg(bias + o0 + lane);
+          if (l < L - 1) v = act_apply(v, p.m.activation);
+          xout[o0 + lane] = v;
+        }
+      }
+      __syncthreads();
+      continue;
+    }
     if (NR == 1 && vec) {
-      // single row (the training rollout, train.py:152): the kernel is a pure weight stream, so every warp keeps FOUR weight rows in flight
-      // (4 output units per iteration, 128-bit loads) and reduces them together — the one-row-at-a-time loop was latency-bound at 1.7 TB/s
+      // single row, other widths: every warp keeps FOUR weight rows in flight (4 output units per iteration, 128-bit loads) and reduces them together
       for (int o0 = warp * 4; o0 < od; o0 += 32) {
         float a4[4] = {0.f, 0.f, 0.f, 0.f};
         for (int k = lane * 4; k < in; k += 128) {
