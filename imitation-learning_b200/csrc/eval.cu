@@ -29,6 +29,7 @@ namespace {
 struct EvalStepParams {
   il_env env;
   int n;                 // R * episodes environments
+  int act_E, act_EP;     // the action of environment e sits at row (e / act_E) * act_EP + e % act_E (padded rows per replica on the tensor-core path; E == EP otherwise)
   const float* action;   // [n, act]
   float* state;          // [n, S]: read by the actor, overwritten with the next state
   float* returns;        // [n]
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(128) eval_step_kernel(const EvalStepParams p) 
   const int S = p.env.obs + (p.env.absorbing ? 1 : 0), act = p.env.act;
   int running = 0;
   if (e < p.n && !p.finished[e]) {
-    const float* a = p.action + (int64_t)e * act;
+    const float* a = p.action + ((int64_t)(e / p.act_E) * p.act_EP + e % p.act_E) * act;
     float* st = p.state + (int64_t)e * S;
     const int t = p.env.t[e];
     const bool rec = p.traj_states != nullptr && t < p.traj_T;
@@ -89,7 +90,17 @@ __global__ void __launch_bounds__(128) eval_step_kernel(const EvalStepParams p) 
   }
 }
 
-__global__ void eval_init_kernel(float* returns, int32_t* finished, int32_t* traj_len, EvalCounters* ctr, int n) {
+// rows [E, EP) of every replica's input block stay zero: they only pad the row count of the grouped GEMMs to the tile height of the tcgen05 engine
+__global__ void eval_pad_rows_kernel(const float* __restrict__ state, float* __restrict__ xpad, int R, int E, int EP, int S) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)R * E * S) return;
+  const int64_t row = i / S;
+  const int k = (int)(i % S);
+  xpad[((row / E) * EP + row % E) * S + k] = state[i];
+}
+
+__global__ void eval_init_kernel(float* returns, int32_t* finished, int32_t* traj_len, EvalCounters* ctr, int n, float* xpad, int64_t xpad_n) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < xpad_n; j += (int64_t)gridDim.x * blockDim.x) xpad[j] = 0.f;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     returns[i] = 0.f;
@@ -119,6 +130,7 @@ __global__ void return_stats3_kernel(const float* __restrict__ returns, int64_t 
 
 struct EvalGraph {
   il_eval_args key;
+  int ep;  // padded rows per replica the graph was built for (depends on the gemm mode of the handle)
   cudaGraph_t graph;
   cudaGraphExec_t exec;
 };
@@ -138,6 +150,15 @@ void il_eval_release(il_handle* h) {
 }
 
 // Builds  [reset] -> while (episodes running) { greedy actor forward ; env step + accumulate + loop condition }
+// Rows per replica of the greedy forward: the episode count, or — when the grouped GEMM program is used and the tensor-core engine is on and
+// applicable (256-wide hidden layers) — the next multiple of the 128-row tcgen05 tile.
+static int eval_padded_rows(const il_handle* h, const il_eval_args* a) {
+  const int E = a->episodes, L = a->actor.n_layers;
+  if (E <= EVAL_SMALL_MAX || h->gemm_mode == IL_GEMM_FP32 || L < 2) return E;
+  for (int l = 1; l < L; ++l)
+    if (a->actor.dims[l] != 256) return E;
+  return (E + 127) / 128 * 128;
+}
 static int eval_build_impl(il_handle* h, EvalGraph* eg, const il_eval_args* a, float* action, int32_t* finished, EvalCounters* ctr, char* ws, cudaStream_t st);
 // Capturing records kernel nodes without running anything, so it happens on a private stream (the caller's stream may be the legacy
 // default stream, which cannot capture); whatever goes wrong, that stream is taken out of capture mode again.
@@ -159,7 +180,12 @@ static int eval_build_impl(il_handle* h, EvalGraph* eg, const il_eval_args* a, f
   IL_CUDA(cudaGraphConditionalHandleCreate(&cond, eg->graph, 1, cudaGraphCondAssignDefault));
   // node 0: reset of returns / finished flags / counters, captured into the top-level graph
   IL_CUDA(cudaStreamBeginCaptureToGraph(st, eg->graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-  eval_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a->returns, finished, a->traj_len, ctr, n);
+  // E > 8 episodes per replica: the greedy forward is a grouped GEMM program; with the tensor-core engine on, the rows of every replica are padded to a
+  // multiple of 128 (zero rows) so that the 256-wide layers run on tcgen05 tiles instead of the fp32 FFMA engine (30 rows -> 128: 4x the MMA work, still
+  // ~3x faster than the FFMA path: the loop body is bound by streaming every replica's weights once per step)
+  const int EP = eval_padded_rows(h, a);
+  float* xpad = nullptr;
+  eval_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a->returns, finished, a->traj_len, ctr, n, EP != E ? reinterpret_cast<float*>(ws) : nullptr, EP != E ? (int64_t)R * EP * S : 0);
   h->launches++;
   cudaGraph_t captured = nullptr;
   IL_CUDA(cudaStreamEndCapture(st, &captured));
@@ -184,20 +210,29 @@ static int eval_build_impl(il_handle* h, EvalGraph* eg, const il_eval_args* a, f
     if (E <= EVAL_SMALL_MAX) {
       rc = mlp_small_forward(h, &a->actor, R, E, X, action, st, act);
     } else {
+      char* w1 = ws;
+      MatView Xin = X;
+      if (EP != E) {
+        xpad = reinterpret_cast<float*>(ws);
+        w1 = ws + il_align_up((int64_t)R * EP * S * 4, 256);
+        eval_pad_rows_kernel<<<(unsigned)(((int64_t)n * S + 255) / 256), 256, 0, st>>>(a->state, xpad, R, E, EP, S);
+        h->launches++;
+        Xin = MatView{xpad, (int64_t)EP * S, 1, S};
+      }
       MlpActs acts;
-      char* w2 = mlp_acts_carve(&a->actor, R, E, ws, &acts);
+      char* w2 = mlp_acts_carve(&a->actor, R, EP, w1, &acts);
       float* head = reinterpret_cast<float*>(w2);
-      rc = mlp_forward(h, &a->actor, R, E, X, acts, head, (int64_t)E * 2 * act, 2 * act, st, MLP_KEEP_NONE);
+      rc = mlp_forward(h, &a->actor, R, EP, Xin, acts, head, (int64_t)EP * 2 * act, 2 * act, st, MLP_KEEP_NONE);
       if (rc == 0) {
         HeadFwdArgs ha{};
-        ha.head = head; ha.action = action; ha.action_rs = (int64_t)E * act; ha.ld_action = act; ha.R = R; ha.n = E; ha.A = act;
+        ha.head = head; ha.action = action; ha.action_rs = (int64_t)EP * act; ha.ld_action = act; ha.R = R; ha.n = EP; ha.A = act;
         rc = launch_actor_head(h, ha, st);
       }
     }
   }
   if (rc == 0) {
     EvalStepParams sp{};
-    sp.env = a->env; sp.n = n; sp.action = action; sp.state = a->state; sp.returns = a->returns; sp.finished = finished; sp.ctr = ctr; sp.cond = cond;
+    sp.env = a->env; sp.n = n; sp.act_E = E; sp.act_EP = (E > EVAL_SMALL_MAX) ? EP : E; sp.action = action; sp.state = a->state; sp.returns = a->returns; sp.finished = finished; sp.ctr = ctr; sp.cond = cond;
     sp.max_iterations = a->max_steps;
     sp.traj_states = a->traj_states; sp.traj_actions = a->traj_actions; sp.traj_rewards = a->traj_rewards; sp.traj_len = a->traj_len; sp.traj_T = a->traj_T;
     eval_step_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(sp);
@@ -216,8 +251,11 @@ extern "C" int64_t il_eval_workspace_bytes(const il_eval_args* a) {
   const int64_t n = (int64_t)a->R * a->episodes;
   const int act = a->env.act;
   // action [n, act] | finished [n] | counters | (episodes > 32: per-layer activations + head of the general MLP path)
-  int64_t b = il_align_up(n * act * 4, 256) + il_align_up(n * 4, 256) + 256;
-  if (a->episodes > EVAL_SMALL_MAX) b += mlp_acts_bytes(&a->actor, a->R, a->episodes) + il_align_up(n * a->actor.dims[a->actor.n_layers] * 4, 256);
+  // worst case over the gemm modes: rows padded to 128 per replica (tensor-core path)
+  const int64_t EP = (a->episodes + 127) / 128 * 128, np = (int64_t)a->R * EP;
+  int64_t b = il_align_up(np * act * 4, 256) + il_align_up(n * 4, 256) + 256;
+  if (a->episodes > EVAL_SMALL_MAX)
+    b += il_align_up(np * a->actor.dims[0] * 4, 256) + mlp_acts_bytes(&a->actor, a->R, (int)EP) + il_align_up(np * a->actor.dims[a->actor.n_layers] * 4, 256);
   return b;
 }
 
@@ -236,19 +274,19 @@ extern "C" int il_eval_rollout(il_handle* h, const il_eval_args* a, void* stream
   IL_CHECK(cs == cudaStreamCaptureStatusNone, "il_eval_rollout: cannot run inside a stream capture (a graph with a conditional node cannot be a child graph)");
   const int n = R * E;
   char* ws = static_cast<char*>(a->workspace);
-  float* action = reinterpret_cast<float*>(ws); ws += il_align_up((int64_t)n * act * 4, 256);
+  float* action = reinterpret_cast<float*>(ws); ws += il_align_up((int64_t)R * ((E + 127) / 128 * 128) * act * 4, 256);  // sized for the padded layout (il_eval_workspace_bytes)
   int32_t* finished = reinterpret_cast<int32_t*>(ws); ws += il_align_up((int64_t)n * 4, 256);
   EvalCounters* ctr = reinterpret_cast<EvalCounters*>(ws); ws += 256;
 
   EvalGraph* eg = static_cast<EvalGraph*>(h->eval_graph);
-  if (eg && memcmp(&eg->key, a, sizeof(il_eval_args)) != 0) {  // different buffers / shapes: rebuild (the old graph may still be running on this stream)
+  if (eg && (memcmp(&eg->key, a, sizeof(il_eval_args)) != 0 || eg->ep != eval_padded_rows(h, a))) {  // different buffers / shapes: rebuild (the old graph may still be running on this stream)
     IL_CUDA(cudaStreamSynchronize(st));
     il_eval_release(h);
     eg = nullptr;
   }
   if (!eg) {
     eg = new EvalGraph();
-    eg->key = *a; eg->graph = nullptr; eg->exec = nullptr;
+    eg->key = *a; eg->graph = nullptr; eg->exec = nullptr; eg->ep = eval_padded_rows(h, a);
     h->eval_graph = eg;
     const int rc = eval_build(h, eg, a, action, finished, ctr, ws);
     if (rc != 0) { il_eval_release(h); return rc; }

@@ -581,43 +581,54 @@ constexpr int ADAM_TMA_MIN_TILES = 4096;        // floats per CTA-iteration belo
 //   db_{L-1}[o] = sum_b dZ[b, o]                                        (was: column-sum kernel, reads dZ again)
 // One CTA per (net, 256 hidden columns) streams Y once and writes dZ once; thread = 4 columns x every 4th row, W_L columns in registers,
 // cross-row-group reduction through shared memory in a fixed order (deterministic).
+template <int NH>  // compile-time bound on the head width (1: critic, HB_MAXN: actor) — the weight / gradient register tiles and the FMA count scale with it
 __global__ void __launch_bounds__(256, 2) head_backward_kernel(const HeadBwdArgs p) {
   extern __shared__ __align__(16) float hb_sm[];   // dOut [n][HB_MAXN] (zero padded), then the reduction scratch [4][HB_MAXN * 4 + 4][64]
   const int g = blockIdx.y, n0 = blockIdx.x * 256, tid = threadIdx.x, tc = tid & 63, tr = tid >> 6, col = n0 + tc * 4;
   float* dos = hb_sm;
   float* red = hb_sm + p.n * HB_MAXN;
   const float* dout = p.dout + (int64_t)(g / p.dout_gdiv) * p.dout_gs;
+  const bool active = col < p.H;
+  const float* Y = p.y + (int64_t)g * p.y_gs + col;
+  float4 yv[4], yn[4];
+  auto fetch = [&](float4 (&dst)[4], int b0) {  // rows b0, b0 + 4, b0 + 8, b0 + 12
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int b = b0 + 4 * u;
+      dst[u] = (active && b < p.n) ? __ldg(reinterpret_cast<const float4*>(Y + (int64_t)b * p.H)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  fetch(yv, tr);  // in flight while dOut is staged
   for (int i = tid; i < p.n * HB_MAXN; i += 256) {
     const int b = i / HB_MAXN, j = i % HB_MAXN;
     dos[i] = j < p.Nh ? __ldg(dout + (int64_t)b * p.ld_dout + j) : 0.f;
   }
-  const bool active = col < p.H;
-  float4 w[HB_MAXN];
+  float4 w[NH];
 #pragma unroll
-  for (int j = 0; j < HB_MAXN; ++j) w[j] = (active && j < p.Nh) ? __ldg(reinterpret_cast<const float4*>(p.w + (int64_t)g * p.w_gs + (int64_t)j * p.H + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < NH; ++j) w[j] = (active && j < p.Nh) ? __ldg(reinterpret_cast<const float4*>(p.w + (int64_t)g * p.w_gs + (int64_t)j * p.H + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  float4 dw[HB_MAXN], cs = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 dw[NH], cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int j = 0; j < HB_MAXN; ++j) dw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < NH; ++j) dw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (active) {
-    const float* Y = p.y + (int64_t)g * p.y_gs + col;
     float* DZ = p.dz + (int64_t)g * p.dz_gs + col;
-    for (int b0 = tr; b0 < p.n; b0 += 16) {  // 4 rows (b0, b0 + 4, b0 + 8, b0 + 12) in flight
-      float4 yv[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int b = b0 + 4 * u;
-        yv[u] = b < p.n ? __ldg(reinterpret_cast<const float4*>(Y + (int64_t)b * p.H)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+    for (int b0 = tr; b0 < p.n; b0 += 16) {
+      fetch(yn, b0 + 16);  // the next 4 rows are in flight while these 4 are consumed
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int b = b0 + 4 * u;
         if (b >= p.n) continue;
-        const float4 d0 = *reinterpret_cast<const float4*>(dos + b * HB_MAXN), d1 = *reinterpret_cast<const float4*>(dos + b * HB_MAXN + 4);
-        const float dj[HB_MAXN] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        float dj[NH];
+        if (NH == 1) dj[0] = dos[b * HB_MAXN];
+        else {
+          const float4 d0 = *reinterpret_cast<const float4*>(dos + b * HB_MAXN), d1 = *reinterpret_cast<const float4*>(dos + b * HB_MAXN + 4);
+          const float t[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+          for (int j = 0; j < NH; ++j) dj[j] = t[j];
+        }
         float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < HB_MAXN; ++j) {
+        for (int j = 0; j < NH; ++j) {
           z.x = fmaf(dj[j], w[j].x, z.x); z.y = fmaf(dj[j], w[j].y, z.y); z.z = fmaf(dj[j], w[j].z, z.z); z.w = fmaf(dj[j], w[j].w, z.w);
           dw[j].x = fmaf(dj[j], yv[u].x, dw[j].x); dw[j].y = fmaf(dj[j], yv[u].y, dw[j].y); dw[j].z = fmaf(dj[j], yv[u].z, dw[j].z); dw[j].w = fmaf(dj[j], yv[u].w, dw[j].w);
         }
@@ -625,18 +636,20 @@ __global__ void __launch_bounds__(256, 2) head_backward_kernel(const HeadBwdArgs
         cs.x += z.x; cs.y += z.y; cs.z += z.z; cs.w += z.w;
         *reinterpret_cast<float4*>(DZ + (int64_t)b * p.H) = z;
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) yv[u] = yn[u];
     }
   }
   // reduce the 4 row groups: red[tr][slot][tc] (slot = j for dW_L rows, HB_MAXN for the column sum), float4 per entry
   float4* r4 = reinterpret_cast<float4*>(red);
 #pragma unroll
-  for (int j = 0; j < HB_MAXN; ++j) r4[(tr * (HB_MAXN + 1) + j) * 64 + tc] = dw[j];
+  for (int j = 0; j < NH; ++j) r4[(tr * (HB_MAXN + 1) + j) * 64 + tc] = dw[j];
   r4[(tr * (HB_MAXN + 1) + HB_MAXN) * 64 + tc] = cs;
   __syncthreads();
   if (tr == 0 && active) {
 #pragma unroll
     for (int j = 0; j <= HB_MAXN; ++j) {
-      if (j < p.Nh || j == HB_MAXN) {
+      if ((j < NH && j < p.Nh) || j == HB_MAXN) {
         float4 a = r4[(0 * (HB_MAXN + 1) + j) * 64 + tc];
 #pragma unroll
         for (int q = 1; q < 4; ++q) {
@@ -775,12 +788,14 @@ int launch_head_dx_bits(il_handle* h, const HeadBwdArgs& a, const uint32_t* bits
 
 int launch_head_backward(il_handle* h, const HeadBwdArgs& a, int G, cudaStream_t stream) {
   const size_t smem = ((size_t)a.n * HB_MAXN + 4 * (HB_MAXN + 1) * 64 * 4) * sizeof(float);
-  IL_LAUNCH(h, head_backward_kernel, dim3((a.H + 255) / 256, G), 256, smem, stream, a);
+  if (a.Nh == 1) IL_LAUNCH(h, head_backward_kernel<1>, dim3((a.H + 255) / 256, G), 256, smem, stream, a);
+  else IL_LAUNCH(h, head_backward_kernel<HB_MAXN>, dim3((a.H + 255) / 256, G), 256, smem, stream, a);
   return 0;
 }
 
 int mlp_init() {
-  IL_CUDA(cudaFuncSetAttribute(head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1024 * HB_MAXN + 4 * (HB_MAXN + 1) * 64 * 4) * 4));
+  IL_CUDA(cudaFuncSetAttribute(head_backward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1024 * HB_MAXN + 4 * (HB_MAXN + 1) * 64 * 4) * 4));
+  IL_CUDA(cudaFuncSetAttribute(head_backward_kernel<HB_MAXN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1024 * HB_MAXN + 4 * (HB_MAXN + 1) * 64 * 4) * 4));
   return 0;
 }
 

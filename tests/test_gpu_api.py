@@ -274,6 +274,31 @@ def test_evaluate_agent_many_episodes_uses_the_general_mlp_path():
   np.testing.assert_allclose(big.cpu().numpy(), small.cpu().numpy(), rtol=1e-4, atol=1e-4)
 
 
+def test_evaluate_agent_on_the_tensor_core_engine_pads_rows_and_matches_fp32():
+  """30 episodes per replica with 256-wide nets and gemm_mode tf32x3 (train.py:213 at the benchmarked configuration): the greedy forward pads every
+  replica's rows to the 128-row tcgen05 tile (zero rows, ignored) — same returns as the fp32 FFMA engine, which runs the 30 rows unpadded."""
+  import il_b200
+  from il_b200 import _lib
+  from il_b200.environments import D4RLEnv
+  from il_b200.evaluation import evaluate_agent
+  R, E = 3, 30
+  cfg = type(MODEL)(hidden_size=256, depth=2, activation='relu')
+  actor = il_b200.SoftActor(12, 3, cfg, replicas=R)
+  u = np.random.RandomState(11).uniform(size=(R * E, 11)).astype(np.float32)
+  lib, h = _lib.lib(), _lib.handle()
+  out = {}
+  for mode in ('fp32', 'tf32x3'):
+    _lib.check(lib.il_set_gemm_mode(h, _lib.GEMM_MODE[mode]))
+    try:
+      env = D4RLEnv('hopper', True, replicas=R, max_episode_steps=60)
+      stats = {}
+      out[mode] = (evaluate_agent(actor, env, E, reset_noise=torch.from_numpy(u), out_stats=stats).cpu().numpy(), dict(stats))
+    finally:
+      _lib.check(lib.il_set_gemm_mode(h, _lib.GEMM_MODE['fp32']))
+  np.testing.assert_allclose(out['tf32x3'][0], out['fp32'][0], rtol=2e-3, atol=2e-3)
+  assert out['tf32x3'][1] == out['fp32'][1]  # same loop length and environment-step count: the padded rows are not episodes
+
+
 def test_return_allreduce_single_process_matches_torch():
   from il_b200 import distributed
   r = torch.randn(7, 30, device='cuda') * 10
